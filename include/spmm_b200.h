@@ -1,0 +1,141 @@
+/*
+ * spmm_b200.h — C-ABI of the B200-native sparse-matrix x fat-vector path.
+ *
+ * Drop-in boundary for AlexisBalayre/SparseMatrixMultiplicationMPI's one hot
+ * path (C = A*B, A CSR FP64/int32, B dense N x k FP64). Plain pointers and
+ * sizes only; every function returns an spmm_status and records a message
+ * readable through spmm_last_error() (thread-local). No function falls back
+ * to the CPU: without a CUDA device they fail with SPMM_ERR_CUDA.
+ *
+ * Each entry cites the reference interface it replaces; paths are relative to
+ * /root/reference/"Source Code"/. Dense operands are flat row-major, the
+ * layout of the reference's serialize() (utils.cpp:216-228). "d_" arguments
+ * are device pointers on the handle's device; all others are host pointers.
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ */
+#ifndef SPMM_B200_H
+#define SPMM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct spmm_csr_s *spmm_csr_t; /* device-resident SparseMatrix (MatrixDefinitions.h:14-19) */
+
+enum spmm_status
+{
+    SPMM_OK = 0,
+    SPMM_ERR_INVALID = 1,     /* bad argument (the reference checks nothing; we do) */
+    SPMM_ERR_CUDA = 2,        /* CUDA runtime error or no device */
+    SPMM_ERR_NOMEM = 3,
+    SPMM_ERR_UNSUPPORTED = 4
+};
+
+/* Kernel families. AUTO picks from the handle's row-length schedule. */
+enum spmm_kernel
+{
+    SPMM_KERNEL_AUTO = 0,
+    SPMM_KERNEL_ROWS = 1,  /* (sub-)warp-per-row teams over contiguous row chunks */
+    SPMM_KERNEL_MERGE = 2  /* nnz-balanced merge-path with deterministic carry fix-up */
+};
+
+const char *spmm_last_error(void);
+int spmm_version(void);
+int spmm_device_count(int *count);
+/* multiProcessorCount, L2 bytes, total global memory of `device` */
+int spmm_device_info(int device, int *sm_count, long long *l2_bytes, long long *hbm_bytes);
+
+/* ---- a1: SparseMatrix in HBM ------------------------------------------------------ */
+
+/* Upload a host CSR (the SparseMatrix fields values/colIndices/rowPtr + numRows/numCols,
+ * MatrixDefinitions.h:14-19, utils.cpp:180-181) to `device` and build its row-length
+ * schedule. Arrays are copied bit-for-bit; the host arrays are not retained. */
+int spmm_csr_create_host(int device, int n_rows, int n_cols, long long nnz,
+                         const int *rowptr, const int *colidx, const double *vals,
+                         spmm_csr_t *out);
+
+/* Same from arrays already on `device`. copy=0 borrows them (caller keeps them alive). */
+int spmm_csr_create_device(int device, int n_rows, int n_cols, long long nnz,
+                           const int *d_rowptr, const int *d_colidx, const double *d_vals,
+                           int copy, spmm_csr_t *out);
+
+/* a7: the CSR assembly of readMatrixMarketFile (utils.cpp:124-181) on the device.
+ * Input = the file's coordinate records in file order, 0-based. Semantics reproduced
+ * bit-exactly: symmetric!=0 mirrors off-diagonal records (:146-152), each row is ordered
+ * by (column, value) ascending (:156-159), duplicates are kept, rowPtr is the prefix sum
+ * (:162-179). *_host copies the records up first; *_device reads device arrays. */
+int spmm_csr_from_coo_host(int device, int n_rows, int n_cols, long long n_entries,
+                           const int *rows, const int *cols, const double *vals,
+                           int symmetric, spmm_csr_t *out);
+int spmm_csr_from_coo_device(int device, int n_rows, int n_cols, long long n_entries,
+                             const int *d_rows, const int *d_cols, const double *d_vals,
+                             int symmetric, spmm_csr_t *out);
+
+int spmm_csr_destroy(spmm_csr_t A);
+int spmm_csr_info(spmm_csr_t A, int *n_rows, int *n_cols, long long *nnz, int *device);
+int spmm_csr_device_ptrs(spmm_csr_t A, const int **d_rowptr, const int **d_colidx, const double **d_vals);
+/* Copy the device CSR back (rowptr n_rows+1, colidx nnz, vals nnz) for memcmp-style checks. */
+int spmm_csr_download(spmm_csr_t A, int *rowptr, int *colidx, double *vals);
+/* Row-length schedule: bins[0..7] = rows with length 0, 1-2, 3-4, 5-8, 9-16, 17-32, 33-256, >256. */
+int spmm_csr_schedule(spmm_csr_t A, long long bins[8], int *max_row_len, double *mean_row_len,
+                      int *auto_kernel);
+/* Sub-matrix A[:, col_begin:col_end) with local column ids (column-block strategy,
+ * north_star reading of sparseMatrixFatVectorMultiplyColumnWise). Built on the device. */
+int spmm_csr_column_block(spmm_csr_t A, int col_begin, int col_end, spmm_csr_t *out);
+
+/* ---- a3: sparseMatrixFatVectorMultiply (SparseMatrixFatVectorMultiply.cpp:11-31) ---- */
+
+/* C[n_rows x k] = A * B[n_cols x k], everything resident on the device. */
+int spmm_multiply_device(spmm_csr_t A, const double *d_B, int k, double *d_C, int kernel, void *stream);
+
+/* Strided form: B has leading dimension ldb, C has ldc; columns [k_begin, k_begin+k_count)
+ * of B/C are computed (the k-slab split of ColumnWise.cpp:25-48). */
+int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, double *d_C, int ldc,
+                                 int k_begin, int k_count, int kernel, void *stream);
+
+/* Host-buffer form, the call the C++ entry points make: copies B up through pinned
+ * staging, multiplies, copies C back. B: n_cols*k doubles, C: n_rows*k doubles. */
+int spmm_multiply_host(spmm_csr_t A, const double *B, int k, double *C, int kernel);
+
+/* ---- a4: row block [row_begin,row_end) (RowWise.cpp:26-50). d_C_local holds
+ * (row_end-row_begin) x k, i.e. the rank's localResult before the Gatherv. ---- */
+int spmm_multiply_rows_device(spmm_csr_t A, int row_begin, int row_end, const double *d_B, int k,
+                              double *d_C_local, int kernel, void *stream);
+
+/* ---- a6: non-zero range [nnz_begin,nnz_end) (NonZeroElement.cpp:24-67).
+ * Rows touched by the range are first_row..last_row; d_C_local holds
+ * (last_row-first_row+1) x k and receives, for each of those rows, the sum over
+ * the range's elements only (boundary rows are therefore partial sums, to be
+ * combined across ranks in rank order). Rows strictly inside get their full value;
+ * empty rows inside get zeros. ---- */
+int spmm_nnz_range_rows(spmm_csr_t A, long long nnz_begin, long long nnz_end, int *first_row, int *last_row);
+int spmm_multiply_nnz_range_device(spmm_csr_t A, long long nnz_begin, long long nnz_end,
+                                   const double *d_B, int k, double *d_C_local, void *stream);
+
+/* ---- partition formulas (bit-for-bit the reference's integer arithmetic) ---- */
+void spmm_partition_rows(int n_rows, int n_ranks, int rank, int *begin, int *end);           /* RowWise.cpp:26-29 */
+void spmm_partition_cols(int k, int n_ranks, int rank, int *begin, int *end);                /* ColumnWise.cpp:25-28 */
+void spmm_partition_nnz(long long nnz, int n_ranks, int rank, long long *begin, long long *end); /* NonZeroElement.cpp:24-39 */
+
+/* ---- a8: host utilities ---- */
+/* generateLargeFatVector (utils.cpp:193-209): rand()%100+1 from the never-seeded libc state. */
+void spmm_generate_fat_vector(int n, int k, double *out);
+/* areMatricesEqual (utils.cpp:38-63): 1 when every |a-b| <= tol. */
+int spmm_are_equal(const double *a, const double *b, long long n, double tol);
+
+/* ---- synthetic workloads generated in HBM (bench / large parity cases) ---- */
+/* Banded: every row has nnz_per_row distinct ascending columns inside a window of
+ * 2*half_bandwidth+1 columns around the diagonal; values in [0.5,1.5). */
+int spmm_gen_banded(int device, int n, int nnz_per_row, int half_bandwidth, unsigned long long seed,
+                    spmm_csr_t *out);
+/* R-MAT (a,b,c,d) edge list of n_edges over 2^scale vertices, duplicates kept, built
+ * into CSR by the device CSR build. */
+int spmm_gen_rmat(int device, int scale, long long n_edges, double a, double b, double c,
+                  unsigned long long seed, spmm_csr_t *out);
+/* Dense fill with integers 1..100 (the value range of generateLargeFatVector). */
+int spmm_gen_fat_vector_device(int device, double *d_out, long long n_elems, unsigned long long seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

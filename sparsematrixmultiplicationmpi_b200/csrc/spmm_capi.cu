@@ -1,0 +1,473 @@
+// spmm_capi.cu — the extern "C" boundary declared in include/spmm_b200.h.
+//
+// Thin by design: argument checks, device memory, the row-length schedule and
+// kernel selection. All arithmetic of the path lives in the CUDA kernels
+// (spmm_rows.cu, spmm_merge.cu, csr_build.cu); nothing here computes on the host.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "spmm_internal.h"
+
+namespace spmm
+{
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    const char *base = std::strrchr(file, '/');
+    g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" +
+                   (base ? base + 1 : file) + ":" + std::to_string(line) + ")";
+    return e == cudaErrorMemoryAllocation ? SPMM_ERR_NOMEM : SPMM_ERR_CUDA;
+}
+
+Tuning &tuning()
+{
+    static Tuning t;
+    return t;
+}
+
+const DeviceProps &device_props(int device)
+{
+    static std::mutex mu;
+    static std::map<int, DeviceProps> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(device);
+    if (it != cache.end())
+        return it->second;
+    DeviceProps p;
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess)
+        p.sm_count = v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, device) == cudaSuccess)
+        p.l2_bytes = v;
+    if (p.sm_count <= 0)
+        p.sm_count = 148;
+    return cache[device] = p;
+}
+
+// ---- row-length schedule ----------------------------------------------------------
+__global__ void schedule_kernel(const int *__restrict__ rowptr, int n_rows, unsigned long long *bins, int *max_len)
+{
+    __shared__ unsigned int s_bins[8];
+    __shared__ int s_max;
+    if (threadIdx.x < 8)
+        s_bins[threadIdx.x] = 0;
+    if (threadIdx.x == 0)
+        s_max = 0;
+    __syncthreads();
+    int local_max = 0;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows;
+         r += (long long)gridDim.x * blockDim.x)
+    {
+        const int len = rowptr[r + 1] - rowptr[r];
+        local_max = max(local_max, len);
+        int b;
+        if (len == 0) b = 0;
+        else if (len <= 2) b = 1;
+        else if (len <= 4) b = 2;
+        else if (len <= 8) b = 3;
+        else if (len <= 16) b = 4;
+        else if (len <= 32) b = 5;
+        else if (len <= 256) b = 6;
+        else b = 7;
+        atomicAdd(&s_bins[b], 1u);
+    }
+    atomicMax(&s_max, local_max);
+    __syncthreads();
+    if (threadIdx.x < 8 && s_bins[threadIdx.x])
+        atomicAdd(&bins[threadIdx.x], (unsigned long long)s_bins[threadIdx.x]);
+    if (threadIdx.x == 0)
+        atomicMax(max_len, s_max);
+}
+
+int build_schedule(spmm_csr_s *A, cudaStream_t stream)
+{
+    Schedule s;
+    if (A->n_rows > 0)
+    {
+        unsigned long long *d_bins = nullptr;
+        SPMM_CUDA(cudaMalloc(&d_bins, 9 * sizeof(unsigned long long)));
+        SPMM_CUDA(cudaMemsetAsync(d_bins, 0, 9 * sizeof(unsigned long long), stream));
+        const int threads = 256;
+        const int blocks = (int)std::min<long long>(((long long)A->n_rows + threads - 1) / threads,
+                                                    (long long)device_props(A->device).sm_count * 8);
+        schedule_kernel<<<blocks, threads, 0, stream>>>(A->d_rowptr, A->n_rows, d_bins, (int *)(d_bins + 8));
+        unsigned long long h[9];
+        cudaError_t e = cudaMemcpyAsync(h, d_bins, sizeof h, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(stream);
+        cudaFree(d_bins);
+        SPMM_CUDA(e);
+        for (int i = 0; i < 8; ++i)
+            s.bins[i] = (long long)h[i];
+        s.max_len = (int)(h[8] & 0xffffffffu);
+        s.mean_len = (double)A->nnz / (double)A->n_rows;
+    }
+    // Power-law rows: one row far longer than an equal-cost chunk would make the
+    // row-chunk kernel serialise on it -> nnz-balanced merge-path instead.
+    const double chunk = (double)A->nnz / (double)(device_props(A->device).sm_count * 8) + 1.0;
+    s.auto_kernel = (s.max_len > 4096 && (double)s.max_len > 0.25 * chunk) ? SPMM_KERNEL_MERGE : SPMM_KERNEL_ROWS;
+    A->sched = s;
+    return SPMM_OK;
+}
+
+static int make_handle(int device, int n_rows, int n_cols, long long nnz, spmm_csr_s **out)
+{
+    SPMM_REQUIRE(out != nullptr, "out handle is NULL");
+    SPMM_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0, "negative size");
+    SPMM_REQUIRE(nnz <= 2147483647LL, "nnz exceeds the int32 rowPtr of the reference data model");
+    int count = 0;
+    SPMM_CUDA(cudaGetDeviceCount(&count));
+    SPMM_REQUIRE(device >= 0 && device < count, "no such CUDA device");
+    SPMM_CUDA(cudaSetDevice(device));
+    spmm_csr_s *A = new spmm_csr_s();
+    A->device = device;
+    A->n_rows = n_rows;
+    A->n_cols = n_cols;
+    A->nnz = nnz;
+    *out = A;
+    return SPMM_OK;
+}
+
+static int alloc_arrays(spmm_csr_s *A)
+{
+    SPMM_CUDA(cudaMalloc(&A->d_rowptr, sizeof(int) * ((size_t)A->n_rows + 1)));
+    SPMM_CUDA(cudaMalloc(&A->d_colidx, sizeof(int) * (size_t)std::max<long long>(A->nnz, 1)));
+    SPMM_CUDA(cudaMalloc(&A->d_vals, sizeof(double) * (size_t)std::max<long long>(A->nnz, 1)));
+    A->owns = true;
+    return SPMM_OK;
+}
+
+static int select_kernel(const spmm_csr_s *A, int kernel)
+{
+    if (kernel == SPMM_KERNEL_AUTO)
+        return A->sched.auto_kernel;
+    return kernel;
+}
+
+} // namespace spmm
+
+using namespace spmm;
+
+extern "C"
+{
+
+const char *spmm_last_error(void) { return g_last_error.c_str(); }
+int spmm_version(void) { return 100; }
+
+int spmm_device_count(int *count)
+{
+    SPMM_REQUIRE(count != nullptr, "count is NULL");
+    SPMM_CUDA(cudaGetDeviceCount(count));
+    return SPMM_OK;
+}
+
+int spmm_device_info(int device, int *sm_count, long long *l2_bytes, long long *hbm_bytes)
+{
+    cudaDeviceProp p;
+    SPMM_CUDA(cudaGetDeviceProperties(&p, device));
+    if (sm_count)
+        *sm_count = p.multiProcessorCount;
+    if (l2_bytes)
+        *l2_bytes = p.l2CacheSize;
+    if (hbm_bytes)
+        *hbm_bytes = (long long)p.totalGlobalMem;
+    return SPMM_OK;
+}
+
+// experiment knob, not part of the stable ABI header
+int spmm_tune_set(const char *key, int value)
+{
+    Tuning &t = tuning();
+    std::string k = key ? key : "";
+    if (k == "rows.np") t.rows_np = value;
+    else if (k == "rows.unroll") t.rows_unroll = value;
+    else if (k == "rows.vec") t.rows_vec = value;
+    else if (k == "rows.ctas_per_sm") t.rows_ctas_per_sm = value;
+    else if (k == "merge.items") t.merge_items = value;
+    else if (k == "reset") t = Tuning();
+    else
+    {
+        set_error("unknown tuning key: " + k);
+        return SPMM_ERR_INVALID;
+    }
+    return SPMM_OK;
+}
+
+int spmm_csr_create_host(int device, int n_rows, int n_cols, long long nnz, const int *rowptr, const int *colidx,
+                         const double *vals, spmm_csr_t *out)
+{
+    SPMM_REQUIRE(rowptr != nullptr, "rowptr is NULL");
+    SPMM_REQUIRE(nnz == 0 || (colidx && vals), "colidx/vals are NULL");
+    SPMM_REQUIRE(rowptr[0] == 0 && rowptr[n_rows] == nnz, "rowptr[0] must be 0 and rowptr[n_rows] must equal nnz");
+    spmm_csr_s *A = nullptr;
+    int rc = make_handle(device, n_rows, n_cols, nnz, &A);
+    if (rc)
+        return rc;
+    rc = alloc_arrays(A);
+    if (!rc)
+    {
+        cudaError_t e = cudaMemcpy(A->d_rowptr, rowptr, sizeof(int) * ((size_t)n_rows + 1), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && nnz)
+            e = cudaMemcpy(A->d_colidx, colidx, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && nnz)
+            e = cudaMemcpy(A->d_vals, vals, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess)
+            rc = cuda_fail(e, "cudaMemcpy(H2D CSR)", __FILE__, __LINE__);
+    }
+    if (!rc)
+        rc = build_schedule(A, nullptr);
+    if (rc)
+    {
+        spmm_csr_destroy(A);
+        return rc;
+    }
+    *out = A;
+    return SPMM_OK;
+}
+
+int spmm_csr_create_device(int device, int n_rows, int n_cols, long long nnz, const int *d_rowptr,
+                           const int *d_colidx, const double *d_vals, int copy, spmm_csr_t *out)
+{
+    SPMM_REQUIRE(d_rowptr != nullptr, "d_rowptr is NULL");
+    SPMM_REQUIRE(nnz == 0 || (d_colidx && d_vals), "d_colidx/d_vals are NULL");
+    spmm_csr_s *A = nullptr;
+    int rc = make_handle(device, n_rows, n_cols, nnz, &A);
+    if (rc)
+        return rc;
+    if (copy)
+    {
+        rc = alloc_arrays(A);
+        if (!rc)
+        {
+            cudaError_t e = cudaMemcpy(A->d_rowptr, d_rowptr, sizeof(int) * ((size_t)n_rows + 1), cudaMemcpyDeviceToDevice);
+            if (e == cudaSuccess && nnz)
+                e = cudaMemcpy(A->d_colidx, d_colidx, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToDevice);
+            if (e == cudaSuccess && nnz)
+                e = cudaMemcpy(A->d_vals, d_vals, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToDevice);
+            if (e != cudaSuccess)
+                rc = cuda_fail(e, "cudaMemcpy(D2D CSR)", __FILE__, __LINE__);
+        }
+    }
+    else
+    {
+        A->d_rowptr = const_cast<int *>(d_rowptr);
+        A->d_colidx = const_cast<int *>(d_colidx);
+        A->d_vals = const_cast<double *>(d_vals);
+        A->owns = false;
+    }
+    if (!rc)
+        rc = build_schedule(A, nullptr);
+    if (rc)
+    {
+        spmm_csr_destroy(A);
+        return rc;
+    }
+    *out = A;
+    return SPMM_OK;
+}
+
+int spmm_csr_destroy(spmm_csr_t A)
+{
+    if (!A)
+        return SPMM_OK;
+    cudaSetDevice(A->device);
+    if (A->owns)
+    {
+        cudaFree(A->d_rowptr);
+        cudaFree(A->d_colidx);
+        cudaFree(A->d_vals);
+    }
+    cudaFree(A->d_B);
+    cudaFree(A->d_C);
+    cudaFree(A->d_carry);
+    cudaFree(A->d_carry_row);
+    if (A->h_stage)
+        cudaFreeHost(A->h_stage);
+    if (A->stream)
+        cudaStreamDestroy(A->stream);
+    delete A;
+    return SPMM_OK;
+}
+
+int spmm_csr_info(spmm_csr_t A, int *n_rows, int *n_cols, long long *nnz, int *device)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    if (n_rows) *n_rows = A->n_rows;
+    if (n_cols) *n_cols = A->n_cols;
+    if (nnz) *nnz = A->nnz;
+    if (device) *device = A->device;
+    return SPMM_OK;
+}
+
+int spmm_csr_device_ptrs(spmm_csr_t A, const int **d_rowptr, const int **d_colidx, const double **d_vals)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    if (d_rowptr) *d_rowptr = A->d_rowptr;
+    if (d_colidx) *d_colidx = A->d_colidx;
+    if (d_vals) *d_vals = A->d_vals;
+    return SPMM_OK;
+}
+
+int spmm_csr_download(spmm_csr_t A, int *rowptr, int *colidx, double *vals)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_CUDA(cudaSetDevice(A->device));
+    if (rowptr)
+        SPMM_CUDA(cudaMemcpy(rowptr, A->d_rowptr, sizeof(int) * ((size_t)A->n_rows + 1), cudaMemcpyDeviceToHost));
+    if (colidx && A->nnz)
+        SPMM_CUDA(cudaMemcpy(colidx, A->d_colidx, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToHost));
+    if (vals && A->nnz)
+        SPMM_CUDA(cudaMemcpy(vals, A->d_vals, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToHost));
+    return SPMM_OK;
+}
+
+int spmm_csr_schedule(spmm_csr_t A, long long bins[8], int *max_row_len, double *mean_row_len, int *auto_kernel)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    if (bins)
+        for (int i = 0; i < 8; ++i)
+            bins[i] = A->sched.bins[i];
+    if (max_row_len) *max_row_len = A->sched.max_len;
+    if (mean_row_len) *mean_row_len = A->sched.mean_len;
+    if (auto_kernel) *auto_kernel = A->sched.auto_kernel;
+    return SPMM_OK;
+}
+
+// ---- multiply ---------------------------------------------------------------------
+
+int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, double *d_C, int ldc, int k_begin,
+                                 int k_count, int kernel, void *stream)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(k_begin >= 0 && k_count >= 0, "negative column range");
+    SPMM_REQUIRE(ldb >= k_begin + k_count && ldc >= k_begin + k_count, "leading dimension smaller than column range");
+    if (A->n_rows == 0 || k_count == 0)
+        return SPMM_OK;
+    SPMM_REQUIRE(d_C != nullptr, "d_C is NULL");
+    SPMM_REQUIRE(d_B != nullptr || A->nnz == 0, "d_B is NULL");
+    SPMM_CUDA(cudaSetDevice(A->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)
+        return launch_merge(A, 0, A->nnz, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, false, s);
+    return launch_rows(A, 0, A->n_rows, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
+}
+
+int spmm_multiply_device(spmm_csr_t A, const double *d_B, int k, double *d_C, int kernel, void *stream)
+{
+    SPMM_REQUIRE(k >= 0, "k is negative");
+    return spmm_multiply_strided_device(A, d_B, k, d_C, k, 0, k, kernel, stream);
+}
+
+int spmm_multiply_rows_device(spmm_csr_t A, int row_begin, int row_end, const double *d_B, int k,
+                              double *d_C_local, int kernel, void *stream)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(k >= 0, "k is negative");
+    SPMM_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= A->n_rows, "row range outside the matrix");
+    if (row_begin == row_end || k == 0)
+        return SPMM_OK;
+    SPMM_REQUIRE(d_C_local != nullptr, "d_C_local is NULL");
+    SPMM_CUDA(cudaSetDevice(A->device));
+    (void)kernel; // a row block always runs the row-chunk kernel
+    return launch_rows(A, row_begin, row_end, row_begin, d_B, k, d_C_local, k, k, (cudaStream_t)stream);
+}
+
+int spmm_multiply_host(spmm_csr_t A, const double *B, int k, double *C, int kernel)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(k >= 0, "k is negative");
+    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)A->n_rows * (size_t)k;
+    if (nc == 0)
+        return SPMM_OK;
+    SPMM_REQUIRE(C != nullptr && (B != nullptr || nb == 0), "B/C is NULL");
+    SPMM_CUDA(cudaSetDevice(A->device));
+    if (!A->stream)
+        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
+    if (A->d_B_elems < nb)
+    {
+        cudaFree(A->d_B);
+        A->d_B = nullptr;
+        A->d_B_elems = 0;
+        SPMM_CUDA(cudaMalloc(&A->d_B, sizeof(double) * std::max<size_t>(nb, 1)));
+        A->d_B_elems = nb;
+    }
+    if (A->d_C_elems < nc)
+    {
+        cudaFree(A->d_C);
+        A->d_C = nullptr;
+        A->d_C_elems = 0;
+        SPMM_CUDA(cudaMalloc(&A->d_C, sizeof(double) * nc));
+        A->d_C_elems = nc;
+    }
+    // Pageable host buffers (std::vector storage) are copied directly; cudaMemcpyAsync
+    // from pageable memory stages through the driver's pinned bounce buffers.
+    if (nb)
+        SPMM_CUDA(cudaMemcpyAsync(A->d_B, B, sizeof(double) * nb, cudaMemcpyHostToDevice, A->stream));
+    int rc = spmm_multiply_device(A, A->d_B, k, A->d_C, kernel, A->stream);
+    if (rc)
+        return rc;
+    SPMM_CUDA(cudaMemcpyAsync(C, A->d_C, sizeof(double) * nc, cudaMemcpyDeviceToHost, A->stream));
+    SPMM_CUDA(cudaStreamSynchronize(A->stream));
+    return SPMM_OK;
+}
+
+// ---- partition formulas -------------------------------------------------------------
+
+void spmm_partition_rows(int n_rows, int n_ranks, int rank, int *begin, int *end)
+{
+    const int base = n_rows / n_ranks, extra = n_rows % n_ranks;
+    const int b = rank * base + std::min(rank, extra);
+    *begin = b;
+    *end = b + base + (rank < extra ? 1 : 0);
+}
+
+void spmm_partition_cols(int k, int n_ranks, int rank, int *begin, int *end)
+{
+    const int base = k / n_ranks, extra = k % n_ranks;
+    *begin = rank * base;
+    *end = rank * base + base + (rank == n_ranks - 1 ? extra : 0);
+}
+
+void spmm_partition_nnz(long long nnz, int n_ranks, int rank, long long *begin, long long *end)
+{
+    const long long per = nnz / n_ranks, extra = nnz % n_ranks;
+    if (rank < extra)
+    {
+        *begin = rank * (per + 1);
+        *end = *begin + per + 1;
+    }
+    else
+    {
+        *begin = rank * per + extra;
+        *end = *begin + per;
+    }
+}
+
+// ---- host utilities -----------------------------------------------------------------
+
+void spmm_generate_fat_vector(int n, int k, double *out)
+{
+    // The reference never seeds (utils.cpp:203): libc's default state == srand(1).
+    srand(1);
+    for (long long i = 0; i < (long long)n * k; ++i)
+        out[i] = rand() % 100 + 1;
+}
+
+int spmm_are_equal(const double *a, const double *b, long long n, double tol)
+{
+    for (long long i = 0; i < n; ++i)
+        if (std::fabs(a[i] - b[i]) > tol)
+            return 0;
+    return 1;
+}
+
+} // extern "C"
