@@ -36,7 +36,8 @@ enum spmm_kernel
 {
     SPMM_KERNEL_AUTO = 0,
     SPMM_KERNEL_ROWS = 1,  /* (sub-)warp-per-row teams over contiguous row chunks */
-    SPMM_KERNEL_MERGE = 2  /* nnz-balanced merge-path with deterministic carry fix-up */
+    SPMM_KERNEL_MERGE = 2, /* nnz-balanced merge-path with deterministic carry fix-up */
+    SPMM_KERNEL_ROWBLOCK = 3 /* R consecutive rows per team over the union of their columns (needs spmm_csr_build_rowblocks) */
 };
 
 const char *spmm_last_error(void);
@@ -79,6 +80,13 @@ int spmm_csr_download(spmm_csr_t A, int *rowptr, int *colidx, double *vals);
 /* Row-length schedule: bins[0..7] = rows with length 0, 1-2, 3-4, 5-8, 9-16, 17-32, 33-256, >256. */
 int spmm_csr_schedule(spmm_csr_t A, long long bins[8], int *max_row_len, double *mean_row_len,
                       int *auto_kernel);
+/* Optional second layout of the same matrix for large k: row blocks of R consecutive rows
+ * with the union of their column lists (spmm_rowblock.cu). rows_per_block:
+ * 2 or 4 = build it; 0 = drop it; -1 = build the widest one whose zero fill stays modest,
+ * or none. The CSR arrays are untouched. Needs ascending column ids inside every row
+ * (what readMatrixMarketFile produces, utils.cpp:156-159); otherwise SPMM_ERR_UNSUPPORTED. */
+int spmm_csr_build_rowblocks(spmm_csr_t A, int rows_per_block);
+int spmm_csr_rowblock_info(spmm_csr_t A, int *rows_per_block, long long *union_entries, double *fill_ratio);
 /* Sub-matrix A[:, col_begin:col_end) with local column ids (column-block strategy,
  * north_star reading of sparseMatrixFatVectorMultiplyColumnWise). Built on the device. */
 int spmm_csr_column_block(spmm_csr_t A, int col_begin, int col_end, spmm_csr_t *out);
@@ -102,6 +110,9 @@ int spmm_multiply_host(spmm_csr_t A, const double *B, int k, double *C, int kern
 int spmm_multiply_rows_device(spmm_csr_t A, int row_begin, int row_end, const double *d_B, int k,
                               double *d_C_local, int kernel, void *stream);
 
+int spmm_multiply_rows_host(spmm_csr_t A, int row_begin, int row_end, const double *B, int k, double *C_local,
+                            int kernel);
+
 /* ---- a6: non-zero range [nnz_begin,nnz_end) (NonZeroElement.cpp:24-67).
  * Rows touched by the range are first_row..last_row; d_C_local holds
  * (last_row-first_row+1) x k and receives, for each of those rows, the sum over
@@ -109,8 +120,11 @@ int spmm_multiply_rows_device(spmm_csr_t A, int row_begin, int row_end, const do
  * combined across ranks in rank order). Rows strictly inside get their full value;
  * empty rows inside get zeros. ---- */
 int spmm_nnz_range_rows(spmm_csr_t A, long long nnz_begin, long long nnz_end, int *first_row, int *last_row);
-int spmm_multiply_nnz_range_device(spmm_csr_t A, long long nnz_begin, long long nnz_end,
-                                   const double *d_B, int k, double *d_C_local, void *stream);
+int spmm_multiply_nnz_range_device(spmm_csr_t A, long long nnz_begin, long long nnz_end, int first_row, int last_row,
+                                   const double *d_B, int k, double *d_C_local, int kernel, void *stream);
+
+int spmm_multiply_nnz_range_host(spmm_csr_t A, long long nnz_begin, long long nnz_end, int first_row, int last_row,
+                                 const double *B, int k, double *C_local, int kernel);
 
 /* ---- partition formulas (bit-for-bit the reference's integer arithmetic) ---- */
 void spmm_partition_rows(int n_rows, int n_ranks, int rank, int *begin, int *end);           /* RowWise.cpp:26-29 */
@@ -128,12 +142,24 @@ int spmm_are_equal(const double *a, const double *b, long long n, double tol);
  * 2*half_bandwidth+1 columns around the diagonal; values in [0.5,1.5). */
 int spmm_gen_banded(int device, int n, int nnz_per_row, int half_bandwidth, unsigned long long seed,
                     spmm_csr_t *out);
+/* Rows [row_begin,row_end) of the same matrix as a local CSR (row_end-row_begin rows x n
+ * columns): bit-identical to those rows of spmm_gen_banded, so every rank of the row-block
+ * strategy can generate just its own block (RowWise.cpp:26-29 partition). */
+int spmm_gen_banded_rows(int device, int n, int row_begin, int row_end, int nnz_per_row, int half_bandwidth,
+                         unsigned long long seed, spmm_csr_t *out);
 /* R-MAT (a,b,c,d) edge list of n_edges over 2^scale vertices, duplicates kept, built
  * into CSR by the device CSR build. */
 int spmm_gen_rmat(int device, int scale, long long n_edges, double a, double b, double c,
                   unsigned long long seed, spmm_csr_t *out);
-/* Dense fill with integers 1..100 (the value range of generateLargeFatVector). */
-int spmm_gen_fat_vector_device(int device, double *d_out, long long n_elems, unsigned long long seed, void *stream);
+/* Dense fill with integers 1..100 (the value range of generateLargeFatVector, utils.cpp:203).
+ * Element i of d_out is a function of (seed, first_elem + i) only, so slabs generated
+ * separately agree with the whole. */
+int spmm_gen_fat_vector_device(int device, double *d_out, long long n_elems, long long first_elem,
+                               unsigned long long seed, void *stream);
+
+/* Measurement knob (not needed for correct results): override the automatic team shape.
+ * keys: rows.kl rows.nv rows.np rows.unroll rows.vec rows.ctas_per_sm merge.items rowblock reset */
+int spmm_tune_set(const char *key, int value);
 
 #ifdef __cplusplus
 }

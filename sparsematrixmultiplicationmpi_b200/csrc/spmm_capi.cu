@@ -119,7 +119,7 @@ int build_schedule(spmm_csr_s *A, cudaStream_t stream)
     return SPMM_OK;
 }
 
-static int make_handle(int device, int n_rows, int n_cols, long long nnz, spmm_csr_s **out)
+int make_handle(int device, int n_rows, int n_cols, long long nnz, spmm_csr_s **out)
 {
     SPMM_REQUIRE(out != nullptr, "out handle is NULL");
     SPMM_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0, "negative size");
@@ -137,7 +137,7 @@ static int make_handle(int device, int n_rows, int n_cols, long long nnz, spmm_c
     return SPMM_OK;
 }
 
-static int alloc_arrays(spmm_csr_s *A)
+int alloc_arrays(spmm_csr_s *A)
 {
     SPMM_CUDA(cudaMalloc(&A->d_rowptr, sizeof(int) * ((size_t)A->n_rows + 1)));
     SPMM_CUDA(cudaMalloc(&A->d_colidx, sizeof(int) * (size_t)std::max<long long>(A->nnz, 1)));
@@ -150,7 +150,7 @@ static int select_kernel(const spmm_csr_s *A, int kernel)
 {
     if (kernel == SPMM_KERNEL_AUTO)
         return A->sched.auto_kernel;
-    return kernel;
+    return kernel == SPMM_KERNEL_MERGE ? SPMM_KERNEL_MERGE : SPMM_KERNEL_ROWS;
 }
 
 } // namespace spmm
@@ -189,6 +189,9 @@ int spmm_tune_set(const char *key, int value)
     Tuning &t = tuning();
     std::string k = key ? key : "";
     if (k == "rows.np") t.rows_np = value;
+    else if (k == "rows.kl") t.rows_kl = value;
+    else if (k == "rows.nv") t.rows_nv = value;
+    else if (k == "rowblock") t.rowblock = value;
     else if (k == "rows.unroll") t.rows_unroll = value;
     else if (k == "rows.vec") t.rows_vec = value;
     else if (k == "rows.ctas_per_sm") t.rows_ctas_per_sm = value;
@@ -286,6 +289,7 @@ int spmm_csr_destroy(spmm_csr_t A)
         cudaFree(A->d_colidx);
         cudaFree(A->d_vals);
     }
+    free_rowblocks(A);
     cudaFree(A->d_B);
     cudaFree(A->d_C);
     cudaFree(A->d_carry);
@@ -356,9 +360,12 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
     SPMM_REQUIRE(d_B != nullptr || A->nnz == 0, "d_B is NULL");
     SPMM_CUDA(cudaSetDevice(A->device));
     cudaStream_t s = (cudaStream_t)stream;
+    SPMM_REQUIRE(kernel >= SPMM_KERNEL_AUTO && kernel <= SPMM_KERNEL_ROWBLOCK, "unknown kernel id");
+    SPMM_REQUIRE(kernel != SPMM_KERNEL_ROWBLOCK || A->rb_R != 0, "row-block kernel requested but spmm_csr_build_rowblocks was not called");
     if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)
-        return launch_merge(A, 0, A->nnz, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, false, s);
-    return launch_rows(A, 0, A->n_rows, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
+        return launch_merge(A, 0, A->n_rows, 0, A->nnz, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
+    return launch_rows(A, 0, A->n_rows, 0, A->nnz, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count,
+                       kernel != SPMM_KERNEL_ROWS, s);
 }
 
 int spmm_multiply_device(spmm_csr_t A, const double *d_B, int k, double *d_C, int kernel, void *stream)
@@ -377,18 +384,83 @@ int spmm_multiply_rows_device(spmm_csr_t A, int row_begin, int row_end, const do
         return SPMM_OK;
     SPMM_REQUIRE(d_C_local != nullptr, "d_C_local is NULL");
     SPMM_CUDA(cudaSetDevice(A->device));
-    (void)kernel; // a row block always runs the row-chunk kernel
-    return launch_rows(A, row_begin, row_end, row_begin, d_B, k, d_C_local, k, k, (cudaStream_t)stream);
+    SPMM_REQUIRE(d_B != nullptr || A->nnz == 0, "d_B is NULL");
+    if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)
+        return launch_merge(A, row_begin, row_end, 0, A->nnz, row_begin, d_B, k, d_C_local, k, k, (cudaStream_t)stream);
+    return launch_rows(A, row_begin, row_end, 0, A->nnz, row_begin, d_B, k, d_C_local, k, k, false,
+                       (cudaStream_t)stream);
 }
 
-int spmm_multiply_host(spmm_csr_t A, const double *B, int k, double *C, int kernel)
+// Rows touched by a non-zero range: first = the row holding element nnz_begin,
+// last = the row holding element nnz_end-1 (NonZeroElement.cpp:42-51 expands the same
+// map element by element; here it is two binary searches on the device row pointer).
+__global__ void nnz_range_rows_kernel(const int *__restrict__ rowptr, int n_rows, int nnz_begin, int nnz_end, int *out)
+{
+    // last row r with rowptr[r] <= x  (rows are non-decreasing; skips empty rows at x)
+    auto find = [&](int x) {
+        int lo = 0, hi = n_rows; // invariant: rowptr[lo] <= x < rowptr[hi] ... hi may be n_rows
+        while (hi - lo > 1)
+        {
+            int mid = lo + ((hi - lo) >> 1);
+            if (rowptr[mid] <= x)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        return lo;
+    };
+    out[0] = find(nnz_begin);
+    out[1] = find(nnz_end - 1);
+}
+
+int spmm_nnz_range_rows(spmm_csr_t A, long long nnz_begin, long long nnz_end, int *first_row, int *last_row)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(first_row && last_row, "output pointer is NULL");
+    SPMM_REQUIRE(0 <= nnz_begin && nnz_begin <= nnz_end && nnz_end <= A->nnz, "non-zero range outside the matrix");
+    if (nnz_begin == nnz_end)
+    {
+        *first_row = 0;
+        *last_row = -1; // empty range touches no row
+        return SPMM_OK;
+    }
+    SPMM_CUDA(cudaSetDevice(A->device));
+    int *d_out = nullptr;
+    SPMM_CUDA(cudaMalloc(&d_out, 2 * sizeof(int)));
+    nnz_range_rows_kernel<<<1, 1>>>(A->d_rowptr, A->n_rows, (int)nnz_begin, (int)nnz_end, d_out);
+    int h[2] = {0, -1};
+    cudaError_t e = cudaMemcpy(h, d_out, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    SPMM_CUDA(e);
+    *first_row = h[0];
+    *last_row = h[1];
+    return SPMM_OK;
+}
+
+int spmm_multiply_nnz_range_device(spmm_csr_t A, long long nnz_begin, long long nnz_end, int first_row, int last_row,
+                                   const double *d_B, int k, double *d_C_local, int kernel, void *stream)
 {
     SPMM_REQUIRE(A != nullptr, "handle is NULL");
     SPMM_REQUIRE(k >= 0, "k is negative");
-    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)A->n_rows * (size_t)k;
-    if (nc == 0)
+    SPMM_REQUIRE(0 <= nnz_begin && nnz_begin <= nnz_end && nnz_end <= A->nnz, "non-zero range outside the matrix");
+    if (nnz_begin == nnz_end || k == 0 || last_row < first_row)
         return SPMM_OK;
-    SPMM_REQUIRE(C != nullptr && (B != nullptr || nb == 0), "B/C is NULL");
+    SPMM_REQUIRE(0 <= first_row && last_row < A->n_rows, "row range outside the matrix");
+    SPMM_REQUIRE(d_C_local != nullptr && d_B != nullptr, "d_B/d_C_local is NULL");
+    SPMM_CUDA(cudaSetDevice(A->device));
+    if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)
+        return launch_merge(A, first_row, last_row + 1, nnz_begin, nnz_end, first_row, d_B, k, d_C_local, k, k,
+                            (cudaStream_t)stream);
+    return launch_rows(A, first_row, last_row + 1, nnz_begin, nnz_end, first_row, d_B, k, d_C_local, k, k, false,
+                       (cudaStream_t)stream);
+}
+
+} // extern "C"
+
+// Host-buffer plumbing shared by the *_host entry points: B up, launch, C_local down.
+template <typename Launch>
+static int host_call(spmm_csr_t A, const double *B, size_t nb, double *C, size_t nc, Launch launch)
+{
     SPMM_CUDA(cudaSetDevice(A->device));
     if (!A->stream)
         SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
@@ -408,16 +480,61 @@ int spmm_multiply_host(spmm_csr_t A, const double *B, int k, double *C, int kern
         SPMM_CUDA(cudaMalloc(&A->d_C, sizeof(double) * nc));
         A->d_C_elems = nc;
     }
-    // Pageable host buffers (std::vector storage) are copied directly; cudaMemcpyAsync
+    // Pageable host buffers (std::vector / numpy storage) are copied directly; cudaMemcpyAsync
     // from pageable memory stages through the driver's pinned bounce buffers.
     if (nb)
         SPMM_CUDA(cudaMemcpyAsync(A->d_B, B, sizeof(double) * nb, cudaMemcpyHostToDevice, A->stream));
-    int rc = spmm_multiply_device(A, A->d_B, k, A->d_C, kernel, A->stream);
+    int rc = launch(A->d_B, A->d_C, A->stream);
     if (rc)
         return rc;
     SPMM_CUDA(cudaMemcpyAsync(C, A->d_C, sizeof(double) * nc, cudaMemcpyDeviceToHost, A->stream));
     SPMM_CUDA(cudaStreamSynchronize(A->stream));
     return SPMM_OK;
+}
+
+extern "C"
+{
+
+int spmm_multiply_host(spmm_csr_t A, const double *B, int k, double *C, int kernel)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(k >= 0, "k is negative");
+    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)A->n_rows * (size_t)k;
+    if (nc == 0)
+        return SPMM_OK;
+    SPMM_REQUIRE(C != nullptr && (B != nullptr || nb == 0), "B/C is NULL");
+    return host_call(A, B, nb, C, nc, [&](const double *dB, double *dC, cudaStream_t s) {
+        return spmm_multiply_device(A, dB, k, dC, kernel, s);
+    });
+}
+
+int spmm_multiply_rows_host(spmm_csr_t A, int row_begin, int row_end, const double *B, int k, double *C_local,
+                            int kernel)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(k >= 0, "k is negative");
+    SPMM_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= A->n_rows, "row range outside the matrix");
+    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)(row_end - row_begin) * (size_t)k;
+    if (nc == 0)
+        return SPMM_OK;
+    SPMM_REQUIRE(C_local != nullptr && (B != nullptr || nb == 0), "B/C is NULL");
+    return host_call(A, B, nb, C_local, nc, [&](const double *dB, double *dC, cudaStream_t s) {
+        return spmm_multiply_rows_device(A, row_begin, row_end, dB, k, dC, kernel, s);
+    });
+}
+
+int spmm_multiply_nnz_range_host(spmm_csr_t A, long long nnz_begin, long long nnz_end, int first_row, int last_row,
+                                 const double *B, int k, double *C_local, int kernel)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(k >= 0, "k is negative");
+    if (last_row < first_row || k == 0 || nnz_begin == nnz_end)
+        return SPMM_OK;
+    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)(last_row - first_row + 1) * (size_t)k;
+    SPMM_REQUIRE(C_local != nullptr && B != nullptr, "B/C is NULL");
+    return host_call(A, B, nb, C_local, nc, [&](const double *dB, double *dC, cudaStream_t s) {
+        return spmm_multiply_nnz_range_device(A, nnz_begin, nnz_end, first_row, last_row, dB, k, dC, kernel, s);
+    });
 }
 
 // ---- partition formulas -------------------------------------------------------------

@@ -1,0 +1,179 @@
+// spmm_dispatch.cu — picks the team shape for a launch and forwards to the per-W
+// translation units. See spmm_launch.cuh for the rules.
+#include "spmm_launch.cuh"
+
+namespace spmm
+{
+
+namespace
+{
+int next_pow2(int x)
+{
+    int p = 1;
+    while (p < x)
+        p <<= 1;
+    return p;
+}
+int floor_pow2(int x)
+{
+    int p = 1;
+    while (p * 2 <= x)
+        p <<= 1;
+    return p;
+}
+
+struct Shape
+{
+    int w, kl, nv, tiles;
+};
+
+Shape pick_shape(const double *d_B, long long ldb, const double *d_C, long long ldc, int kc)
+{
+    const Tuning &t = tuning();
+    const bool even = (kc % 2 == 0) && (ldb % 2 == 0) && (ldc % 2 == 0) && ((uintptr_t)d_B % 16 == 0) &&
+                      ((uintptr_t)d_C % 16 == 0);
+    Shape s;
+    s.w = even ? 2 : 1;
+    if (t.rows_vec == 1)
+        s.w = 1;
+    const int kq = (kc + s.w - 1) / s.w; // accesses needed across the columns
+    if (kq <= 8)
+    {
+        s.kl = next_pow2(kq);
+        s.nv = 1;
+    }
+    else if (kq <= 16)
+    {
+        s.kl = 8;
+        s.nv = 2;
+    }
+    else if (kq <= 32)
+    {
+        s.kl = 8;
+        s.nv = 4;
+    }
+    else if (kq <= 64)
+    {
+        s.kl = 16;
+        s.nv = 4;
+    }
+    else
+    {
+        s.kl = 32;
+        s.nv = 4;
+    }
+    if (t.rows_kl > 0)
+        s.kl = t.rows_kl;
+    if (t.rows_nv > 0)
+        s.nv = t.rows_nv;
+    const int tile = s.kl * s.nv;
+    s.tiles = (kq + tile - 1) / tile;
+    return s;
+}
+} // namespace
+
+int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
+                const double *d_B, long long ldb, double *d_C, long long ldc, int kc, bool use_rowblock,
+                cudaStream_t stream)
+{
+    if (row_end <= row_begin || kc <= 0)
+        return SPMM_OK;
+    const Tuning &t = tuning();
+    const Shape s = pick_shape(d_B, ldb, d_C, ldc, kc);
+    // whole-matrix launch with a row-block format on the handle: use it when the shape fits
+    if (use_rowblock && A->rb_R && t.rowblock != 0 && row_begin == 0 && row_end == A->n_rows && nnz_lo == 0 &&
+        nnz_hi == A->nnz && c_row0 == 0 && rowblock_shape_ok(s.w, s.kl, s.nv, s.tiles, kc))
+        return launch_rowblock(A, s.w, s.kl, s.nv, s.tiles, d_B, ldb, d_C, ldc, stream);
+    int np = 1;
+    if (s.nv == 1)
+    {
+        // lanes of a warp that a single row can keep busy: about half its mean length
+        const int want = floor_pow2(std::max(1, (int)(A->sched.mean_len * 0.5)));
+        np = std::max(1, std::min(want, 32 / s.kl));
+        if (s.kl >= 4)
+            np = std::min(np, 4);
+    }
+    if (t.rows_np > 0)
+        np = t.rows_np;
+    if (s.nv != 1)
+        np = 1;
+    np = std::max(1, std::min(np, 32 / s.kl));
+    int u = t.rows_unroll > 0 ? t.rows_unroll : (np >= 8 ? 1 : np >= 2 ? 2 : (s.nv >= 4 ? 2 : 4));
+
+    SpmmArgs args = {};
+    args.rowptr = A->d_rowptr;
+    args.colidx = A->d_colidx;
+    args.vals = A->d_vals;
+    args.B = d_B;
+    args.C = d_C;
+    args.ldb = ldb;
+    args.ldc = ldc;
+    args.row_begin = row_begin;
+    args.row_end = row_end;
+    args.nnz_lo = (int)nnz_lo;
+    args.nnz_hi = (int)nnz_hi;
+    args.c_row0 = c_row0;
+    args.kc = kc;
+    return s.w == 2 ? launch_rows_w2(s.kl, s.nv, np, u, args, s.tiles, A->device, stream)
+                    : launch_rows_w1(s.kl, s.nv, np, u, args, s.tiles, A->device, stream);
+}
+
+int launch_merge(spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
+                 const double *d_B, long long ldb, double *d_C, long long ldc, int kc, cudaStream_t stream)
+{
+    if (row_end <= row_begin || kc <= 0)
+        return SPMM_OK;
+    const Tuning &t = tuning();
+    const Shape s = pick_shape(d_B, ldb, d_C, ldc, kc);
+    const int u = t.rows_unroll > 0 ? t.rows_unroll : (s.nv >= 4 ? 2 : 4);
+    const long long total = (long long)(row_end - row_begin) + (nnz_hi - nnz_lo);
+    long long items = t.merge_items > 0 ? t.merge_items : 512;
+    // enough teams to fill the machine, few enough that the carry rows stay a small fraction of C
+    const long long teams_per_wave = (long long)device_props(A->device).sm_count * 64 * (32 / s.kl);
+    while (items > 64 && (total + items - 1) / items < teams_per_wave)
+        items >>= 1;
+    const long long n_teams = std::max(1LL, (total + items - 1) / items);
+    const int ldcarry = s.tiles * s.kl * s.nv * s.w;
+
+    const size_t need_elems = (size_t)(2 * n_teams) * (size_t)ldcarry;
+    if (A->carry_elems < need_elems)
+    {
+        cudaFree(A->d_carry);
+        A->d_carry = nullptr;
+        A->carry_elems = 0;
+        SPMM_CUDA(cudaMalloc(&A->d_carry, sizeof(double) * need_elems));
+        A->carry_elems = need_elems;
+    }
+    if (A->carry_rows < (size_t)(2 * n_teams))
+    {
+        cudaFree(A->d_carry_row);
+        A->d_carry_row = nullptr;
+        A->carry_rows = 0;
+        SPMM_CUDA(cudaMalloc(&A->d_carry_row, sizeof(int) * (size_t)(2 * n_teams)));
+        A->carry_rows = (size_t)(2 * n_teams);
+    }
+
+    SpmmArgs args = {};
+    args.rowptr = A->d_rowptr;
+    args.colidx = A->d_colidx;
+    args.vals = A->d_vals;
+    args.B = d_B;
+    args.C = d_C;
+    args.ldb = ldb;
+    args.ldc = ldc;
+    args.row_begin = row_begin;
+    args.row_end = row_end;
+    args.nnz_lo = (int)nnz_lo;
+    args.nnz_hi = (int)nnz_hi;
+    args.c_row0 = c_row0;
+    args.kc = kc;
+    args.items_per_team = (int)items;
+    args.n_teams = (int)n_teams;
+    args.carry = A->d_carry;
+    args.carry_row = A->d_carry_row;
+    args.ldcarry = ldcarry;
+    return s.w == 2 ? launch_merge_w2(s.kl, s.nv, u, args, s.tiles, stream)
+                    : launch_merge_w1(s.kl, s.nv, u, args, s.tiles, stream);
+}
+
+} // namespace spmm

@@ -42,12 +42,14 @@ struct Schedule
 // Tuning knobs (0 = choose automatically). Set through spmm_tune_set for experiments.
 struct Tuning
 {
-    int rows_np = 0;        // concurrent non-zeros per team
-    int rows_unroll = 0;    // B-row loads in flight per team step
-    int rows_vec = 0;       // doubles per lane (1, 2, 4)
+    int rows_kl = 0;        // lanes across the columns of a B row
+    int rows_nv = 0;        // accesses per lane (1, 2, 4)
+    int rows_np = 0;        // concurrent non-zeros of one row per team
+    int rows_unroll = 0;    // steps in flight per team
+    int rows_vec = 0;       // 1 forces 8-byte accesses
     int rows_ctas_per_sm = 0;
-    int rows_threads = 0;   // 128 / 256 / 512
     int merge_items = 0;    // merge-path items per team
+    int rowblock = -1;      // -1 auto, 0 never use the row-block format, 1 always when built
 };
 Tuning &tuning();
 
@@ -76,6 +78,11 @@ struct spmm_csr_s
     double *d_B = nullptr, *d_C = nullptr;
     size_t d_B_elems = 0, d_C_elems = 0;
     cudaStream_t stream = nullptr; // owned, for host-buffer calls
+    // row-block union format (spmm_rowblock.cu), optional
+    int rb_R = 0, rb_blocks = 0;
+    long long rb_entries = 0;
+    int *d_blkptr = nullptr, *d_ucol = nullptr;
+    double *d_uval = nullptr;
     // merge-path scratch (carry rows), grown on demand
     double *d_carry = nullptr;
     int *d_carry_row = nullptr;
@@ -85,9 +92,18 @@ struct spmm_csr_s
 namespace spmm
 {
 // launchers implemented in the kernel translation units
-int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, int c_row0, const double *d_B, long long ldb,
-                double *d_C, long long ldc, int kc, cudaStream_t stream);
-int launch_merge(spmm_csr_s *A, long long nnz_begin, long long nnz_end, int c_row0, const double *d_B,
-                 long long ldb, double *d_C, long long ldc, int kc, bool range_mode, cudaStream_t stream);
+// rows [row_begin,row_end), each clipped to the non-zero range [nnz_lo,nnz_hi); row c_row0 is stored at d_C[0]
+int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
+                const double *d_B, long long ldb, double *d_C, long long ldc, int kc, bool use_rowblock,
+                cudaStream_t stream);
+int launch_merge(spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
+                 const double *d_B, long long ldb, double *d_C, long long ldc, int kc, cudaStream_t stream);
+bool rowblock_shape_ok(int w, int kl, int nv, int tiles, int kc);
+int launch_rowblock(const spmm_csr_s *A, int w, int kl, int nv, int tiles, const double *d_B, long long ldb,
+                    double *d_C, long long ldc, cudaStream_t stream);
+void free_rowblocks(spmm_csr_s *A);
+// handle plumbing shared by spmm_capi.cu and csr_build.cu
+int make_handle(int device, int n_rows, int n_cols, long long nnz, spmm_csr_s **out);
+int alloc_arrays(spmm_csr_s *A);
 int build_schedule(spmm_csr_s *A, cudaStream_t stream);
 } // namespace spmm

@@ -7,18 +7,27 @@
 // ColumnWise.cpp:34-48, NonZeroElement.cpp:56-67).
 //
 // The path is not a dense contraction: no tensor cores. It is bound by HBM
-// (A streamed once, B and C touched once) and, at large k, by the L1/L2 -> SM
-// gather of B rows. Design rules used below (DESIGN.md has the arithmetic):
-//   * lanes map across the k columns of a B row, 16 B (double2) per lane, so a B
-//     row is one fully coalesced request; several non-zeros / rows share a warp
-//     when k is small ("team" = KL lanes x NP concurrent non-zeros);
+// (A streamed once, B and C touched once) and, at large k, by the L1 -> register
+// gather of B rows (128 B/clk/SM). Design rules used below (DESIGN.md has the
+// arithmetic):
+//   * a "team" of KL lanes maps across the k columns of a B row. Lane kl owns NV
+//     chunks of W doubles (W=2: one 16-byte load) interleaved at stride KL*W, so
+//     every load instruction of a team covers one contiguous KL*W*8-byte piece of
+//     the B row (a full 128-byte line for KL=8, W=2) — no half-used L1 wavefronts;
+//   * 32/(KL*NP) teams share a warp, each on its own row, so one index/value load
+//     instruction serves several non-zeros; NP>1 puts NP non-zeros of the SAME row
+//     side by side (small k) and folds them with warp shuffles;
 //   * every CTA owns ONE CONTIGUOUS chunk of rows, cut so that chunks cost the
 //     same (nnz + row overhead), and the grid is one resident wave
 //     (SMs x CTAs/SM): neighbouring rows of FEM-like matrices share B rows, and
 //     a contiguous sweep turns that into L1 hits instead of L2 traffic;
 //   * A (col ids, values) is streamed with L1::no_allocate so it does not evict
 //     B rows from L1; C is written with streaming stores;
-//   * UNROLL independent B-row loads are in flight per team before the FMAs.
+//   * U steps of independent B-row loads are in flight per team before the FMAs.
+//
+// Row extents are always read through RowClip: the per-rank non-zero range of
+// the NonZeroElement strategy (NonZeroElement.cpp:24-39) is the same CSR with
+// every row clipped to [nnz_lo, nnz_hi).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,25 +39,25 @@ namespace spmm
 __device__ __forceinline__ int ld_stream_i32(const int *p)
 {
     int v;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ double ld_stream_f64(const double *p)
 {
     double v;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ double ld_b1(const double *p)
 {
     double v;
-    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    asm("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ double2 ld_b2(const double *p)
 {
     double2 v;
-    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
 __device__ __forceinline__ void st_c1(double *p, double v)
@@ -60,69 +69,118 @@ __device__ __forceinline__ void st_c2(double *p, double x, double y)
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x), "d"(y) : "memory");
 }
 
-// VEC contiguous doubles of one B row / C row per lane.
-template <int VEC>
-struct Vec
+// Row extents clipped to a non-zero range (no-op for the whole matrix).
+struct RowClip
 {
-    double v[VEC];
+    const int *rowptr;
+    int lo, hi;
+    __device__ __forceinline__ int operator()(int r) const { return min(max(rowptr[r], lo), hi); }
+};
+
+// The slice of one B/C row a lane owns: NV chunks of W doubles, chunk i at
+// column (i*KL + kl)*W of the launch's column tile.
+template <int KL, int NV, int W>
+struct Slice
+{
+    double v[NV * W];
+    static constexpr int TILE = KL * NV * W; // columns covered by one team
     __device__ __forceinline__ void zero()
     {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i)
+        for (int i = 0; i < NV * W; ++i)
             v[i] = 0.0;
     }
-    __device__ __forceinline__ void load(const double *p)
+    // p = row base + tile base + kl*W; `mask` bit i = chunk i lies inside the k columns.
+    // FULL (every chunk inside): unconditional loads, which ptxas batches ahead of the FMAs.
+    template <bool FULL>
+    __device__ __forceinline__ void load(const double *p, unsigned mask)
     {
-        if constexpr (VEC == 1)
-            v[0] = ld_b1(p);
-        else
-        {
 #pragma unroll
-            for (int i = 0; i < VEC; i += 2)
+        for (int i = 0; i < NV; ++i)
+        {
+            if constexpr (!FULL)
             {
-                double2 t = ld_b2(p + i);
-                v[i] = t.x;
-                v[i + 1] = t.y;
+#pragma unroll
+                for (int w = 0; w < W; ++w)
+                    v[i * W + w] = 0.0;
+                if (!(mask & (1u << i)))
+                    continue;
             }
+            if constexpr (W == 2)
+            {
+                double2 t = ld_b2(p + i * KL * W);
+                v[2 * i] = t.x;
+                v[2 * i + 1] = t.y;
+            }
+            else
+                v[i] = ld_b1(p + i * KL * W);
         }
     }
-    __device__ __forceinline__ void store(double *p) const
+    __device__ __forceinline__ void store(double *p, unsigned mask) const
     {
-        if constexpr (VEC == 1)
-            st_c1(p, v[0]);
-        else
-        {
 #pragma unroll
-            for (int i = 0; i < VEC; i += 2)
-                st_c2(p + i, v[i], v[i + 1]);
-        }
+        for (int i = 0; i < NV; ++i)
+            if (mask & (1u << i))
+            {
+                if constexpr (W == 2)
+                    st_c2(p + i * KL * W, v[2 * i], v[2 * i + 1]);
+                else
+                    st_c1(p + i * KL * W, v[i]);
+            }
     }
-    __device__ __forceinline__ void fma(double a, const Vec &b)
+    // plain (cached) store/load for the merge kernel's carry rows
+    __device__ __forceinline__ void store_plain(double *p) const
     {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i)
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int w = 0; w < W; ++w)
+                p[i * KL * W + w] = v[i * W + w];
+    }
+    __device__ __forceinline__ void add_plain(const double *p)
+    {
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int w = 0; w < W; ++w)
+                v[i * W + w] += p[i * KL * W + w];
+    }
+    __device__ __forceinline__ void fma(double a, const Slice &b)
+    {
+#pragma unroll
+        for (int i = 0; i < NV * W; ++i)
             v[i] = ::fma(a, b.v[i], v[i]);
     }
 };
+
+template <int KL, int NV, int W>
+__device__ __forceinline__ unsigned slice_mask(int tile0, int kl, int kc)
+{
+    unsigned m = 0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if (tile0 + (i * KL + kl) * W < kc) // W==2 launches have even kc: a chunk is all in or all out
+            m |= 1u << i;
+    return m;
+}
 
 // Cost model used to cut rows into equal-cost contiguous chunks: one unit per
 // non-zero plus ROW_COST units per row (row-pointer loads, C store, loop set-up).
 constexpr int ROW_COST = 4;
 
-__device__ __forceinline__ long long chunk_cost(const int *__restrict__ rowptr, int row_begin, int r)
+__device__ __forceinline__ long long chunk_cost(const RowClip &rp, int row_begin, int r)
 {
-    return (long long)(rowptr[r] - rowptr[row_begin]) + (long long)ROW_COST * (r - row_begin);
+    return (long long)(rp(r) - rp(row_begin)) + (long long)ROW_COST * (r - row_begin);
 }
 
 // First row r in [row_begin,row_end] whose prefix cost reaches `target`.
-__device__ __forceinline__ int chunk_lower_bound(const int *__restrict__ rowptr, int row_begin, int row_end,
-                                                 long long target)
+__device__ __forceinline__ int chunk_lower_bound(const RowClip &rp, int row_begin, int row_end, long long target)
 {
     int lo = row_begin, hi = row_end;
     while (lo < hi)
     {
         int mid = lo + ((hi - lo) >> 1);
-        if (chunk_cost(rowptr, row_begin, mid) < target)
+        if (chunk_cost(rp, row_begin, mid) < target)
             lo = mid + 1;
         else
             hi = mid;
@@ -130,7 +188,7 @@ __device__ __forceinline__ int chunk_lower_bound(const int *__restrict__ rowptr,
     return lo;
 }
 
-struct RowsArgs
+struct SpmmArgs
 {
     const int *rowptr;
     const int *colidx;
@@ -139,40 +197,49 @@ struct RowsArgs
     double *C;       // already offset to the first computed column; row `c_row0` is at C[0]
     long long ldb, ldc;
     int row_begin, row_end; // rows computed by this launch
+    int nnz_lo, nnz_hi;     // rows are clipped to this non-zero range
     int c_row0;             // row id stored at C[0]
-    int kc;                 // columns computed (per blockIdx.y tile: KL*VEC of them)
+    int kc;                 // columns computed
+    // merge-path kernel only
+    int items_per_team;
+    int n_teams;
+    double *carry;  // [2*n_teams][ldcarry]
+    int *carry_row; // [2*n_teams], -1 = unused
+    int ldcarry;
 };
 
-// Team kernel. A team of KL*NP lanes owns one row at a time: KL lanes across the
-// columns (VEC doubles each), NP non-zeros of the row in flight side by side,
-// UNROLL steps issued back to back. 32/(KL*NP) teams share a warp.
-template <int KL, int VEC, int NP, int UNROLL, int THREADS>
-__global__ void __launch_bounds__(THREADS) spmm_rows_kernel(const RowsArgs a)
+// Row kernel. A team of KL*NP lanes owns one row at a time: KL lanes across the
+// columns, NP non-zeros of the row in flight side by side, U steps issued back
+// to back. 32/(KL*NP) teams share a warp.
+template <int KL, int NV, int W, int NP, int U, bool FULL, int THREADS>
+__global__ void __launch_bounds__(THREADS) spmm_rows_kernel(const SpmmArgs a)
 {
     constexpr int T = KL * NP;
     constexpr int RW = 32 / T;
     constexpr int SLOTS = (THREADS / 32) * RW;
     static_assert(T <= 32 && 32 % T == 0, "team must divide a warp");
+    using S = Slice<KL, NV, W>;
 
+    const RowClip rp{a.rowptr, a.nnz_lo, a.nnz_hi};
     __shared__ int s_chunk[2];
     if (threadIdx.x == 0)
     {
-        const long long total = chunk_cost(a.rowptr, a.row_begin, a.row_end);
+        const long long total = chunk_cost(rp, a.row_begin, a.row_end);
         const long long g = gridDim.x, b = blockIdx.x;
-        s_chunk[0] = b == 0 ? a.row_begin : chunk_lower_bound(a.rowptr, a.row_begin, a.row_end, (total * b + g - 1) / g);
-        s_chunk[1] = b == g - 1 ? a.row_end : chunk_lower_bound(a.rowptr, a.row_begin, a.row_end, (total * (b + 1) + g - 1) / g);
+        s_chunk[0] = b == 0 ? a.row_begin : chunk_lower_bound(rp, a.row_begin, a.row_end, (total * b + g - 1) / g);
+        s_chunk[1] = b == g - 1 ? a.row_end : chunk_lower_bound(rp, a.row_begin, a.row_end, (total * (b + 1) + g - 1) / g);
     }
     __syncthreads();
     const int lo = s_chunk[0], hi = s_chunk[1];
 
     const int lane = threadIdx.x & 31;
-    const int lt = lane % T;   // lane inside the team
-    const int g = lt / KL;     // which of the NP concurrent non-zeros
-    const int kl = lt % KL;    // which column group
+    const int lt = lane % T; // lane inside the team
+    const int g = lt / KL;   // which of the NP concurrent non-zeros
+    const int kl = lt % KL;  // which column group
     const int slot = (threadIdx.x >> 5) * RW + lane / T;
-    const int kcol = blockIdx.y * (KL * VEC) + kl * VEC;
-    const bool kact = kcol < a.kc;
-    const double *__restrict__ Bk = a.B + kcol;
+    const int tile0 = blockIdx.y * S::TILE;
+    const unsigned mask = slice_mask<KL, NV, W>(tile0, kl, a.kc);
+    const double *__restrict__ Bk = a.B + tile0 + kl * W;
 
     for (int base = lo; base < hi; base += SLOTS)
     {
@@ -181,51 +248,249 @@ __global__ void __launch_bounds__(THREADS) spmm_rows_kernel(const RowsArgs a)
         int js = 0, je = 0;
         if (valid)
         {
-            js = a.rowptr[row];
-            je = a.rowptr[row + 1];
+            js = rp(row);
+            je = rp(row + 1);
         }
-        Vec<VEC> acc;
+        S acc;
         acc.zero();
-        for (int j = js + g; j < je; j += NP * UNROLL)
+        int j = js + g;
+        // full groups: U steps in flight, every load unconditional
+        for (; j + (U - 1) * NP < je; j += NP * U)
         {
-            int c[UNROLL];
-            double x[UNROLL];
-            Vec<VEC> b[UNROLL];
+            int c[U];
+            double x[U];
+            S b[U];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u)
+            for (int u = 0; u < U; ++u)
             {
-                const int jj = j + u * NP;
-                c[u] = 0;
-                x[u] = 0.0;
-                if (jj < je)
+                c[u] = ld_stream_i32(a.colidx + j + u * NP);
+                x[u] = ld_stream_f64(a.vals + j + u * NP);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                b[u].template load<FULL>(Bk + (long long)c[u] * a.ldb, mask);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                acc.fma(x[u], b[u]);
+        }
+        // tail: fewer than U steps left
+        if constexpr (U > 1)
+        {
+            if (j < je)
+            {
+                int c[U - 1];
+                double x[U - 1];
+                S b[U - 1];
+#pragma unroll
+                for (int u = 0; u < U - 1; ++u)
                 {
+                    const int jj = min(j + u * NP, je - 1); // clamp: a valid element, weight 0 when past the end
                     c[u] = ld_stream_i32(a.colidx + jj);
                     x[u] = ld_stream_f64(a.vals + jj);
                 }
-            }
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u)
-            {
-                b[u].zero();
-                if (kact && (j + u * NP) < je)
-                    b[u].load(Bk + (long long)c[u] * a.ldb);
-            }
+                for (int u = 0; u < U - 1; ++u)
+                    b[u].template load<FULL>(Bk + (long long)c[u] * a.ldb, mask);
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u)
-                if ((j + u * NP) < je)
-                    acc.fma(x[u], b[u]);
+                for (int u = 0; u < U - 1; ++u)
+                    if (j + u * NP < je)
+                        acc.fma(x[u], b[u]);
+            }
         }
         if constexpr (NP > 1)
         {
 #pragma unroll
             for (int off = KL; off < T; off <<= 1)
 #pragma unroll
-                for (int i = 0; i < VEC; ++i)
+                for (int i = 0; i < NV * W; ++i)
                     acc.v[i] += __shfl_xor_sync(0xffffffffu, acc.v[i], off);
         }
-        if (valid && g == 0 && kact)
-            acc.store(a.C + (long long)(row - a.c_row0) * a.ldc + kcol);
+        if (valid && g == 0)
+            acc.store(a.C + (long long)(row - a.c_row0) * a.ldc + tile0 + kl * W, mask);
     }
+}
+
+// ---- nnz-balanced merge-path kernel ---------------------------------------------------
+// The work list is the merge of the row-end offsets (one "flush" item per row) with
+// the non-zero indices; every team takes items_per_team consecutive items, found by a
+// diagonal binary search. A row that starts inside a team's range and ends there is
+// stored straight to C. A row cut by a team boundary is never stored by the sweep:
+// every team that touched it leaves its partial sum in a carry slot (head = the team
+// that reaches the row's end, tail = teams that ran out of items inside the row), and
+// spmm_merge_fixup_kernel adds the slots of a row in team order — deterministic, no
+// atomics.
+__device__ __forceinline__ void merge_path_search(const RowClip &rp, int row_begin, int n_rows, int nnz_lo,
+                                                  int n_nnz, long long diag, int &x_out, int &y_out)
+{
+    long long x_min = diag > n_nnz ? diag - n_nnz : 0;
+    long long x_max = diag < n_rows ? diag : n_rows;
+    while (x_min < x_max)
+    {
+        const long long pivot = (x_min + x_max) >> 1;
+        // row-end item `pivot` precedes non-zero item (diag - pivot - 1) when its offset is <= that index
+        if ((long long)rp(row_begin + (int)pivot + 1) <= (long long)nnz_lo + (diag - pivot - 1))
+            x_min = pivot + 1;
+        else
+            x_max = pivot;
+    }
+    x_out = (int)x_min;
+    y_out = (int)(diag - x_min);
+}
+
+template <int KL, int NV, int W, int U, bool FULL, int THREADS>
+__global__ void __launch_bounds__(THREADS) spmm_merge_kernel(const SpmmArgs a)
+{
+    constexpr int RW = 32 / KL;
+    using S = Slice<KL, NV, W>;
+    const RowClip rp{a.rowptr, a.nnz_lo, a.nnz_hi};
+
+    const int lane = threadIdx.x & 31;
+    const int kl = lane % KL;
+    const long long team = ((long long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5)) * RW + lane / KL;
+    if (team >= a.n_teams)
+        return;
+    const int tile0 = blockIdx.y * S::TILE;
+    const unsigned mask = slice_mask<KL, NV, W>(tile0, kl, a.kc);
+    const double *__restrict__ Bk = a.B + tile0 + kl * W;
+    const int n_rows = a.row_end - a.row_begin;
+    const int n_nnz = a.nnz_hi - a.nnz_lo;
+    const long long total = (long long)n_rows + n_nnz;
+    const long long d0 = min(team * (long long)a.items_per_team, total);
+    const long long d1 = min(d0 + a.items_per_team, total);
+
+    int x, y;
+    merge_path_search(rp, a.row_begin, n_rows, a.nnz_lo, n_nnz, d0, x, y);
+    int row = a.row_begin + x;
+    int j = a.nnz_lo + y;
+    int items = (int)(d1 - d0);
+
+    double *carry_head = a.carry + (2 * team) * (long long)a.ldcarry + tile0 + kl * W;
+    double *carry_tail = carry_head + a.ldcarry;
+    int head_row = -1, tail_row = -1;
+
+    S acc;
+    acc.zero();
+    // fresh = no earlier team consumed a non-zero of `row`
+    bool fresh = row < a.row_end ? (j == rp(row)) : true;
+    while (items > 0 && row < a.row_end)
+    {
+        const int row_end_j = rp(row + 1);
+        const int n = min(row_end_j - j, items);
+        const int je = j + n;
+        for (; j + U <= je; j += U)
+        {
+            int c[U];
+            double xv[U];
+            S b[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+            {
+                c[u] = ld_stream_i32(a.colidx + j + u);
+                xv[u] = ld_stream_f64(a.vals + j + u);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                b[u].template load<FULL>(Bk + (long long)c[u] * a.ldb, mask);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                acc.fma(xv[u], b[u]);
+        }
+        if (j < je)
+        {
+            int c[U - 1];
+            double xv[U - 1];
+            S b[U - 1];
+#pragma unroll
+            for (int u = 0; u < U - 1; ++u)
+            {
+                const int jj = min(j + u, je - 1);
+                c[u] = ld_stream_i32(a.colidx + jj);
+                xv[u] = ld_stream_f64(a.vals + jj);
+            }
+#pragma unroll
+            for (int u = 0; u < U - 1; ++u)
+                b[u].template load<FULL>(Bk + (long long)c[u] * a.ldb, mask);
+#pragma unroll
+            for (int u = 0; u < U - 1; ++u)
+                if (j + u < je)
+                    acc.fma(xv[u], b[u]);
+        }
+        j = je;
+        items -= n;
+        if (items > 0)
+        {
+            // the row-end item: this team closes `row`
+            if (fresh)
+                acc.store(a.C + (long long)(row - a.c_row0) * a.ldc + tile0 + kl * W, mask);
+            else
+            {
+                acc.store_plain(carry_head);
+                head_row = row;
+            }
+            acc.zero();
+            fresh = true;
+            ++row;
+            --items;
+        }
+    }
+    // ran out of items inside a row some of whose non-zeros are already consumed
+    if (row < a.row_end && j > rp(row))
+    {
+        acc.store_plain(carry_tail);
+        tail_row = row;
+    }
+    if (kl == 0 && blockIdx.y == 0)
+    {
+        a.carry_row[2 * team] = head_row;
+        a.carry_row[2 * team + 1] = tail_row;
+    }
+}
+
+// One team per carry slot. The first slot of a row's run sums the run in slot order
+// and stores the row. Used slots of one row are at most one unused slot apart.
+template <int KL, int NV, int W, int THREADS>
+__global__ void __launch_bounds__(THREADS) spmm_merge_fixup_kernel(const SpmmArgs a)
+{
+    constexpr int RW = 32 / KL;
+    using S = Slice<KL, NV, W>;
+    const int lane = threadIdx.x & 31;
+    const int kl = lane % KL;
+    const long long n_slots = 2LL * a.n_teams;
+    const long long s = ((long long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5)) * RW + lane / KL;
+    if (s >= n_slots)
+        return;
+    const int row = a.carry_row[s];
+    if (row < 0)
+        return;
+    if (s >= 1)
+    {
+        const int p1 = a.carry_row[s - 1];
+        if (p1 == row)
+            return;
+        if (p1 < 0 && s >= 2 && a.carry_row[s - 2] == row)
+            return;
+    }
+    const int tile0 = blockIdx.y * S::TILE;
+    const unsigned mask = slice_mask<KL, NV, W>(tile0, kl, a.kc);
+    const double *cp = a.carry + tile0 + kl * W;
+    S acc;
+    acc.zero();
+    acc.add_plain(cp + s * (long long)a.ldcarry);
+    int gap = 0;
+    for (long long q = s + 1; q < n_slots && gap < 2; ++q)
+    {
+        const int r = a.carry_row[q];
+        if (r == row)
+        {
+            acc.add_plain(cp + q * (long long)a.ldcarry);
+            gap = 0;
+        }
+        else if (r < 0)
+            ++gap;
+        else
+            break;
+    }
+    acc.store(a.C + (long long)(row - a.c_row0) * a.ldc + tile0 + kl * W, mask);
 }
 
 } // namespace spmm

@@ -1,0 +1,121 @@
+"""The four entry points of the reference, same names, argument meaning and result.
+
+  sparseMatrixFatVectorMultiply                 SparseMatrixFatVectorMultiply.h:14-15, .cpp:11-31
+  sparseMatrixFatVectorMultiplyRowWise          SparseMatrixFatVectorMultiplyRowWise.h:15-17, .cpp:12-126
+  sparseMatrixFatVectorMultiplyColumnWise       SparseMatrixFatVectorMultiplyColumnWise.h:15, .cpp:13-131
+  sparseMatrixFatVectorMultiplyNonZeroElement   SparseMatrixFatVectorMultiplyNonZeroElement.h:15, .cpp:12-120
+
+Inputs are host objects (SparseMatrix, FatVector = (N,k) float64 array), replicated on every
+rank as main.cpp:106-146 leaves them; the result is a host FatVector on rank 0 and an empty one
+elsewhere (RowWise.cpp:125). A "rank" is one process driving one B200 (torchrun); without an
+initialised process group there is one rank. All arithmetic runs in the sm_100a kernels; a
+missing extension or GPU raises (no CPU fallback).
+
+The device copy of a matrix shard is cached per (matrix buffers, strategy, rank layout), so
+main()'s four back-to-back calls on the same M upload A once per strategy shard. The reference
+checks nothing about its arguments; here sizes are validated and errors surface as RuntimeError
+(the reference's only convention: std::runtime_error).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .matrix import DeviceCSR, SparseMatrix, as_fat_vector
+from .strategies import ColumnBlocks, ColumnSlabs, CudaCompute, NonZeroRanges, RowWise, world
+
+_compute: CudaCompute | None = None
+_cache: dict = {}
+_CACHE_MAX = 8
+
+
+def _engine() -> CudaCompute:
+    global _compute
+    if _compute is None:
+        _compute = CudaCompute()
+    return _compute
+
+
+def clear_cache() -> None:
+    """Drop every cached device shard (call after mutating a SparseMatrix in place)."""
+    for plan in _cache.values():
+        A = getattr(plan, "A", plan)
+        if isinstance(A, DeviceCSR):
+            A.close()
+    _cache.clear()
+
+
+def _key(m: SparseMatrix, tag: str, k: int | None):
+    rank, P = world()
+    return (m.values.ctypes.data, m.colIndices.ctypes.data, m.rowPtr.ctypes.data, m.nnz, m.numRows, m.numCols,
+            tag, k, rank, P)
+
+
+def _cached(m: SparseMatrix, tag: str, k: int | None, make):
+    key = _key(m, tag, k)
+    if key not in _cache:
+        if len(_cache) >= _CACHE_MAX:
+            clear_cache()
+        _cache[key] = make()
+    return _cache[key]
+
+
+def _check(m: SparseMatrix, v, k: int) -> np.ndarray:
+    if k < 0:
+        raise RuntimeError("vecCols must be non-negative")
+    if m.rowPtr.size != m.numRows + 1 or m.values.size != m.colIndices.size:
+        raise RuntimeError("SparseMatrix arrays are inconsistent (rowPtr needs numRows+1 entries)")
+    B = as_fat_vector(v)
+    if B.shape[0] < m.numCols or B.shape[1] < k:
+        raise RuntimeError(f"fatVector must hold at least {m.numCols} rows of {k} values")
+    if B.shape[1] != k or B.shape[0] != m.numCols:
+        B = np.ascontiguousarray(B[:m.numCols, :k])
+    return B
+
+
+def _to_device(B: np.ndarray, eng: CudaCompute) -> torch.Tensor:
+    return torch.from_numpy(B).to(eng.device, non_blocking=False)
+
+
+def _to_host(Cd: torch.Tensor | None, k: int) -> np.ndarray:
+    if Cd is None:
+        return np.empty((0, k), dtype=np.float64)  # FatVector{} on non-root ranks
+    return Cd.cpu().numpy()
+
+
+def sparseMatrixFatVectorMultiply(sparseMatrix: SparseMatrix, fatVector, vecCols: int) -> np.ndarray:
+    """C = A * B on one B200 (the sequential reference function; no communication)."""
+    B = _check(sparseMatrix, fatVector, vecCols)
+    eng = _engine()
+    A = _cached(sparseMatrix, "seq", None, lambda: eng.upload(sparseMatrix))
+    return A.multiply_host(B, vecCols, eng.kernel)
+
+
+def sparseMatrixFatVectorMultiplyRowWise(sparseMatrix: SparseMatrix, fatVector, vecCols: int) -> np.ndarray:
+    B = _check(sparseMatrix, fatVector, vecCols)
+    eng = _engine()
+    plan = _cached(sparseMatrix, "row", vecCols, lambda: RowWise.from_host(eng, sparseMatrix, vecCols))
+    return _to_host(plan.run(_to_device(B, eng)), vecCols)
+
+
+def sparseMatrixFatVectorMultiplyColumnWise(sparseMatrix: SparseMatrix, fatVector, vecCols: int,
+                                            mode: str = "blocks") -> np.ndarray:
+    """mode="blocks": column blocks of A + reduce-scatter (BASELINE.json); mode="slabs": the reference's
+    split of B's k columns. Same C either way (up to FP64 summation order for "blocks")."""
+    B = _check(sparseMatrix, fatVector, vecCols)
+    eng = _engine()
+    if mode == "slabs":
+        plan = _cached(sparseMatrix, "colslab", vecCols, lambda: ColumnSlabs.from_host(eng, sparseMatrix, vecCols))
+        return _to_host(plan.run(_to_device(B, eng)), vecCols)
+    if mode != "blocks":
+        raise RuntimeError("mode must be 'blocks' or 'slabs'")
+    plan = _cached(sparseMatrix, "colblk", vecCols, lambda: ColumnBlocks.from_host(eng, sparseMatrix, vecCols))
+    B_local = _to_device(np.ascontiguousarray(B[plan.col_start:plan.col_end]), eng)
+    return _to_host(plan.run(B_local), vecCols)
+
+
+def sparseMatrixFatVectorMultiplyNonZeroElement(sparseMatrix: SparseMatrix, fatVector, vecCols: int) -> np.ndarray:
+    B = _check(sparseMatrix, fatVector, vecCols)
+    eng = _engine()
+    plan = _cached(sparseMatrix, "nnz", vecCols, lambda: NonZeroRanges.from_host(eng, sparseMatrix, vecCols))
+    return _to_host(plan.run(_to_device(B, eng)), vecCols)

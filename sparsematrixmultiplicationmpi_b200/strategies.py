@@ -1,0 +1,340 @@
+"""The reference's three MPI decompositions as one-process-per-GPU partitions over torch.distributed.
+
+  RowWise          rows of A / C in contiguous blocks        RowWise.cpp:12-126
+                   B replicated by broadcast, C gathered      (NCCL broadcast / gather)
+  ColumnBlocks     column blocks of A with the matching row   BASELINE.json north_star reading of
+                   slab of B; full-size partial C summed by   ColumnWise.cpp:13-131
+                   reduce-scatter
+  ColumnSlabs      the reference's own reading: B's k columns ColumnWise.cpp:25-48,82-84
+                   split across ranks, slabs gathered
+  NonZeroRanges    equal ranges of the non-zero stream;       NonZeroElement.cpp:12-120
+                   only rows cut by a range boundary are
+                   exchanged, peer to peer, and summed in
+                   rank order (no dense reduce)
+
+Every class works on torch tensors living on the device of its `compute` engine. `CudaCompute`
+(the product) runs the sm_100a kernels through the C-ABI; the CPU tests inject their own engine
+on gloo to exercise the partition / exchange logic. There is no CPU engine in the package.
+
+rank/size come from torch.distributed when it is initialised (one process per GPU, launched by
+torchrun), else the single-rank degenerate case — exactly how the reference's code behaves at
+mpirun -np 1.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+from .matrix import DeviceCSR, SparseMatrix
+
+
+def world(group=None) -> tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def partition_rows(n_rows: int, P: int, r: int) -> tuple[int, int]:
+    """RowWise.cpp:26-29: base = N/P, the first N%P ranks take one more row."""
+    base, extra = divmod(n_rows, P)
+    s = r * base + min(r, extra)
+    return s, s + base + (1 if r < extra else 0)
+
+
+def partition_cols(k: int, P: int, r: int) -> tuple[int, int]:
+    """ColumnWise.cpp:25-28: k/P each, the LAST rank also takes all k%P extras."""
+    base, extra = divmod(k, P)
+    s = r * base
+    return s, s + base + (extra if r == P - 1 else 0)
+
+
+def partition_nnz(nnz: int, P: int, r: int) -> tuple[int, int]:
+    """NonZeroElement.cpp:24-39: the first nnz%P ranks take one more element."""
+    per, extra = divmod(nnz, P)
+    if r < extra:
+        s = r * (per + 1)
+        return s, s + per + 1
+    s = r * per + extra
+    return s, s + per
+
+
+class CudaCompute:
+    """Engine of the product path: CSR shards in HBM, multiply through libspmm_b200.so."""
+
+    def __init__(self, device: int | None = None, kernel: str = "auto", rowblocks: int = -1):
+        if not torch.cuda.is_available():
+            raise RuntimeError("sparsematrixmultiplicationmpi_b200 needs a CUDA device (no CPU fallback)")
+        _cabi.lib()  # fail loudly if the extension is not built
+        self.index = torch.cuda.current_device() if device is None else device
+        self.device = torch.device("cuda", self.index)
+        self.kernel = kernel
+        self.rowblocks = rowblocks
+
+    def upload(self, m: SparseMatrix) -> DeviceCSR:
+        return DeviceCSR.from_host(m, self.index, self.rowblocks)
+
+    def multiply(self, A: DeviceCSR, B: torch.Tensor, k: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """out[n_rows, k] = A * B[n_cols, k]; contiguous float64 tensors on self.device."""
+        assert B.is_cuda and B.dtype == torch.float64 and B.is_contiguous()
+        if out is None:
+            out = torch.empty((A.n_rows, k), dtype=torch.float64, device=self.device)
+        if A.n_rows and k:
+            A.multiply(B.data_ptr(), k, out.data_ptr(), self.kernel, torch.cuda.current_stream(self.device).cuda_stream)
+        return out
+
+    def multiply_slab(self, A: DeviceCSR, B: torch.Tensor, k: int, k_begin: int, k_count: int, out: torch.Tensor):
+        """Columns [k_begin, k_begin+k_count) of out = A * B, both with leading dimension k."""
+        if A.n_rows and k_count:
+            A.multiply_strided(B.data_ptr(), k, out.data_ptr(), k, k_begin, k_count, self.kernel,
+                               torch.cuda.current_stream(self.device).cuda_stream)
+        return out
+
+
+def _gather_rows_to_root(local: torch.Tensor, counts: list[int], k: int, group=None) -> torch.Tensor | None:
+    """Gatherv of row blocks to rank 0 (RowWise.cpp:85-87): equal-size padded blocks, trimmed at the root."""
+    rank, P = world(group)
+    if P == 1:
+        return local
+    pad_rows = max(counts)
+    send = local
+    if local.shape[0] != pad_rows:
+        send = torch.zeros((pad_rows, k), dtype=local.dtype, device=local.device)
+        send[:local.shape[0]] = local
+    if rank == 0:
+        recv = [torch.empty((pad_rows, k), dtype=local.dtype, device=local.device) for _ in range(P)]
+        dist.gather(send, recv, dst=0, group=group)
+        return torch.cat([recv[r][:counts[r]] for r in range(P)], dim=0)
+    dist.gather(send, None, dst=0, group=group)
+    return None
+
+
+class RowWise:
+    """Rank r owns rows [start,end) of A (RowWise.cpp:26-29) and the same rows of C."""
+
+    def __init__(self, compute, n_rows: int, k: int, local_A, group=None):
+        self.compute, self.n_rows, self.k, self.A, self.group = compute, n_rows, k, local_A, group
+        self.rank, self.P = world(group)
+        self.start, self.end = partition_rows(n_rows, self.P, self.rank)
+        self.counts = [partition_rows(n_rows, self.P, r)[1] - partition_rows(n_rows, self.P, r)[0]
+                       for r in range(self.P)]
+        assert local_A.n_rows == self.end - self.start
+
+    @classmethod
+    def from_host(cls, compute, m: SparseMatrix, k: int, group=None) -> "RowWise":
+        rank, P = world(group)
+        s, e = partition_rows(m.numRows, P, rank)
+        return cls(compute, m.numRows, k, compute.upload(m.row_block(s, e)), group)
+
+    def broadcast_B(self, B: torch.Tensor) -> torch.Tensor:
+        """B replicated from rank 0 (main.cpp:137 does this with MPI_Bcast, outside the timed region)."""
+        if self.P > 1:
+            dist.broadcast(B, src=0, group=self.group)
+        return B
+
+    def multiply_local(self, B: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        return self.compute.multiply(self.A, B, self.k, out)
+
+    def gather(self, C_local: torch.Tensor) -> torch.Tensor | None:
+        return _gather_rows_to_root(C_local, self.counts, self.k, self.group)
+
+    def all_gather(self, C_local: torch.Tensor) -> torch.Tensor:
+        """Full C on every rank (what an iterative caller needs as the next B)."""
+        if self.P == 1:
+            return C_local
+        pad = max(self.counts)
+        send = C_local
+        if C_local.shape[0] != pad:
+            send = torch.zeros((pad, self.k), dtype=C_local.dtype, device=C_local.device)
+            send[:C_local.shape[0]] = C_local
+        recv = torch.empty((self.P * pad, self.k), dtype=C_local.dtype, device=C_local.device)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        if all(c == pad for c in self.counts):
+            return recv
+        return torch.cat([recv[r * pad:r * pad + self.counts[r]] for r in range(self.P)], dim=0)
+
+    def run(self, B: torch.Tensor) -> torch.Tensor | None:
+        """The reference call: local rows, then Gatherv to rank 0; None on the other ranks."""
+        return self.gather(self.multiply_local(B))
+
+
+class ColumnBlocks:
+    """Rank r owns columns J_r of A (contiguous, RowWise-style split of numCols) and rows J_r of B.
+
+    Each rank produces a full-size partial C; reduce-scatter(sum) leaves rank r with rows R_r of
+    C (contiguous blocks of ceil(N/P) rows, zero padded at the end).
+    """
+
+    def __init__(self, compute, n_rows: int, n_cols: int, k: int, local_A, group=None):
+        self.compute, self.n_rows, self.n_cols, self.k, self.A, self.group = compute, n_rows, n_cols, k, local_A, group
+        self.rank, self.P = world(group)
+        self.col_start, self.col_end = partition_rows(n_cols, self.P, self.rank)
+        self.block = -(-n_rows // self.P)  # rows of C per rank after the reduce-scatter
+        assert local_A.n_rows == n_rows and local_A.n_cols == self.col_end - self.col_start
+
+    @classmethod
+    def from_host(cls, compute, m: SparseMatrix, k: int, group=None) -> "ColumnBlocks":
+        rank, P = world(group)
+        c0, c1 = partition_rows(m.numCols, P, rank)
+        keep = (m.colIndices >= c0) & (m.colIndices < c1)
+        csum = np.concatenate(([0], np.cumsum(keep, dtype=np.int64)))
+        local = SparseMatrix(m.values[keep], m.colIndices[keep] - c0, csum[m.rowPtr].astype(np.int32), m.numRows, c1 - c0)
+        return cls(compute, m.numRows, m.numCols, k, compute.upload(local), group)
+
+    def local_B(self, B_full: torch.Tensor) -> torch.Tensor:
+        return B_full[self.col_start:self.col_end].contiguous()
+
+    def multiply_local(self, B_local: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Partial C, (P*block) x k with the rows past n_rows zero."""
+        rows_pad = self.block * self.P
+        if out is None:
+            out = torch.empty((rows_pad, self.k), dtype=torch.float64, device=B_local.device)
+        if rows_pad > self.n_rows:
+            out[self.n_rows:].zero_()
+        self.compute.multiply(self.A, B_local, self.k, out[:self.n_rows])
+        return out
+
+    def reduce_scatter(self, partial: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty((self.block, self.k), dtype=partial.dtype, device=partial.device)
+        if self.P == 1:
+            out.copy_(partial[:self.block])
+            return out
+        dist.reduce_scatter_tensor(out, partial, op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+    def run(self, B_local: torch.Tensor) -> torch.Tensor | None:
+        mine = self.reduce_scatter(self.multiply_local(B_local))
+        counts = [max(0, min(self.block, self.n_rows - r * self.block)) for r in range(self.P)]
+        return _gather_rows_to_root(mine[:counts[self.rank]], counts, self.k, self.group)
+
+
+class ColumnSlabs:
+    """The reference's own column-wise strategy: rank r computes columns [s,e) of C (ColumnWise.cpp:25-48)."""
+
+    def __init__(self, compute, k: int, A, group=None):
+        self.compute, self.k, self.A, self.group = compute, k, A, group
+        self.rank, self.P = world(group)
+        self.k_start, self.k_end = partition_cols(k, self.P, self.rank)
+
+    @classmethod
+    def from_host(cls, compute, m: SparseMatrix, k: int, group=None) -> "ColumnSlabs":
+        return cls(compute, k, compute.upload(m), group)
+
+    def run(self, B: torch.Tensor) -> torch.Tensor | None:
+        n = self.A.n_rows
+        Cw = torch.zeros((n, self.k), dtype=torch.float64, device=B.device)
+        self.compute.multiply_slab(self.A, B, self.k, self.k_start, self.k_end - self.k_start, Cw)
+        if self.P == 1:
+            return Cw
+        # slab gather (ColumnWise.cpp:82-84) + root interleave (:109-126): slabs are disjoint column
+        # ranges of zero-initialised buffers, so a sum to the root is exactly the interleave.
+        dist.reduce(Cw, dst=0, op=dist.ReduceOp.SUM, group=self.group)
+        return Cw if self.rank == 0 else None
+
+
+class NonZeroRanges:
+    """Rank r owns elements [begin,end) of the non-zero stream (NonZeroElement.cpp:24-39).
+
+    Its shard is the CSR of the rows first_row..last_row clipped to that range, so the local
+    multiply yields complete rows inside the range and PARTIAL rows at its two ends. A row cut by
+    one or more range boundaries is owned by the lowest rank that holds a piece of it; the other
+    holders send their k-double partial to the owner, which adds them in rank order.
+    """
+
+    def __init__(self, compute, n_rows: int, k: int, local_A, first_row: int, last_row: int, starts_mid_row: bool,
+                 group=None):
+        self.compute, self.n_rows, self.k, self.A, self.group = compute, n_rows, k, local_A, group
+        self.rank, self.P = world(group)
+        self.first_row, self.last_row = first_row, last_row
+        meta = [first_row, last_row, int(starts_mid_row)]
+        if self.P > 1:
+            allm = [None] * self.P
+            dist.all_gather_object(allm, meta, group=self.group)
+        else:
+            allm = [meta]
+        self.meta = allm
+        # owner[r] = rank that owns rank r's first row; ranks with an empty range have last < first
+        self.owner_of_first = []
+        for r, (f, l, mid) in enumerate(allm):
+            o = r
+            if l >= f and mid:
+                o = r - 1
+                while o > 0 and (allm[o][1] < allm[o][0] or (allm[o][0] == f and allm[o][2])):
+                    o -= 1
+            self.owner_of_first.append(o)
+
+    @staticmethod
+    def shard_of(m: SparseMatrix, P: int, r: int):
+        """(local SparseMatrix, first_row, last_row, starts_mid_row) of rank r's non-zero range."""
+        b, e = partition_nnz(m.nnz, P, r)
+        if e <= b:
+            return SparseMatrix(np.empty(0), np.empty(0, np.int32), np.zeros(1, np.int32), 0, m.numCols), 0, -1, False
+        rp = m.rowPtr.astype(np.int64)
+        first = int(np.searchsorted(rp, b, side="right") - 1)
+        last = int(np.searchsorted(rp, e - 1, side="right") - 1)
+        local_rp = (np.clip(rp[first:last + 2], b, e) - b).astype(np.int32)
+        local = SparseMatrix(m.values[b:e], m.colIndices[b:e], local_rp, last - first + 1, m.numCols)
+        return local, first, last, bool(b > rp[first])
+
+    @classmethod
+    def from_host(cls, compute, m: SparseMatrix, k: int, group=None) -> "NonZeroRanges":
+        rank, P = world(group)
+        local, first, last, mid = cls.shard_of(m, P, rank)
+        return cls(compute, m.numRows, k, compute.upload(local), first, last, mid, group)
+
+    def multiply_local(self, B: torch.Tensor) -> torch.Tensor:
+        return self.compute.multiply(self.A, B, self.k)
+
+    def fix_boundaries(self, C_local: torch.Tensor) -> torch.Tensor:
+        """Peer-to-peer exchange of the cut rows; afterwards every rank holds complete values for the rows it owns."""
+        if self.P == 1:
+            return C_local
+        ops, recv_bufs = [], []
+        me = self.rank
+        if self.meta[me][1] >= self.meta[me][0] and self.owner_of_first[me] != me:
+            ops.append(dist.P2POp(dist.isend, C_local[0].contiguous(), self.owner_of_first[me], group=self.group))
+        for r in range(me + 1, self.P):
+            if self.meta[r][1] >= self.meta[r][0] and self.owner_of_first[r] == me:
+                buf = torch.empty(self.k, dtype=C_local.dtype, device=C_local.device)
+                recv_bufs.append((r, buf))
+                ops.append(dist.P2POp(dist.irecv, buf, r, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for r, buf in recv_bufs:  # ascending rank order: deterministic sum
+            C_local[self.meta[r][0] - self.first_row] += buf
+        return C_local
+
+    def owned_rows(self) -> tuple[int, int]:
+        f, l, _ = self.meta[self.rank]
+        if l < f:
+            return 0, 0
+        return (f + 1, l + 1) if self.owner_of_first[self.rank] != self.rank else (f, l + 1)
+
+    def run(self, B: torch.Tensor) -> torch.Tensor | None:
+        C_local = self.fix_boundaries(self.multiply_local(B))
+        lo, hi = self.owned_rows()
+        mine = C_local[lo - self.first_row:hi - self.first_row] if hi > lo else C_local[:0]
+        if self.P == 1:
+            out = torch.zeros((self.n_rows, self.k), dtype=torch.float64, device=B.device)
+            out[lo:hi] = mine
+            return out
+        # owned blocks are disjoint row ranges; rows nobody owns are empty rows (zero)
+        spans = []
+        for r in range(self.P):
+            f, l, _ = self.meta[r]
+            spans.append((0, 0) if l < f else ((f + 1, l + 1) if self.owner_of_first[r] != r else (f, l + 1)))
+        if self.rank == 0:
+            out = torch.zeros((self.n_rows, self.k), dtype=torch.float64, device=B.device)
+            out[lo:hi] = mine
+            ops = [dist.P2POp(dist.irecv, out[a:b], r, group=self.group) for r, (a, b) in enumerate(spans) if r and b > a]
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            return out
+        if hi > lo:
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, mine.contiguous(), 0, group=self.group)]):
+                w.wait()
+        return None

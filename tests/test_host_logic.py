@@ -1,0 +1,113 @@
+"""Host-side logic that needs no GPU: partitions, utils mirrors, MatrixMarket front end, generators, shards."""
+import os
+
+import numpy as np
+import pytest
+
+import sparsematrixmultiplicationmpi_b200 as spmm
+from sparsematrixmultiplicationmpi_b200 import _cabi, generators as gen
+from sparsematrixmultiplicationmpi_b200.strategies import NonZeroRanges
+from conftest import GOLDEN, random_csr
+
+
+@pytest.mark.parametrize("total,P", [(10, 3), (5, 6), (121192, 8), (0, 4), (7, 7), (2624331, 5), (64, 64)])
+def test_partitions_equal_oracle(oracle, total, P):
+    for r in range(P):
+        assert spmm.partition_rows(total, P, r) == oracle.partition("rows", total, P, r) == _cabi.partition_rows(total, P, r)
+        assert spmm.partition_cols(total, P, r) == oracle.partition("cols", total, P, r) == _cabi.partition_cols(total, P, r)
+        assert spmm.partition_nnz(total, P, r) == oracle.partition("nnz", total, P, r) == _cabi.partition_nnz(total, P, r)
+
+
+def test_generate_fat_vector_is_the_reference_sequence(golden_multiply):
+    assert np.array_equal(spmm.generateLargeFatVector(4, 3), golden_multiply["kat_B"])
+    assert np.array_equal(spmm.generateLargeFatVector(7, 5), golden_multiply["fatvec_7x5"])
+    assert np.array_equal(spmm.generateLargeFatVector(7, 5), spmm.generateLargeFatVector(7, 5))
+
+
+def test_serialize_roundtrip_and_compare():
+    a = spmm.generateLargeFatVector(6, 4)
+    flat = spmm.serialize(a)
+    assert flat.shape == (24,) and np.array_equal(flat, a.reshape(-1))
+    assert np.array_equal(spmm.deserialize(flat, 6, 4), a)
+    b = a.copy()
+    b[3, 2] += 5e-7
+    assert spmm.areMatricesEqual(a, b, 1e-6)
+    b[3, 2] += 1e-6
+    assert not spmm.areMatricesEqual(a, b, 1e-6)
+    assert not spmm.areMatricesEqual(a, a[:5], 1e-6)
+
+
+@pytest.mark.parametrize("name", ["general_unsorted", "symmetric", "pattern", "duplicates", "skew_symmetric",
+                                  "rectangular", "pattern_symmetric", "empty_rows", "random_symmetric"])
+def test_matrix_market_front_end_feeds_the_same_records(oracle, golden_loader, name):
+    path = os.path.join(GOLDEN, name + ".mtx")
+    nr, nc, rows, cols, vals, sym = spmm.parse_matrix_market(path)
+    onr, onc, orows, ocols, ovals, osym, _ = oracle.read_mtx_coo(path)
+    assert (nr, nc, sym) == (onr, onc, osym)
+    assert np.array_equal(rows, orows) and np.array_equal(cols, ocols)
+    assert np.array_equal(vals.view(np.uint64), ovals.view(np.uint64))
+    # and the oracle's CSR assembly of those records is the reference loader's output
+    rp, ci, va = oracle.csr_from_coo(nr, rows, cols, vals, sym)
+    assert np.array_equal(rp, golden_loader[f"{name}_rowptr"]) and np.array_equal(ci, golden_loader[f"{name}_colidx"])
+
+
+def test_matrix_market_errors(tmp_path):
+    with pytest.raises(RuntimeError, match="Unable to open file"):
+        spmm.parse_matrix_market(str(tmp_path / "nope.mtx"))
+    p = tmp_path / "short.mtx"
+    p.write_text("%%MatrixMarket matrix coordinate real general\n3 3 4\n1 1 1\n2 2 2\n")
+    with pytest.raises(RuntimeError, match="Failed to read data"):
+        spmm.parse_matrix_market(str(p))
+    p2 = tmp_path / "nosize.mtx"
+    p2.write_text("%%MatrixMarket matrix coordinate real general\n")
+    with pytest.raises(RuntimeError, match="Failed to read matrix dimensions"):
+        spmm.parse_matrix_market(str(p2))
+
+
+def test_cop20k_shaped_generator_hits_the_published_shape():
+    n, nc, r, c, v, sym = gen.cop20k_A_shaped()
+    assert (n, nc, sym) == (121192, 121192, True)
+    assert gen.expanded_nnz(r, c, sym) == 2624331  # report/425500_Report.tex:687
+    assert np.all(r >= c)  # lower triangle, MatrixMarket symmetric storage
+    deg = np.bincount(r, minlength=n) + np.bincount(c, minlength=n) - np.bincount(r[r == c], minlength=n)
+    assert deg.max() <= 81 and (deg == 0).sum() > 0
+    assert np.all((v >= 0.5) & (v < 1.5))
+    # banded: columns sit within +-2 grid planes (+ ring) of the diagonal
+    assert np.max(r - c) <= 2 * 49 * 49 + 2 * 49 + 2
+
+
+def test_uniform_random_generator_cfg1():
+    n, _, r, c, v, sym = gen.uniform_random(10_000, 10, seed=1)
+    assert r.size == 100_000 and not sym
+    key = r.astype(np.int64) * n + c
+    assert np.unique(key).size == key.size  # distinct columns in every row
+
+
+def test_nnz_shards_tile_the_stream(oracle):
+    rowptr, colidx, vals = random_csr(5, 120, 120, 6, long_row=700, empty_every=4)
+    m = spmm.SparseMatrix(vals, colidx, rowptr, 120, 120)
+    B = np.random.default_rng(1).integers(1, 101, (120, 3)).astype(np.float64)
+    for P in (1, 2, 5, 16):
+        total = np.zeros((120, 3))
+        covered = 0
+        for r in range(P):
+            local, first, last, mid = NonZeroRanges.shard_of(m, P, r)
+            b, e = spmm.partition_nnz(m.nnz, P, r)
+            covered += local.nnz
+            assert local.nnz == e - b
+            if local.nnz:
+                assert mid == (b > rowptr[first])
+                part = oracle.spmm(local.rowPtr, local.colIndices, local.values, B, 3)
+                total[first:last + 1] += part
+        assert covered == m.nnz
+        assert np.allclose(total, oracle.spmm(rowptr, colidx, vals, B, 3), rtol=1e-13, atol=1e-9)
+
+
+def test_product_package_never_touches_the_oracle():
+    """No file of the package may import, load or name anything under oracle/ (parity would be void)."""
+    pkg = os.path.dirname(spmm.__file__)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "pyoracle" not in text and "liboracle" not in text and "oracle_spmm" not in text, f
