@@ -164,12 +164,18 @@ class DeviceCSR:
         _cabi.check(_cabi.lib().spmm_multiply_nnz_range_device(self.handle, nnz_begin, nnz_end, first_row, last_row,
                                                                d_B, k, d_C_local, _cabi.KERNELS[kernel], stream))
 
-    def multiply_host(self, B: np.ndarray, k: int, kernel: str = "auto") -> np.ndarray:
-        """Host buffers in, host buffer out (the call the reference-shaped entry points make)."""
+    def multiply_host(self, B: np.ndarray, k: int, kernel: str = "auto", out: np.ndarray | None = None) -> np.ndarray:
+        """Host buffers in, host buffer out (the call the reference-shaped entry points make).
+        `out` lets a caller reuse a (pinned) result buffer instead of a fresh allocation."""
         B = as_fat_vector(B)
         if B.shape[0] < self.n_cols or B.shape[1] != k:
             raise ValueError(f"fat vector must be at least {self.n_cols} x {k}")
-        Cm = np.empty((self.n_rows, k), dtype=np.float64)
+        if out is not None:
+            if out.shape != (self.n_rows, k) or out.dtype != np.float64 or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous float64 array of shape (n_rows, k)")
+            Cm = out
+        else:
+            Cm = np.empty((self.n_rows, k), dtype=np.float64)
         _cabi.check(_cabi.lib().spmm_multiply_host(self.handle, B.ctypes.data, k, Cm.ctypes.data,
                                                    _cabi.KERNELS[kernel]))
         return Cm

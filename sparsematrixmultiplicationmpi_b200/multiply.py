@@ -83,12 +83,13 @@ def _to_host(Cd: torch.Tensor | None, k: int) -> np.ndarray:
     return Cd.cpu().numpy()
 
 
-def sparseMatrixFatVectorMultiply(sparseMatrix: SparseMatrix, fatVector, vecCols: int) -> np.ndarray:
-    """C = A * B on one B200 (the sequential reference function; no communication)."""
+def sparseMatrixFatVectorMultiply(sparseMatrix: SparseMatrix, fatVector, vecCols: int, out=None) -> np.ndarray:
+    """C = A * B on one B200 (the sequential reference function; no communication).
+    `out` (optional, not in the reference signature) reuses a caller-owned result buffer."""
     B = _check(sparseMatrix, fatVector, vecCols)
     eng = _engine()
     A = _cached(sparseMatrix, "seq", None, lambda: eng.upload(sparseMatrix))
-    return A.multiply_host(B, vecCols, eng.kernel)
+    return A.multiply_host(B, vecCols, eng.kernel, out)
 
 
 def sparseMatrixFatVectorMultiplyRowWise(sparseMatrix: SparseMatrix, fatVector, vecCols: int) -> np.ndarray:

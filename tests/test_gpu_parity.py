@@ -1,0 +1,363 @@
+"""Parity of the CUDA path against the oracle, through the C-ABI (include/spmm_b200.h). B200 only."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import sparsematrixmultiplicationmpi_b200 as spmm
+from sparsematrixmultiplicationmpi_b200 import _cabi, generators as gen
+from conftest import GOLDEN, REL_TOL, assert_close_rel, random_csr
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def gpu_multiply(m, B, k, kernel="auto", tune=None, rowblocks=0):
+    """C = A*B through spmm_multiply_device with device-resident operands."""
+    _cabi.tune("reset", 0)
+    for key, val in (tune or {}).items():
+        _cabi.tune(key, val)
+    try:
+        with spmm.DeviceCSR.from_host(m, 0, rowblocks) as A:
+            dB = dev(B)
+            dC = torch.full((m.numRows, k), np.nan, dtype=torch.float64, device="cuda")
+            A.multiply(dB.data_ptr(), k, dC.data_ptr(), kernel, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            return dC.cpu().numpy()
+    finally:
+        _cabi.tune("reset", 0)
+
+
+# ---------------------------------------------------------------- golden vectors (reference outputs)
+def test_kat_report_example(golden_multiply):
+    g = golden_multiply
+    m = spmm.SparseMatrix(g["kat_vals"], g["kat_colidx"], g["kat_rowptr"], 4, 4)
+    for kernel in ("rows", "merge"):
+        assert np.array_equal(gpu_multiply(m, g["kat_B"], 3, kernel), g["kat_C"])  # small integers: exact
+    assert np.array_equal(spmm.sparseMatrixFatVectorMultiply(m, g["kat_B"], 3), g["kat_C"])
+
+
+@pytest.mark.parametrize("name", ["small", "hub", "k1", "k8"])
+@pytest.mark.parametrize("kernel", ["rows", "merge"])
+def test_golden_cases(golden_multiply, name, kernel):
+    g = golden_multiply
+    rp, ci, va, B = g[f"{name}_rowptr"], g[f"{name}_colidx"], g[f"{name}_vals"], g[f"{name}_B"]
+    n, k = len(rp) - 1, B.shape[1]
+    got = gpu_multiply(spmm.SparseMatrix(va, ci, rp, n, n), B, k, kernel)
+    assert_close_rel(got, g[f"{name}_C_seq"], rp, ci, va, B)
+
+
+# ---------------------------------------------------------------- kernel families x k x shapes vs the oracle
+SHAPES = {
+    # name: (seed, n_rows, n_cols, mean_len, long_row, empty_every)
+    "short": (1, 3000, 3000, 4, None, 9),
+    "fem_like": (2, 2500, 2500, 22, None, 0),
+    "hub": (3, 1200, 1200, 6, 40000, 5),
+    "rect_wide": (4, 700, 5000, 12, None, 0),
+    "rect_tall": (5, 5000, 300, 3, None, 4),
+    "single_row": (6, 1, 64, 40, None, 0),
+    "all_empty": (7, 50, 50, 0, None, 0),
+}
+
+
+@pytest.mark.parametrize("shape", list(SHAPES))
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 7, 8, 12, 16, 32, 33, 64, 100, 128, 130, 300])
+@pytest.mark.parametrize("kernel", ["rows", "merge"])
+def test_kernels_vs_oracle(oracle, shape, k, kernel):
+    seed, n, nc, mean, long_row, empty_every = SHAPES[shape]
+    if shape == "hub" and k > 64:
+        pytest.skip("hub row x wide k: covered at k<=64")
+    rp, ci, va = random_csr(seed, n, nc, mean, long_row=long_row, empty_every=empty_every, positive=True)
+    B = np.random.default_rng(seed + k).integers(1, 101, (nc, k)).astype(np.float64)
+    ref = oracle.spmm(rp, ci, va, B, k)
+    got = gpu_multiply(spmm.SparseMatrix(va, ci, rp, n, nc), B, k, kernel)
+    # positive data: the north_star contract verbatim, |x-ref| <= 1e-12*|ref| per entry
+    assert_close_rel(got, ref, tol=REL_TOL)
+
+
+@pytest.mark.parametrize("tune", [
+    {"rows.kl": 32, "rows.nv": 1}, {"rows.kl": 16, "rows.nv": 2}, {"rows.kl": 8, "rows.nv": 4, "rows.unroll": 4},
+    {"rows.kl": 8, "rows.nv": 4, "rows.unroll": 1}, {"rows.vec": 1}, {"rows.vec": 1, "rows.kl": 32, "rows.nv": 2},
+    {"rows.ctas_per_sm": 1}, {"merge.items": 64}, {"merge.items": 4096},
+])
+@pytest.mark.parametrize("kernel", ["rows", "merge"])
+def test_team_shape_overrides(oracle, tune, kernel):
+    rp, ci, va = random_csr(11, 2000, 2000, 20, long_row=5000, empty_every=13, positive=True)
+    B = np.random.default_rng(5).integers(1, 101, (2000, 64)).astype(np.float64)
+    got = gpu_multiply(spmm.SparseMatrix(va, ci, rp, 2000, 2000), B, 64, kernel, tune)
+    assert_close_rel(got, oracle.spmm(rp, ci, va, B, 64), tol=REL_TOL)
+
+
+@pytest.mark.parametrize("np_", [1, 2, 4, 8, 16, 32])
+@pytest.mark.parametrize("k", [1, 2, 4, 8])
+def test_side_by_side_nonzeros(oracle, np_, k):
+    rp, ci, va = random_csr(12, 1500, 1500, 21, long_row=700, empty_every=10, positive=True)
+    B = np.random.default_rng(6).integers(1, 101, (1500, k)).astype(np.float64)
+    got = gpu_multiply(spmm.SparseMatrix(va, ci, rp, 1500, 1500), B, k, "rows", {"rows.np": np_, "rows.unroll": 2})
+    assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
+
+
+@pytest.mark.parametrize("R", [2, 4])
+@pytest.mark.parametrize("k", [8, 16, 32, 64, 128, 256])
+def test_rowblock_kernel(oracle, R, k):
+    rp, ci, va = random_csr(13, 2501, 2501, 20, empty_every=17, positive=True)  # 2501: last block is ragged
+    m = spmm.SparseMatrix(va, ci, rp, 2501, 2501)
+    B = np.random.default_rng(7).integers(1, 101, (2501, k)).astype(np.float64)
+    got = gpu_multiply(m, B, k, "rowblock", rowblocks=R)
+    assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
+    with spmm.DeviceCSR.from_host(m, 0, R) as A:
+        info = A.rowblock_info()
+        assert info["rows_per_block"] == R and 1.0 <= info["fill_ratio"] <= R
+
+
+def test_rowblock_duplicates_and_mixed_sign(oracle, golden_multiply):
+    g = golden_multiply  # golden rows hold duplicated columns and mixed-sign values
+    rp, ci, va, B = g["k8_rowptr"], g["k8_colidx"], g["k8_vals"], g["k8_B"]
+    m = spmm.SparseMatrix(va, ci, rp, len(rp) - 1, len(rp) - 1)
+    for R in (2, 4):
+        assert_close_rel(gpu_multiply(m, B, 8, "rowblock", rowblocks=R), g["k8_C_seq"], rp, ci, va, B)
+
+
+def test_rowblock_refuses_unsorted_rows():
+    m = spmm.SparseMatrix([1., 2.], [3, 1], [0, 2], 1, 4)
+    with spmm.DeviceCSR.from_host(m, 0, 0) as A:
+        with pytest.raises(_cabi.SpmmError):
+            A.build_rowblocks(2)
+        assert A.build_rowblocks(-1)["rows_per_block"] == 0  # auto: quietly keeps the CSR kernels
+        B = np.arange(8, dtype=np.float64).reshape(4, 2)
+        assert np.array_equal(A.multiply_host(B, 2), [[1 * 6 + 2 * 2, 1 * 7 + 2 * 3]])
+
+
+# ---------------------------------------------------------------- sub-ranges used by the strategies
+@pytest.mark.parametrize("kernel", ["rows", "merge"])
+def test_row_blocks_and_nnz_ranges(oracle, kernel):
+    n, k = 900, 16
+    rp, ci, va = random_csr(14, n, n, 9, long_row=6000, empty_every=6, positive=True)
+    m = spmm.SparseMatrix(va, ci, rp, n, n)
+    B = np.random.default_rng(8).integers(1, 101, (n, k)).astype(np.float64)
+    seq = oracle.spmm(rp, ci, va, B, k)
+    dB = dev(B)
+    with spmm.DeviceCSR.from_host(m, 0, 0) as A:
+        for P in (1, 3, 8):
+            # a4: every rank's row block
+            for r in range(P):
+                s, e = spmm.partition_rows(n, P, r)
+                out = torch.full((e - s, k), np.nan, dtype=torch.float64, device="cuda")
+                A.multiply_rows(s, e, dB.data_ptr(), k, out.data_ptr(), kernel)
+                assert_close_rel(out.cpu().numpy(), seq[s:e], tol=REL_TOL)
+            # a6: every rank's non-zero range; partial boundary rows summed in rank order
+            total = np.zeros((n, k))
+            for r in range(P):
+                b, e = spmm.partition_nnz(m.nnz, P, r)
+                first, last = A.nnz_range_rows(b, e)
+                assert rp[first] <= b < rp[first + 1] and rp[last] <= e - 1 < rp[last + 1]
+                out = torch.full((last - first + 1, k), np.nan, dtype=torch.float64, device="cuda")
+                A.multiply_nnz_range(b, e, first, last, dB.data_ptr(), k, out.data_ptr(), kernel)
+                total[first:last + 1] += out.cpu().numpy()
+            assert_close_rel(total, oracle.spmm(rp, ci, va, B, k, "nnz", P), tol=REL_TOL)
+
+
+def test_column_slabs_strided(oracle):
+    n, k = 800, 12
+    rp, ci, va = random_csr(15, n, n, 10, empty_every=8, positive=True)
+    B = np.random.default_rng(9).integers(1, 101, (n, k)).astype(np.float64)
+    seq = oracle.spmm(rp, ci, va, B, k)
+    dB = dev(B)
+    with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, n, n), 0, 0) as A:
+        for P in (1, 5, 16):  # 16 > k: leading ranks own no column, the last owns all extras (ColumnWise.cpp:25-28)
+            out = torch.zeros((n, k), dtype=torch.float64, device="cuda")
+            for r in range(P):
+                s, e = spmm.partition_cols(k, P, r)
+                A.multiply_strided(dB.data_ptr(), k, out.data_ptr(), k, s, e - s)
+            assert_close_rel(out.cpu().numpy(), seq, tol=REL_TOL)
+
+
+def test_column_block_submatrix(oracle):
+    n, k = 1000, 8
+    rp, ci, va = random_csr(16, n, n, 14, empty_every=5, positive=True)
+    B = np.random.default_rng(10).integers(1, 101, (n, k)).astype(np.float64)
+    with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, n, n), 0, 0) as A:
+        total = np.zeros((n, k))
+        nnz = 0
+        for r in range(3):
+            c0, c1 = spmm.partition_rows(n, 3, r)
+            with A.column_block(c0, c1) as S:
+                h = S.download()
+                keep = (ci >= c0) & (ci < c1)
+                assert np.array_equal(h.colIndices, ci[keep] - c0) and np.array_equal(h.values, va[keep])
+                nnz += h.nnz
+                total += S.multiply_host(B[c0:c1], k)
+        assert nnz == len(ci)
+        assert_close_rel(total, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
+
+
+# ---------------------------------------------------------------- CSR construction: bit-exact
+LOADER = ["general_unsorted", "symmetric", "pattern", "duplicates", "skew_symmetric", "rectangular",
+          "pattern_symmetric", "empty_rows", "random_symmetric"]
+
+
+@pytest.mark.parametrize("name", LOADER)
+def test_loader_bit_exact_vs_reference_golden(golden_loader, name):
+    m = spmm.readMatrixMarketFile(os.path.join(GOLDEN, name + ".mtx"))
+    g = golden_loader
+    assert [m.numRows, m.numCols] == g[f"{name}_shape"].tolist()
+    assert m.rowPtr.tobytes() == g[f"{name}_rowptr"].tobytes()
+    assert m.colIndices.tobytes() == g[f"{name}_colidx"].tobytes()
+    assert m.values.tobytes() == g[f"{name}_vals"].tobytes()
+
+
+def test_device_csr_build_bit_exact_on_cop20k_shape(oracle):
+    n, nc, r, c, v, sym = gen.cop20k_A_shaped()
+    with spmm.DeviceCSR.from_coo_host(n, nc, r, c, v, sym) as A:
+        got = A.download()
+        sched = A.schedule()
+    rp, ci, va = oracle.csr_from_coo(n, r, c, v, sym)
+    assert got.nnz == 2624331
+    assert got.rowPtr.tobytes() == rp.tobytes() and got.colIndices.tobytes() == ci.tobytes()
+    assert got.values.tobytes() == va.tobytes()
+    assert sum(sched["bins"].values()) == n and sched["max_row_len"] == int(np.diff(rp).max())
+    assert sched["bins"]["0"] == int((np.diff(rp) == 0).sum()) and sched["auto_kernel"] == "rows"
+
+
+def test_device_csr_build_ties_and_negative_zero(oracle):
+    rng = np.random.default_rng(3)
+    m = 20000
+    r, c = rng.integers(0, 50, m), rng.integers(0, 50, m)
+    v = rng.choice([-2.5, -1.0, 1.0, 1.0, 3.25, 1e-300, -1e300], m)
+    with spmm.DeviceCSR.from_coo_host(50, 50, r, c, v, False) as A:
+        got = A.download()
+    rp, ci, va = oracle.csr_from_coo(50, r, c, v, False)
+    assert got.rowPtr.tobytes() == rp.tobytes() and got.colIndices.tobytes() == ci.tobytes()
+    assert got.values.tobytes() == va.tobytes()
+
+
+def test_csr_build_rejects_out_of_range():
+    with pytest.raises(_cabi.SpmmError):
+        spmm.DeviceCSR.from_coo_host(3, 3, [0, 3], [0, 0], [1., 2.])
+    with pytest.raises(_cabi.SpmmError):
+        spmm.DeviceCSR.from_coo_host(2, 4, [0], [3], [1.], symmetric=True)  # mirror would leave the matrix
+
+
+def test_upload_download_roundtrip_is_bitwise():
+    rp, ci, va = random_csr(17, 500, 700, 8, long_row=900, empty_every=3)
+    with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, 500, 700), 0, 0) as A:
+        h = A.download()
+    assert h.rowPtr.tobytes() == rp.tobytes() and h.colIndices.tobytes() == ci.tobytes() and h.values.tobytes() == va.tobytes()
+
+
+# ---------------------------------------------------------------- the reference-shaped entry points (host buffers)
+def test_entry_points_single_rank(oracle):
+    n, _, r, c, v, sym = gen.uniform_random(10_000, 10, seed=1)  # BASELINE.json configs[0]
+    rp, ci, va = oracle.csr_from_coo(n, r, c, v, sym)
+    m = spmm.SparseMatrix(va, ci, rp, n, n)
+    B = spmm.generateLargeFatVector(n, 4)
+    seq = oracle.spmm(rp, ci, va, B, 4)
+    for fn in (spmm.sparseMatrixFatVectorMultiply, spmm.sparseMatrixFatVectorMultiplyRowWise,
+               spmm.sparseMatrixFatVectorMultiplyColumnWise, spmm.sparseMatrixFatVectorMultiplyNonZeroElement):
+        got = fn(m, B, 4)
+        assert_close_rel(got, seq, tol=REL_TOL)
+        assert spmm.areMatricesEqual(got, seq, 1e-6)  # the reference's own runtime check (main.cpp:184)
+    got = spmm.sparseMatrixFatVectorMultiplyColumnWise(m, B, 4, mode="slabs")
+    assert_close_rel(got, seq, tol=REL_TOL)
+    got = spmm.sparseMatrixFatVectorMultiply(m, [list(row) for row in B], 4)  # vector<vector<double>> shape
+    assert_close_rel(got, seq, tol=REL_TOL)
+    spmm.clear_cache()
+
+
+def test_entry_point_argument_errors():
+    m = spmm.SparseMatrix([1.], [0], [0, 1], 1, 2)
+    with pytest.raises(RuntimeError):
+        spmm.sparseMatrixFatVectorMultiply(m, np.ones((1, 3)), 3)  # fat vector shorter than numCols
+    with pytest.raises(RuntimeError):
+        spmm.sparseMatrixFatVectorMultiply(m, np.ones((2, 3)), -1)
+    assert spmm.sparseMatrixFatVectorMultiply(m, np.ones((2, 3)), 0).shape == (1, 0)
+
+
+# ---------------------------------------------------------------- BASELINE.json full sizes: size-independent properties
+def test_cop20k_shape_all_k_vs_oracle_and_properties(oracle):
+    n, nc, r, c, v, sym = gen.cop20k_A_shaped()
+    with spmm.DeviceCSR.from_coo_host(n, nc, r, c, v, sym) as A:
+        host = A.download()
+        rb = A.build_rowblocks(-1)
+        for k in (1, 8, 32, 64):
+            B = np.random.default_rng(k).integers(1, 101, (n, k)).astype(np.float64)
+            ref = oracle.spmm(host.rowPtr, host.colIndices, host.values, B, k)
+            dB = dev(B)
+            kernels = ["rows", "merge"] + (["rowblock"] if rb["rows_per_block"] else [])
+            for kernel in kernels + ["auto"]:
+                dC = torch.full((n, k), np.nan, dtype=torch.float64, device="cuda")
+                A.multiply(dB.data_ptr(), k, dC.data_ptr(), kernel)
+                assert_close_rel(dC.cpu().numpy(), ref, tol=REL_TOL)
+        # symmetry of A (pattern and values): x^T (A y) == y^T (A x) up to rounding
+        x, y = torch.rand(n, 1, dtype=torch.float64, device="cuda"), torch.rand(n, 1, dtype=torch.float64, device="cuda")
+        Ax, Ay = torch.empty_like(x), torch.empty_like(y)
+        A.multiply(x.data_ptr(), 1, Ax.data_ptr())
+        A.multiply(y.data_ptr(), 1, Ay.data_ptr())
+        assert abs(float((x * Ay).sum() - (y * Ax).sum())) <= 1e-9 * float((x * Ay).sum())
+
+
+def test_large_banded_properties():
+    """2^22 x 2^22 banded, 32 per row (cfg4's shape at 1/8 size): checksum and linearity properties."""
+    n, k = 1 << 22, 16
+    with spmm.DeviceCSR.banded(n, 32, 4096, seed=7) as A:
+        ones = torch.ones((n, k), dtype=torch.float64, device="cuda")
+        C1 = torch.empty((n, k), dtype=torch.float64, device="cuda")
+        A.multiply(ones.data_ptr(), k, C1.data_ptr())
+        vals = A.download().values.reshape(n, 32)
+        rowsum = torch.from_numpy(vals).cuda().sum(dim=1, keepdim=True)
+        # A * ones == row sums in every column
+        assert torch.allclose(C1, rowsum.expand(n, k), rtol=1e-12, atol=0)
+        # linearity: A(2x + y) == 2 A x + A y
+        x = torch.randint(1, 101, (n, k), device="cuda").double()
+        y = torch.randint(1, 101, (n, k), device="cuda").double()
+        Cx, Cy, Cz = (torch.empty((n, k), dtype=torch.float64, device="cuda") for _ in range(3))
+        z = 2 * x + y
+        for src, dst in ((x, Cx), (y, Cy), (z, Cz)):
+            A.multiply(src.data_ptr(), k, dst.data_ptr())
+        assert torch.allclose(Cz, 2 * Cx + Cy, rtol=1e-12, atol=0)
+        # a row block generated alone is bit-identical to the same rows of the whole matrix
+        s, e = spmm.partition_rows(n, 8, 3)
+        with spmm.DeviceCSR.banded(n, 32, 4096, seed=7, row_begin=s, row_end=e) as blk:
+            hb = blk.download()
+            assert hb.values.tobytes() == vals[s:e].tobytes()
+            Cb = torch.empty((e - s, k), dtype=torch.float64, device="cuda")
+            blk.multiply(x.data_ptr(), k, Cb.data_ptr())
+            assert torch.equal(Cb, Cx[s:e])
+
+
+def test_rmat_merge_equals_rows_kernel():
+    """R-MAT scale 18 (cfg3's family): power-law rows; merge-path and row kernels agree, schedule picks merge."""
+    with spmm.DeviceCSR.rmat(18, 16 << 18, seed=3) as A:
+        n, k = A.n_rows, 32
+        sched = A.schedule()
+        assert sched["max_row_len"] > 1000 and sched["bins"]["0"] > 0
+        B = torch.randint(1, 101, (n, k), device="cuda").double()
+        Cr, Cm = torch.empty((n, k), dtype=torch.float64, device="cuda"), torch.empty((n, k), dtype=torch.float64, device="cuda")
+        A.multiply(B.data_ptr(), k, Cr.data_ptr(), "rows")
+        A.multiply(B.data_ptr(), k, Cm.data_ptr(), "merge")
+        assert torch.allclose(Cr, Cm, rtol=1e-12, atol=0)
+        host = A.download()
+        assert np.all(np.diff(host.rowPtr) >= 0) and host.rowPtr[-1] == 16 << 18
+        # rows sorted by (column, value) as the loader leaves them
+        rows = np.repeat(np.arange(n), np.diff(host.rowPtr))
+        order = np.lexsort((host.values, host.colIndices, rows))
+        assert np.array_equal(order, np.arange(host.nnz))
+
+
+def test_strategy_classes_on_one_gpu(oracle):
+    rp, ci, va = random_csr(19, 3000, 3000, 15, long_row=4000, empty_every=7, positive=True)
+    m = spmm.SparseMatrix(va, ci, rp, 3000, 3000)
+    B = np.random.default_rng(2).integers(1, 101, (3000, 16)).astype(np.float64)
+    seq = oracle.spmm(rp, ci, va, B, 16)
+    eng = spmm.CudaCompute()
+    dB = dev(B)
+    assert_close_rel(spmm.RowWise.from_host(eng, m, 16).run(dB).cpu().numpy(), seq, tol=REL_TOL)
+    blk = spmm.ColumnBlocks.from_host(eng, m, 16)
+    assert_close_rel(blk.run(blk.local_B(dB)).cpu().numpy(), seq, tol=REL_TOL)
+    assert_close_rel(spmm.ColumnSlabs.from_host(eng, m, 16).run(dB).cpu().numpy(), seq, tol=REL_TOL)
+    assert_close_rel(spmm.NonZeroRanges.from_host(eng, m, 16).run(dB).cpu().numpy(), seq, tol=REL_TOL)
