@@ -53,6 +53,43 @@ const DeviceProps &device_props(int device)
     return cache[device] = p;
 }
 
+int cached_bounds(const spmm_csr_s *A, int kind, int grid, cudaStream_t stream, const int **out,
+                  const std::function<void(int *)> &fill)
+{
+    const long long key = ((long long)kind << 32) | (unsigned)grid;
+    auto it = A->bounds.find(key);
+    if (it == A->bounds.end())
+    {
+        int *d = nullptr;
+        SPMM_CUDA(cudaMalloc(&d, sizeof(int) * ((size_t)grid + 1)));
+        fill(d);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess)
+        {
+            cudaFree(d);
+            return cuda_fail(e, "CTA cut kernel", __FILE__, __LINE__);
+        }
+        it = A->bounds.emplace(key, d).first;
+    }
+    (void)stream;
+    *out = it->second;
+    return SPMM_OK;
+}
+
+void drop_bounds(spmm_csr_s *A, int kind)
+{
+    for (auto it = A->bounds.begin(); it != A->bounds.end();)
+    {
+        if (kind < 0 || (int)(it->first >> 32) == kind)
+        {
+            cudaFree(it->second);
+            it = A->bounds.erase(it);
+        }
+        else
+            ++it;
+    }
+}
+
 // ---- row-length schedule ----------------------------------------------------------
 __global__ void schedule_kernel(const int *__restrict__ rowptr, int n_rows, unsigned long long *bins, int *max_len)
 {
@@ -290,6 +327,7 @@ int spmm_csr_destroy(spmm_csr_t A)
         cudaFree(A->d_vals);
     }
     free_rowblocks(A);
+    drop_bounds(A, -1);
     cudaFree(A->d_B);
     cudaFree(A->d_C);
     cudaFree(A->d_carry);

@@ -114,8 +114,8 @@ int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_l
     args.nnz_hi = (int)nnz_hi;
     args.c_row0 = c_row0;
     args.kc = kc;
-    return s.w == 2 ? launch_rows_w2(s.kl, s.nv, np, u, args, s.tiles, A->device, stream)
-                    : launch_rows_w1(s.kl, s.nv, np, u, args, s.tiles, A->device, stream);
+    return s.w == 2 ? launch_rows_w2(A, s.kl, s.nv, np, u, args, s.tiles, A->device, stream)
+                    : launch_rows_w1(A, s.kl, s.nv, np, u, args, s.tiles, A->device, stream);
 }
 
 int launch_merge(spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,

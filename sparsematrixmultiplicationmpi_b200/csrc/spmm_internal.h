@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <functional>
+#include <map>
 #include <string>
 
 #include "spmm_b200.h"
@@ -83,6 +85,8 @@ struct spmm_csr_s
     long long rb_entries = 0;
     int *d_blkptr = nullptr, *d_ucol = nullptr;
     double *d_uval = nullptr;
+    // precomputed CTA cuts per (kind, grid size): kind 0 = rows of the CSR, 1 = row blocks
+    mutable std::map<long long, int *> bounds;
     // merge-path scratch (carry rows), grown on demand
     double *d_carry = nullptr;
     int *d_carry_row = nullptr;
@@ -102,6 +106,10 @@ bool rowblock_shape_ok(int w, int kl, int nv, int tiles, int kc);
 int launch_rowblock(const spmm_csr_s *A, int w, int kl, int nv, int tiles, const double *d_B, long long ldb,
                     double *d_C, long long ldc, cudaStream_t stream);
 void free_rowblocks(spmm_csr_s *A);
+// CTA cuts cached on the handle; `fill` launches the kernel that computes grid+1 cuts into its argument
+int cached_bounds(const spmm_csr_s *A, int kind, int grid, cudaStream_t stream, const int **out,
+                  const std::function<void(int *)> &fill);
+void drop_bounds(spmm_csr_s *A, int kind); // kind < 0: all
 // handle plumbing shared by spmm_capi.cu and csr_build.cu
 int make_handle(int device, int n_rows, int n_cols, long long nnz, spmm_csr_s **out);
 int alloc_arrays(spmm_csr_s *A);

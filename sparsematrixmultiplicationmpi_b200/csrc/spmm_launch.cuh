@@ -52,7 +52,7 @@ int kernel_info(K kern, int *ctas_per_sm)
 }
 
 template <int KL, int NV, int W, int NP, int U, bool FULL>
-int launch_rows_full(const SpmmArgs &args, int tiles, int device, cudaStream_t stream)
+int launch_rows_full(const spmm_csr_s *A, const SpmmArgs &args, int tiles, int device, cudaStream_t stream)
 {
     auto kern = spmm_rows_kernel<KL, NV, W, NP, U, FULL, THREADS>;
     int per_sm = 1;
@@ -66,99 +66,111 @@ int launch_rows_full(const SpmmArgs &args, int tiles, int device, cudaStream_t s
     const long long rows = (long long)args.row_end - args.row_begin;
     long long grid = (long long)device_props(device).sm_count * per_sm;
     grid = std::max(1LL, std::min(grid, (rows + SLOTS - 1) / SLOTS));
-    kern<<<dim3((unsigned)grid, (unsigned)tiles), THREADS, 0, stream>>>(args);
+    SpmmArgs a2 = args;
+    a2.bounds = nullptr;
+    if (args.row_begin == 0 && args.row_end == A->n_rows && args.nnz_lo == 0 && args.nnz_hi == A->nnz)
+    {
+        // whole matrix: the equal-cost CTA cuts are part of the handle's schedule
+        rc = cached_bounds(A, 0, (int)grid, stream, &a2.bounds, [&](int *out) {
+            chunk_bounds_kernel<<<((unsigned)grid + 256) / 256, 256, 0, stream>>>(args.rowptr, A->n_rows, (int)A->nnz,
+                                                                             (int)grid, out);
+        });
+        if (rc)
+            return rc;
+    }
+    kern<<<dim3((unsigned)grid, (unsigned)tiles), THREADS, 0, stream>>>(a2);
     SPMM_CUDA(cudaGetLastError());
     return SPMM_OK;
 }
 
 template <int KL, int NV, int W, int NP, int U>
-int launch_rows_one(const SpmmArgs &args, int tiles, int device, cudaStream_t stream)
+int launch_rows_one(const spmm_csr_s *A, const SpmmArgs &args, int tiles, int device, cudaStream_t stream)
 {
     // FULL: the k columns fill every chunk of every column tile
     if (args.kc == tiles * KL * NV * W)
-        return launch_rows_full<KL, NV, W, NP, U, true>(args, tiles, device, stream);
-    return launch_rows_full<KL, NV, W, NP, U, false>(args, tiles, device, stream);
+        return launch_rows_full<KL, NV, W, NP, U, true>(A, args, tiles, device, stream);
+    return launch_rows_full<KL, NV, W, NP, U, false>(A, args, tiles, device, stream);
 }
 
 template <int KL, int NV, int W, int NP>
-int launch_rows_u(int u, const SpmmArgs &a, int tiles, int dev, cudaStream_t s)
+int launch_rows_u(const spmm_csr_s *A, int u, const SpmmArgs &a, int tiles, int dev, cudaStream_t s)
 {
     if constexpr (NP >= 8)
     {
         if (u >= 2)
-            return launch_rows_one<KL, NV, W, NP, 2>(a, tiles, dev, s);
-        return launch_rows_one<KL, NV, W, NP, 1>(a, tiles, dev, s);
+            return launch_rows_one<KL, NV, W, NP, 2>(A, a, tiles, dev, s);
+        return launch_rows_one<KL, NV, W, NP, 1>(A, a, tiles, dev, s);
     }
     else if constexpr (NP >= 2)
     {
         if (u >= 4)
-            return launch_rows_one<KL, NV, W, NP, 4>(a, tiles, dev, s);
+            return launch_rows_one<KL, NV, W, NP, 4>(A, a, tiles, dev, s);
         if (u >= 2)
-            return launch_rows_one<KL, NV, W, NP, 2>(a, tiles, dev, s);
-        return launch_rows_one<KL, NV, W, NP, 1>(a, tiles, dev, s);
+            return launch_rows_one<KL, NV, W, NP, 2>(A, a, tiles, dev, s);
+        return launch_rows_one<KL, NV, W, NP, 1>(A, a, tiles, dev, s);
     }
     else
     {
         if constexpr (NV <= 2)
             if (u >= 8)
-                return launch_rows_one<KL, NV, W, NP, 8>(a, tiles, dev, s);
+                return launch_rows_one<KL, NV, W, NP, 8>(A, a, tiles, dev, s);
         if (u >= 4)
-            return launch_rows_one<KL, NV, W, NP, 4>(a, tiles, dev, s);
+            return launch_rows_one<KL, NV, W, NP, 4>(A, a, tiles, dev, s);
         if (u >= 2)
-            return launch_rows_one<KL, NV, W, NP, 2>(a, tiles, dev, s);
-        return launch_rows_one<KL, NV, W, NP, 1>(a, tiles, dev, s);
+            return launch_rows_one<KL, NV, W, NP, 2>(A, a, tiles, dev, s);
+        return launch_rows_one<KL, NV, W, NP, 1>(A, a, tiles, dev, s);
     }
 }
 
 template <int KL, int W>
-int launch_rows_np(int np, int u, const SpmmArgs &a, int tiles, int dev, cudaStream_t s)
+int launch_rows_np(const spmm_csr_s *A, int np, int u, const SpmmArgs &a, int tiles, int dev, cudaStream_t s)
 {
     constexpr int MAXNP = 32 / KL;
     np = std::max(1, std::min(np, MAXNP));
 #define SPMM_NP_CASE(N)           \
     if constexpr (N <= MAXNP)     \
         if (np >= N)              \
-            return launch_rows_u<KL, 1, W, N>(u, a, tiles, dev, s);
+            return launch_rows_u<KL, 1, W, N>(A, u, a, tiles, dev, s);
     SPMM_NP_CASE(32)
     SPMM_NP_CASE(16)
     SPMM_NP_CASE(8)
     SPMM_NP_CASE(4)
     SPMM_NP_CASE(2)
 #undef SPMM_NP_CASE
-    return launch_rows_u<KL, 1, W, 1>(u, a, tiles, dev, s);
+    return launch_rows_u<KL, 1, W, 1>(A, u, a, tiles, dev, s);
 }
 
 template <int W>
-int launch_rows_shape(int kl, int nv, int np, int u, const SpmmArgs &a, int tiles, int dev, cudaStream_t s)
+int launch_rows_shape(const spmm_csr_s *A, int kl, int nv, int np, int u, const SpmmArgs &a, int tiles, int dev, cudaStream_t s)
 {
     if (nv == 1)
     {
         switch (kl)
         {
-        case 1: return launch_rows_np<1, W>(np, u, a, tiles, dev, s);
-        case 2: return launch_rows_np<2, W>(np, u, a, tiles, dev, s);
-        case 4: return launch_rows_np<4, W>(np, u, a, tiles, dev, s);
-        case 8: return launch_rows_np<8, W>(np, u, a, tiles, dev, s);
-        case 16: return launch_rows_np<16, W>(np, u, a, tiles, dev, s);
-        case 32: return launch_rows_np<32, W>(np, u, a, tiles, dev, s);
+        case 1: return launch_rows_np<1, W>(A, np, u, a, tiles, dev, s);
+        case 2: return launch_rows_np<2, W>(A, np, u, a, tiles, dev, s);
+        case 4: return launch_rows_np<4, W>(A, np, u, a, tiles, dev, s);
+        case 8: return launch_rows_np<8, W>(A, np, u, a, tiles, dev, s);
+        case 16: return launch_rows_np<16, W>(A, np, u, a, tiles, dev, s);
+        case 32: return launch_rows_np<32, W>(A, np, u, a, tiles, dev, s);
         }
     }
     else if (nv == 2)
     {
         switch (kl)
         {
-        case 8: return launch_rows_u<8, 2, W, 1>(u, a, tiles, dev, s);
-        case 16: return launch_rows_u<16, 2, W, 1>(u, a, tiles, dev, s);
-        case 32: return launch_rows_u<32, 2, W, 1>(u, a, tiles, dev, s);
+        case 8: return launch_rows_u<8, 2, W, 1>(A, u, a, tiles, dev, s);
+        case 16: return launch_rows_u<16, 2, W, 1>(A, u, a, tiles, dev, s);
+        case 32: return launch_rows_u<32, 2, W, 1>(A, u, a, tiles, dev, s);
         }
     }
     else if (nv == 4)
     {
         switch (kl)
         {
-        case 8: return launch_rows_u<8, 4, W, 1>(u, a, tiles, dev, s);
-        case 16: return launch_rows_u<16, 4, W, 1>(u, a, tiles, dev, s);
-        case 32: return launch_rows_u<32, 4, W, 1>(u, a, tiles, dev, s);
+        case 8: return launch_rows_u<8, 4, W, 1>(A, u, a, tiles, dev, s);
+        case 16: return launch_rows_u<16, 4, W, 1>(A, u, a, tiles, dev, s);
+        case 32: return launch_rows_u<32, 4, W, 1>(A, u, a, tiles, dev, s);
         }
     }
     set_error("rows kernel: unsupported team shape kl=" + std::to_string(kl) + " nv=" + std::to_string(nv));
@@ -225,8 +237,8 @@ int launch_merge_shape(int kl, int nv, int u, const SpmmArgs &a, int tiles, cuda
 }
 
 // entry points of the two per-W translation units
-int launch_rows_w1(int kl, int nv, int np, int u, const SpmmArgs &a, int tiles, int dev, cudaStream_t s);
-int launch_rows_w2(int kl, int nv, int np, int u, const SpmmArgs &a, int tiles, int dev, cudaStream_t s);
+int launch_rows_w1(const spmm_csr_s *A, int kl, int nv, int np, int u, const SpmmArgs &a, int tiles, int dev, cudaStream_t s);
+int launch_rows_w2(const spmm_csr_s *A, int kl, int nv, int np, int u, const SpmmArgs &a, int tiles, int dev, cudaStream_t s);
 int launch_merge_w1(int kl, int nv, int u, const SpmmArgs &a, int tiles, cudaStream_t s);
 int launch_merge_w2(int kl, int nv, int u, const SpmmArgs &a, int tiles, cudaStream_t s);
 

@@ -95,6 +95,7 @@ struct RbArgs
     double *C;
     long long ldb, ldc;
     int n_rows, n_blocks;
+    const int *bounds; // CTA cuts over row blocks (gridDim.x+1 entries)
 };
 
 __device__ __forceinline__ void ld_vals(const double *p, double (&x)[2])
@@ -131,6 +132,15 @@ __device__ __forceinline__ int rb_lower_bound(const int *__restrict__ blkptr, in
     return lo;
 }
 
+__global__ void rb_bounds_kernel(const int *blkptr, int n_blocks, int grid, int *bounds)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > grid)
+        return;
+    const long long total = (long long)blkptr[n_blocks] + (long long)RB_BLOCK_COST * n_blocks;
+    bounds[b] = b == 0 ? 0 : (b == grid ? n_blocks : rb_lower_bound(blkptr, n_blocks, (total * b + grid - 1) / grid));
+}
+
 // A team of KL lanes owns one row block (R rows) at a time; 32/KL teams per warp; every
 // CTA sweeps one contiguous, equal-cost run of row blocks (same reasoning as the row kernel).
 template <int R, int KL, int NV, int W, int U, int THREADS_>
@@ -141,13 +151,8 @@ __global__ void __launch_bounds__(THREADS_) spmm_rowblock_kernel(const RbArgs a)
     using S = Slice<KL, NV, W>;
 
     __shared__ int s_chunk[2];
-    if (threadIdx.x == 0)
-    {
-        const long long total = (long long)a.blkptr[a.n_blocks] + (long long)RB_BLOCK_COST * a.n_blocks;
-        const long long g = gridDim.x, b = blockIdx.x;
-        s_chunk[0] = b == 0 ? 0 : rb_lower_bound(a.blkptr, a.n_blocks, (total * b + g - 1) / g);
-        s_chunk[1] = b == g - 1 ? a.n_blocks : rb_lower_bound(a.blkptr, a.n_blocks, (total * (b + 1) + g - 1) / g);
-    }
+    if (threadIdx.x < 2)
+        s_chunk[threadIdx.x] = a.bounds[blockIdx.x + threadIdx.x];
     __syncthreads();
     const int lo = s_chunk[0], hi = s_chunk[1];
 
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(THREADS_) spmm_rowblock_kernel(const RbArgs a)
 }
 
 template <int R, int KL, int NV, int W, int U>
-int launch_rb_one(const RbArgs &args, int tiles, int device, cudaStream_t stream)
+int launch_rb_one(const spmm_csr_s *A, const RbArgs &args, int tiles, int device, cudaStream_t stream)
 {
     auto kern = spmm_rowblock_kernel<R, KL, NV, W, U, THREADS>;
     int per_sm = 1;
@@ -229,20 +234,26 @@ int launch_rb_one(const RbArgs &args, int tiles, int device, cudaStream_t stream
     constexpr int SLOTS = (THREADS / 32) * (32 / KL);
     long long grid = (long long)device_props(device).sm_count * per_sm;
     grid = std::max(1LL, std::min(grid, ((long long)args.n_blocks + SLOTS - 1) / SLOTS));
-    kern<<<dim3((unsigned)grid, (unsigned)tiles), THREADS, 0, stream>>>(args);
+    RbArgs a2 = args;
+    rc = cached_bounds(A, 1, (int)grid, stream, &a2.bounds, [&](int *out) {
+        rb_bounds_kernel<<<((unsigned)grid + 256) / 256, 256, 0, stream>>>(args.blkptr, args.n_blocks, (int)grid, out);
+    });
+    if (rc)
+        return rc;
+    kern<<<dim3((unsigned)grid, (unsigned)tiles), THREADS, 0, stream>>>(a2);
     SPMM_CUDA(cudaGetLastError());
     return SPMM_OK;
 }
 
 template <int R, int W>
-int launch_rb_shape(int kl, int nv, int u, const RbArgs &a, int tiles, int dev, cudaStream_t s)
+int launch_rb_shape(const spmm_csr_s *A, int kl, int nv, int u, const RbArgs &a, int tiles, int dev, cudaStream_t s)
 {
 #define SPMM_RB_CASE(K, N)                                    \
     if (kl == K && nv == N)                                   \
     {                                                         \
         if (u >= 2)                                           \
-            return launch_rb_one<R, K, N, W, 2>(a, tiles, dev, s); \
-        return launch_rb_one<R, K, N, W, 1>(a, tiles, dev, s);    \
+            return launch_rb_one<R, K, N, W, 2>(A, a, tiles, dev, s); \
+        return launch_rb_one<R, K, N, W, 1>(A, a, tiles, dev, s);    \
     }
     SPMM_RB_CASE(4, 1)
     SPMM_RB_CASE(8, 1)
@@ -279,13 +290,14 @@ int launch_rowblock(const spmm_csr_s *A, int w, int kl, int nv, int tiles, const
     args.ldc = ldc;
     args.n_rows = A->n_rows;
     args.n_blocks = A->rb_blocks;
+    args.bounds = nullptr;
     int rc = -1;
     if (A->rb_R == 2)
-        rc = w == 2 ? launch_rb_shape<2, 2>(kl, nv, u, args, tiles, A->device, stream)
-                    : launch_rb_shape<2, 1>(kl, nv, u, args, tiles, A->device, stream);
+        rc = w == 2 ? launch_rb_shape<2, 2>(A, kl, nv, u, args, tiles, A->device, stream)
+                    : launch_rb_shape<2, 1>(A, kl, nv, u, args, tiles, A->device, stream);
     else if (A->rb_R == 4)
-        rc = w == 2 ? launch_rb_shape<4, 2>(kl, nv, u, args, tiles, A->device, stream)
-                    : launch_rb_shape<4, 1>(kl, nv, u, args, tiles, A->device, stream);
+        rc = w == 2 ? launch_rb_shape<4, 2>(A, kl, nv, u, args, tiles, A->device, stream)
+                    : launch_rb_shape<4, 1>(A, kl, nv, u, args, tiles, A->device, stream);
     if (rc == -1)
     {
         set_error("row-block kernel: unsupported shape");
@@ -296,6 +308,7 @@ int launch_rowblock(const spmm_csr_s *A, int w, int kl, int nv, int tiles, const
 
 void free_rowblocks(spmm_csr_s *A)
 {
+    drop_bounds(A, 1);
     cudaFree(A->d_blkptr);
     cudaFree(A->d_ucol);
     cudaFree(A->d_uval);
