@@ -229,6 +229,8 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "rows.kl") t.rows_kl = value;
     else if (k == "rows.nv") t.rows_nv = value;
     else if (k == "rowblock") t.rowblock = value;
+    else if (k == "rows.sweep") t.rows_sweep = value;
+    else if (k == "rows.threads") t.rows_threads = value;
     else if (k == "rows.unroll") t.rows_unroll = value;
     else if (k == "rows.vec") t.rows_vec = value;
     else if (k == "rows.ctas_per_sm") t.rows_ctas_per_sm = value;

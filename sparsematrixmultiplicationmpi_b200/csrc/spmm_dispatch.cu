@@ -99,6 +99,9 @@ int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_l
         np = 1;
     np = std::max(1, std::min(np, 32 / s.kl));
     int u = t.rows_unroll > 0 ? t.rows_unroll : (np >= 8 ? 1 : np >= 2 ? 2 : (s.nv >= 4 ? 2 : 4));
+    const bool sweep = t.rows_sweep > 0 && s.w == 2;
+    if (sweep && t.rows_np > 0)
+        np = std::max(1, std::min(t.rows_np, 32 / s.kl)); // sweep shapes allow NP > 1 with NV > 1
 
     SpmmArgs args = {};
     args.rowptr = A->d_rowptr;
@@ -114,6 +117,14 @@ int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_l
     args.nnz_hi = (int)nnz_hi;
     args.c_row0 = c_row0;
     args.kc = kc;
+    args.tiles = s.tiles;
+    if (sweep)
+    {
+        const int rc = launch_sweep_w2(A, s.kl, s.nv, np, u, t.rows_threads > 0 ? t.rows_threads : 512, args, s.tiles,
+                                       A->device, stream);
+        if (rc != -1)
+            return rc;
+    }
     return s.w == 2 ? launch_rows_w2(A, s.kl, s.nv, np, u, args, s.tiles, A->device, stream)
                     : launch_rows_w1(A, s.kl, s.nv, np, u, args, s.tiles, A->device, stream);
 }

@@ -51,6 +51,8 @@ struct Tuning
     int rows_vec = 0;       // 1 forces 8-byte accesses
     int rows_ctas_per_sm = 0;
     int merge_items = 0;    // merge-path items per team
+    int rows_sweep = 0;     // 1: one CTA per SM walks the column tiles itself (L1-resident window)
+    int rows_threads = 0;   // sweep kernels: 512 or 1024 threads
     int rowblock = -1;      // -1 auto, 0 never use the row-block format, 1 always when built
 };
 Tuning &tuning();

@@ -271,6 +271,7 @@ struct SpmmArgs
     int c_row0;             // row id stored at C[0]
     int kc;                 // columns computed
     const int *bounds;      // optional precomputed CTA row cuts (gridDim.x+1 entries)
+    int tiles;              // column tiles (SWEEP kernels walk them in-kernel)
     // merge-path kernel only
     int items_per_team;
     int n_teams;
@@ -279,11 +280,28 @@ struct SpmmArgs
     int ldcarry;
 };
 
+// Resident CTAs per SM the register allocator is asked to honour: room for the U in-flight B
+// slices plus double-buffered indices. Without it ptxas schedules for minimum registers and
+// serialises every B load behind the FMA of the previous one (ncu: 100 % long-scoreboard stalls).
+constexpr int min_blocks(int nv, int w, int u, int rows, int threads)
+{
+    const int est = 44 + nv * w * 2 * (rows + u) + 6 * u;
+    const int mb = 65536 / (threads * est);
+    return mb < 1 ? 1 : (mb > 8 ? 8 : mb);
+}
+
 // Row kernel. A team of KL*NP lanes owns one row at a time: KL lanes across the
-// columns, NP non-zeros of the row in flight side by side, U steps issued back
-// to back. 32/(KL*NP) teams share a warp.
-template <int KL, int NV, int W, int NP, int U, bool FULL, int THREADS>
-__global__ void __launch_bounds__(THREADS) spmm_rows_kernel(const SpmmArgs a)
+// columns, NP non-zeros of the row in flight side by side, U steps per group.
+// 32/(KL*NP) teams share a warp. Software pipeline: while the U B-row slices of a
+// group are in flight, the column ids / values of the next group and the extent of
+// the team's next row are already being fetched, so a group costs one memory latency.
+//
+// SWEEP=true: one launch row (gridDim.y == 1) walks ALL column tiles of its chunk itself, one
+// after the other, instead of spreading the tiles over blockIdx.y. With one such CTA per SM the
+// SM follows a single stream of consecutive rows on a narrow column tile, which is what keeps
+// the B rows shared by neighbouring rows resident in L1.
+template <int KL, int NV, int W, int NP, int U, bool FULL, int THREADS, bool SWEEP = false>
+__global__ void __launch_bounds__(THREADS, SWEEP ? 1 : min_blocks(NV, W, U, 1, THREADS)) spmm_rows_kernel(const SpmmArgs a)
 {
     constexpr int T = KL * NP;
     constexpr int RW = 32 / T;
@@ -301,64 +319,74 @@ __global__ void __launch_bounds__(THREADS) spmm_rows_kernel(const SpmmArgs a)
     const int g = lt / KL;   // which of the NP concurrent non-zeros
     const int kl = lt % KL;  // which column group
     const int slot = (threadIdx.x >> 5) * RW + lane / T;
-    const int tile0 = blockIdx.y * S::TILE;
+  for (int tile = SWEEP ? 0 : (int)blockIdx.y; tile < (SWEEP ? a.tiles : (int)blockIdx.y + 1); ++tile)
+  {
+    const int tile0 = tile * S::TILE;
     const unsigned mask = slice_mask<KL, NV, W>(tile0, kl, a.kc);
     const double *__restrict__ Bk = a.B + tile0 + kl * W;
 
+    int row = lo + slot;
+    int js = 0, je = 0;
+    if (row < hi)
+    {
+        js = rp(row);
+        je = rp(row + 1);
+    }
     for (int base = lo; base < hi; base += SLOTS)
     {
-        const int row = base + slot;
         const bool valid = row < hi;
-        int js = 0, je = 0;
-        if (valid)
+        const int nrow = row + SLOTS; // the team's next row: fetch its extent now
+        int njs = 0, nje = 0;
+        if (nrow < hi)
         {
-            js = rp(row);
-            je = rp(row + 1);
+            njs = rp(nrow);
+            nje = rp(nrow + 1);
         }
         S acc;
         acc.zero();
         int j = js + g;
-        // full groups: U steps in flight, every load unconditional
-        for (; j + (U - 1) * NP < je; j += NP * U)
+        if (j < je)
         {
             int c[U];
             double x[U];
-            S b[U];
 #pragma unroll
             for (int u = 0; u < U; ++u)
             {
-                c[u] = ld_stream_i32(a.colidx + j + u * NP);
-                x[u] = ld_stream_f64(a.vals + j + u * NP);
+                const int jj = min(j + u * NP, je - 1); // clamped: a valid element, never accumulated past the end
+                c[u] = ld_stream_i32(a.colidx + jj);
+                x[u] = ld_stream_f64(a.vals + jj);
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                b[u].template load<FULL>(Bk + (long long)c[u] * a.ldb, mask);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                acc.fma(x[u], b[u]);
-        }
-        // tail: fewer than U steps left
-        if constexpr (U > 1)
-        {
-            if (j < je)
+            while (true)
             {
-                int c[U - 1];
-                double x[U - 1];
-                S b[U - 1];
+                S b[U];
 #pragma unroll
-                for (int u = 0; u < U - 1; ++u)
+                for (int u = 0; u < U; ++u)
+                    b[u].template load<FULL>(Bk + (long long)c[u] * a.ldb, mask);
+                const int jn = j + NP * U;
+                const bool more = jn < je;
+                int cn[U];
+                double xn[U];
+                // unconditional (clamped) so the fetch is issued while the B slices are in flight
+#pragma unroll
+                for (int u = 0; u < U; ++u)
                 {
-                    const int jj = min(j + u * NP, je - 1); // clamp: a valid element, weight 0 when past the end
-                    c[u] = ld_stream_i32(a.colidx + jj);
-                    x[u] = ld_stream_f64(a.vals + jj);
+                    const int jj = min(jn + u * NP, je - 1);
+                    cn[u] = ld_stream_i32(a.colidx + jj);
+                    xn[u] = ld_stream_f64(a.vals + jj);
                 }
 #pragma unroll
-                for (int u = 0; u < U - 1; ++u)
-                    b[u].template load<FULL>(Bk + (long long)c[u] * a.ldb, mask);
-#pragma unroll
-                for (int u = 0; u < U - 1; ++u)
+                for (int u = 0; u < U; ++u)
                     if (j + u * NP < je)
                         acc.fma(x[u], b[u]);
+                if (!more)
+                    break;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                {
+                    c[u] = cn[u];
+                    x[u] = xn[u];
+                }
+                j = jn;
             }
         }
         if constexpr (NP > 1)
@@ -371,7 +399,11 @@ __global__ void __launch_bounds__(THREADS) spmm_rows_kernel(const SpmmArgs a)
         }
         if (valid && g == 0)
             acc.store(a.C + (long long)(row - a.c_row0) * a.ldc + tile0 + kl * W, mask);
+        row = nrow;
+        js = njs;
+        je = nje;
     }
+  }
 }
 
 // ---- nnz-balanced merge-path kernel ---------------------------------------------------
@@ -402,7 +434,7 @@ __device__ __forceinline__ void merge_path_search(const RowClip &rp, int row_beg
 }
 
 template <int KL, int NV, int W, int U, bool FULL, int THREADS>
-__global__ void __launch_bounds__(THREADS) spmm_merge_kernel(const SpmmArgs a)
+__global__ void __launch_bounds__(THREADS, min_blocks(NV, W, U, 1, THREADS)) spmm_merge_kernel(const SpmmArgs a)
 {
     constexpr int RW = 32 / KL;
     using S = Slice<KL, NV, W>;

@@ -144,7 +144,7 @@ __global__ void rb_bounds_kernel(const int *blkptr, int n_blocks, int grid, int 
 // A team of KL lanes owns one row block (R rows) at a time; 32/KL teams per warp; every
 // CTA sweeps one contiguous, equal-cost run of row blocks (same reasoning as the row kernel).
 template <int R, int KL, int NV, int W, int U, int THREADS_>
-__global__ void __launch_bounds__(THREADS_) spmm_rowblock_kernel(const RbArgs a)
+__global__ void __launch_bounds__(THREADS_, min_blocks(NV, W, U, R, THREADS_)) spmm_rowblock_kernel(const RbArgs a)
 {
     constexpr int RW = 32 / KL;
     constexpr int SLOTS = (THREADS_ / 32) * RW;
@@ -162,50 +162,75 @@ __global__ void __launch_bounds__(THREADS_) spmm_rowblock_kernel(const RbArgs a)
     const int tile0 = blockIdx.y * S::TILE;
     const double *__restrict__ Bk = a.B + tile0 + kl * W;
 
+    int blk = lo + slot;
+    int es = 0, ee = 0;
+    if (blk < hi)
+    {
+        es = a.blkptr[blk];
+        ee = a.blkptr[blk + 1];
+    }
     for (int base = lo; base < hi; base += SLOTS)
     {
-        const int blk = base + slot;
-        int es = 0, ee = 0;
-        if (blk < hi)
+        const int nblk = blk + SLOTS; // the team's next row block: fetch its extent now
+        int nes = 0, nee = 0;
+        if (nblk < hi)
         {
-            es = a.blkptr[blk];
-            ee = a.blkptr[blk + 1];
+            nes = a.blkptr[nblk];
+            nee = a.blkptr[nblk + 1];
         }
         S acc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r)
             acc[r].zero();
-        int e = es;
-        for (; e + U <= ee; e += U)
+        if (es < ee)
         {
+            int e = es;
             int c[U];
             double x[U][R];
-            S b[U];
 #pragma unroll
             for (int u = 0; u < U; ++u)
             {
-                c[u] = ld_stream_i32(a.ucol + e + u);
-                ld_vals(a.uval + (long long)(e + u) * R, x[u]);
+                const int ej = min(e + u, ee - 1);
+                c[u] = ld_stream_i32(a.ucol + ej);
+                ld_vals(a.uval + (long long)ej * R, x[u]);
             }
+            while (true)
+            {
+                S b[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                b[u].template load<true>(Bk + (long long)c[u] * a.ldb, 0xffffffffu);
+                for (int u = 0; u < U; ++u)
+                    b[u].template load<true>(Bk + (long long)c[u] * a.ldb, 0xffffffffu);
+                const int en = e + U;
+                const bool more = en < ee;
+                int cn[U];
+                double xn[U][R];
 #pragma unroll
-            for (int u = 0; u < U; ++u)
+                for (int u = 0; u < U; ++u)
+                {
+                    const int ej = min(en + u, ee - 1); // clamped, unconditional: overlaps the B loads
+                    cn[u] = ld_stream_i32(a.ucol + ej);
+                    ld_vals(a.uval + (long long)ej * R, xn[u]);
+                }
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    acc[r].fma(x[u][r], b[u]);
-        }
-        for (; e < ee; ++e)
-        {
-            const int c = ld_stream_i32(a.ucol + e);
-            double x[R];
-            ld_vals(a.uval + (long long)e * R, x);
-            S b;
-            b.template load<true>(Bk + (long long)c * a.ldb, 0xffffffffu);
+                for (int u = 0; u < U; ++u)
+                    if (e + u < ee)
+                    {
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-                acc[r].fma(x[r], b);
+                        for (int r = 0; r < R; ++r)
+                            acc[r].fma(x[u][r], b[u]);
+                    }
+                if (!more)
+                    break;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                {
+                    c[u] = cn[u];
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        x[u][r] = xn[u][r];
+                }
+                e = en;
+            }
         }
         if (blk < hi)
         {
@@ -217,6 +242,9 @@ __global__ void __launch_bounds__(THREADS_) spmm_rowblock_kernel(const RbArgs a)
                     acc[r].store(a.C + row * a.ldc + tile0 + kl * W, 0xffffffffu);
             }
         }
+        blk = nblk;
+        es = nes;
+        ee = nee;
     }
 }
 

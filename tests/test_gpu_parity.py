@@ -361,3 +361,15 @@ def test_strategy_classes_on_one_gpu(oracle):
     assert_close_rel(blk.run(blk.local_B(dB)).cpu().numpy(), seq, tol=REL_TOL)
     assert_close_rel(spmm.ColumnSlabs.from_host(eng, m, 16).run(dB).cpu().numpy(), seq, tol=REL_TOL)
     assert_close_rel(spmm.NonZeroRanges.from_host(eng, m, 16).run(dB).cpu().numpy(), seq, tol=REL_TOL)
+
+
+@pytest.mark.parametrize("nv,np_,u,th", [(1, 1, 2, 512), (1, 4, 4, 1024), (2, 2, 2, 512), (2, 4, 4, 512), (4, 1, 4, 512),
+                                          (4, 2, 2, 1024), (4, 4, 4, 1024), (2, 1, 4, 1024)])
+@pytest.mark.parametrize("k", [64, 96, 16])
+def test_sweep_kernel_variants(oracle, nv, np_, u, th, k):
+    """One CTA per SM walking the column tiles in-kernel (rows.sweep), incl. ragged last tile (k=96 at nv=4)."""
+    rp, ci, va = random_csr(21, 3000, 3000, 20, long_row=900, empty_every=13, positive=True)
+    B = np.random.default_rng(k).integers(1, 101, (3000, k)).astype(np.float64)
+    tune = {"rows.sweep": 1, "rows.kl": 8, "rows.nv": nv, "rows.np": np_, "rows.unroll": u, "rows.threads": th}
+    got = gpu_multiply(spmm.SparseMatrix(va, ci, rp, 3000, 3000), B, k, "rows", tune)
+    assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)

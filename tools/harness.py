@@ -29,6 +29,7 @@ import sparsematrixmultiplicationmpi_b200 as spmm  # noqa: E402
 from sparsematrixmultiplicationmpi_b200 import _cabi, generators as gen  # noqa: E402
 
 L2_BYTES = 126e6
+ONLY = ""
 
 
 def peak_gbs():
@@ -71,7 +72,10 @@ def operand_sets(make_A, n_cols, n_rows, k, dev, footprint):
 def run_variants(name, sets, k, variants, iters, emit, nnz, n_rows, extra=None):
     stream = torch.cuda.current_stream().cuda_stream
     pk = peak_gbs()
+    import re
     for label, kernel, tune in variants:
+        if ONLY and not re.search(ONLY, label):
+            continue
         _cabi.tune("reset", 0)
         for key, val in tune.items():
             _cabi.tune(key, val)
@@ -111,6 +115,17 @@ def variant_list(k, full):
         for np_ in (1, 2, 4, 8, 16, 32):
             for u in (1, 2, 4):
                 v.append((f"rows np={np_} u={u}", "rows", {"rows.np": np_, "rows.unroll": u}))
+    if k >= 16:
+        for nv in (1, 2, 4):
+            if (k // 2) % (8 * nv):
+                continue
+            for np_ in (1, 2, 4):
+                for u in (2, 4):
+                    for th in (512, 1024):
+                        for ctas in ((1, 2) if th == 512 else (1,)):
+                            v.append((f"sweep nv={nv} np={np_} u={u} th={th} ctas={ctas}", "rows",
+                                      {"rows.sweep": 1, "rows.kl": 8, "rows.nv": nv, "rows.np": np_, "rows.unroll": u,
+                                       "rows.threads": th, "rows.ctas_per_sm": ctas}))
     for items in (128, 256, 1024, 2048):
         v.append((f"merge items={items}", "merge", {"merge.items": items}))
     return v
@@ -123,7 +138,7 @@ def cfg2(args, emit, dev):
     emit({"config": "cfg2", "schedule": first.schedule(), "n_rows": n, "nnz": host.nnz})
     for k in [int(x) for x in args.k.split(",")] if args.k else (1, 8, 32, 64):
         fp = abytes(n, host.nnz, k)
-        for R in ((0, 2, 4) if k >= 8 else (0,)):
+        for R in ([int(x) for x in args.rowblocks.split(",")] if k >= 8 else (0,)):
             def make(s, R=R):
                 A = spmm.DeviceCSR.from_host(host, dev.index, 0)
                 if R:
@@ -337,8 +352,12 @@ def main():
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--variants", action="store_true")
     ap.add_argument("--cpu", action="store_true", help="also time the reference CPU code on cfg2")
+    ap.add_argument("--only", default="", help="regex: run only the variants whose label matches")
+    ap.add_argument("--rowblocks", default="0,2,4", help="row-block layouts to time on cfg2")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "harness.jsonl"))
     args = ap.parse_args()
+    global ONLY
+    ONLY = args.only
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
