@@ -37,7 +37,8 @@ enum spmm_kernel
     SPMM_KERNEL_AUTO = 0,
     SPMM_KERNEL_ROWS = 1,  /* (sub-)warp-per-row teams over contiguous row chunks */
     SPMM_KERNEL_MERGE = 2, /* nnz-balanced merge-path with deterministic carry fix-up */
-    SPMM_KERNEL_ROWBLOCK = 3 /* R consecutive rows per team over the union of their columns (needs spmm_csr_build_rowblocks) */
+    SPMM_KERNEL_ROWBLOCK = 3, /* R consecutive rows per team over the union of their columns (needs spmm_csr_build_rowblocks) */
+    SPMM_KERNEL_PACKED = 4    /* warp-packed coalesced A stream (needs spmm_csr_build_packed) */
 };
 
 const char *spmm_last_error(void);
@@ -87,6 +88,14 @@ int spmm_csr_schedule(spmm_csr_t A, long long bins[8], int *max_row_len, double 
  * (what readMatrixMarketFile produces, utils.cpp:156-159); otherwise SPMM_ERR_UNSUPPORTED. */
 int spmm_csr_build_rowblocks(spmm_csr_t A, int rows_per_block);
 int spmm_csr_rowblock_info(spmm_csr_t A, int *rows_per_block, long long *union_entries, double *fill_ratio);
+/* Optional third layout: the A stream re-laid per warp ("SELL-4-4": slices of 32/lanes_per_row
+ * consecutive rows — or row blocks of 2 rows when rows_per_unit = 2, which needs
+ * spmm_csr_build_rowblocks(A, 2) first — in groups of 4 steps, ids as int4, values as double2,
+ * padded with id -1) so a warp reads it as one coalesced stream (spmm_packed.cu).
+ * rows_per_unit 0 drops it. lanes_per_row: 8 or 16. Used by AUTO for whole-matrix multiplies
+ * whose k is a multiple of 2*lanes_per_row. */
+int spmm_csr_build_packed(spmm_csr_t A, int rows_per_unit, int lanes_per_row);
+int spmm_csr_packed_info(spmm_csr_t A, int *rows_per_unit, int *lanes_per_row, long long *slots, double *fill_ratio);
 /* Sub-matrix A[:, col_begin:col_end) with local column ids (column-block strategy,
  * north_star reading of sparseMatrixFatVectorMultiplyColumnWise). Built on the device. */
 int spmm_csr_column_block(spmm_csr_t A, int col_begin, int col_end, spmm_csr_t *out);

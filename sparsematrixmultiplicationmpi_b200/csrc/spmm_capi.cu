@@ -230,6 +230,7 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "rows.nv") t.rows_nv = value;
     else if (k == "rowblock") t.rowblock = value;
     else if (k == "rows.sweep") t.rows_sweep = value;
+    else if (k == "rows.prefetch") t.rows_prefetch = value;
     else if (k == "rows.threads") t.rows_threads = value;
     else if (k == "rows.unroll") t.rows_unroll = value;
     else if (k == "rows.vec") t.rows_vec = value;
@@ -329,6 +330,7 @@ int spmm_csr_destroy(spmm_csr_t A)
         cudaFree(A->d_vals);
     }
     free_rowblocks(A);
+    free_packed(A);
     drop_bounds(A, -1);
     cudaFree(A->d_B);
     cudaFree(A->d_C);
@@ -400,12 +402,13 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
     SPMM_REQUIRE(d_B != nullptr || A->nnz == 0, "d_B is NULL");
     SPMM_CUDA(cudaSetDevice(A->device));
     cudaStream_t s = (cudaStream_t)stream;
-    SPMM_REQUIRE(kernel >= SPMM_KERNEL_AUTO && kernel <= SPMM_KERNEL_ROWBLOCK, "unknown kernel id");
+    SPMM_REQUIRE(kernel >= SPMM_KERNEL_AUTO && kernel <= SPMM_KERNEL_PACKED, "unknown kernel id");
+    SPMM_REQUIRE(kernel != SPMM_KERNEL_PACKED || A->pk_R != 0, "packed kernel requested but spmm_csr_build_packed was not called");
     SPMM_REQUIRE(kernel != SPMM_KERNEL_ROWBLOCK || A->rb_R != 0, "row-block kernel requested but spmm_csr_build_rowblocks was not called");
     if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)
         return launch_merge(A, 0, A->n_rows, 0, A->nnz, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
     return launch_rows(A, 0, A->n_rows, 0, A->nnz, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count,
-                       kernel != SPMM_KERNEL_ROWS, s);
+                       kernel == SPMM_KERNEL_ROWS ? 0 : (kernel == SPMM_KERNEL_AUTO ? 1 : kernel), s);
 }
 
 int spmm_multiply_device(spmm_csr_t A, const double *d_B, int k, double *d_C, int kernel, void *stream)
@@ -427,7 +430,7 @@ int spmm_multiply_rows_device(spmm_csr_t A, int row_begin, int row_end, const do
     SPMM_REQUIRE(d_B != nullptr || A->nnz == 0, "d_B is NULL");
     if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)
         return launch_merge(A, row_begin, row_end, 0, A->nnz, row_begin, d_B, k, d_C_local, k, k, (cudaStream_t)stream);
-    return launch_rows(A, row_begin, row_end, 0, A->nnz, row_begin, d_B, k, d_C_local, k, k, false,
+    return launch_rows(A, row_begin, row_end, 0, A->nnz, row_begin, d_B, k, d_C_local, k, k, 0,
                        (cudaStream_t)stream);
 }
 
@@ -491,7 +494,7 @@ int spmm_multiply_nnz_range_device(spmm_csr_t A, long long nnz_begin, long long 
     if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)
         return launch_merge(A, first_row, last_row + 1, nnz_begin, nnz_end, first_row, d_B, k, d_C_local, k, k,
                             (cudaStream_t)stream);
-    return launch_rows(A, first_row, last_row + 1, nnz_begin, nnz_end, first_row, d_B, k, d_C_local, k, k, false,
+    return launch_rows(A, first_row, last_row + 1, nnz_begin, nnz_end, first_row, d_B, k, d_C_local, k, k, 0,
                        (cudaStream_t)stream);
 }
 

@@ -73,17 +73,33 @@ Shape pick_shape(const double *d_B, long long ldb, const double *d_C, long long 
 } // namespace
 
 int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
-                const double *d_B, long long ldb, double *d_C, long long ldc, int kc, bool use_rowblock,
+                const double *d_B, long long ldb, double *d_C, long long ldc, int kc, int derived,
                 cudaStream_t stream)
 {
     if (row_end <= row_begin || kc <= 0)
         return SPMM_OK;
     const Tuning &t = tuning();
     const Shape s = pick_shape(d_B, ldb, d_C, ldc, kc);
-    // whole-matrix launch with a row-block format on the handle: use it when the shape fits
-    if (use_rowblock && A->rb_R && t.rowblock != 0 && row_begin == 0 && row_end == A->n_rows && nnz_lo == 0 &&
-        nnz_hi == A->nnz && c_row0 == 0 && rowblock_shape_ok(s.w, s.kl, s.nv, s.tiles, kc))
-        return launch_rowblock(A, s.w, s.kl, s.nv, s.tiles, d_B, ldb, d_C, ldc, stream);
+    // whole-matrix launch with a derived layout on the handle: use it when the shape fits
+    const bool whole = row_begin == 0 && row_end == A->n_rows && nnz_lo == 0 && nnz_hi == A->nnz && c_row0 == 0;
+    if (derived && whole)
+    {
+        Shape ps = s;
+        if (A->pk_R && A->pk_kl != s.kl && (kc % (2 * A->pk_kl) == 0) && s.w == 2)
+        {
+            // the packed layout fixes the lanes per row: re-derive nv / tiles for it
+            const int kq = kc / 2;
+            ps.kl = A->pk_kl;
+            ps.nv = t.rows_nv > 0 ? t.rows_nv : std::min(4, std::max(1, kq / ps.kl));
+            while (ps.nv > 1 && kq % (ps.kl * ps.nv))
+                ps.nv >>= 1;
+            ps.tiles = kq / (ps.kl * ps.nv);
+        }
+        if ((derived == 1 || derived == 4) && packed_shape_ok(A, ps.w, ps.kl, ps.nv, ps.tiles, kc))
+            return launch_packed(A, ps.nv, ps.tiles, d_B, ldb, d_C, ldc, stream);
+        if ((derived == 1 || derived == 3) && A->rb_R && t.rowblock != 0 && rowblock_shape_ok(s.w, s.kl, s.nv, s.tiles, kc))
+            return launch_rowblock(A, s.w, s.kl, s.nv, s.tiles, d_B, ldb, d_C, ldc, stream);
+    }
     int np = 1;
     if (s.nv == 1)
     {
@@ -118,6 +134,11 @@ int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_l
     args.c_row0 = c_row0;
     args.kc = kc;
     args.tiles = s.tiles;
+    // L2 prefetch only when the operands are 16-byte aligned, B is one contiguous block that starts
+    // at column 0 of its rows (no k-slab), and the A arrays are the handle's own (padded) allocations
+    const bool aligned = ((uintptr_t)A->d_colidx % 16 == 0) && ((uintptr_t)A->d_vals % 16 == 0) && ((uintptr_t)d_B % 16 == 0);
+    args.prefetch = aligned ? (t.rows_prefetch >= 0 ? t.rows_prefetch : 3) : 0;
+    args.b_bytes = (ldb == kc) ? (long long)A->n_cols * ldb * 8 : 0;
     if (sweep)
     {
         const int rc = launch_sweep_w2(A, s.kl, s.nv, np, u, t.rows_threads > 0 ? t.rows_threads : 512, args, s.tiles,

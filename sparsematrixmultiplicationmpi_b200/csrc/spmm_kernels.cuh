@@ -36,16 +36,21 @@ namespace spmm
 {
 
 // ---- cache-hinted accessors ------------------------------------------------------
+#if defined(SPMM_ABLATE) && (SPMM_ABLATE & 1) // diagnostic build: A stream allocates in L1
+#define SPMM_A_HINT ""
+#else
+#define SPMM_A_HINT ".L1::no_allocate"
+#endif
 __device__ __forceinline__ int ld_stream_i32(const int *p)
 {
     int v;
-    asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm("ld.global.nc" SPMM_A_HINT ".s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ double ld_stream_f64(const double *p)
 {
     double v;
-    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    asm("ld.global.nc" SPMM_A_HINT ".f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ double ld_b1(const double *p)
@@ -67,6 +72,19 @@ __device__ __forceinline__ void st_c1(double *p, double v)
 __device__ __forceinline__ void st_c2(double *p, double x, double y)
 {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x), "d"(y) : "memory");
+}
+
+// Fire-and-forget TMA prefetch of a byte range into L2 (UBLKPF.L2). Called by every thread of a
+// CTA; thread t takes the pieces t, t+THREADS, ... of `piece` bytes. base must be 16-byte aligned.
+__device__ __forceinline__ void bulk_prefetch_l2(const char *base, size_t bytes, int tid, int nthreads)
+{
+    constexpr size_t piece = 4096;
+    bytes &= ~(size_t)15;
+    for (size_t off = (size_t)tid * piece; off < bytes; off += (size_t)nthreads * piece)
+    {
+        const unsigned n = (unsigned)(bytes - off < piece ? bytes - off : piece);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(n) : "memory");
+    }
 }
 
 // Row extents clipped to a non-zero range (no-op for the whole matrix).
@@ -272,6 +290,8 @@ struct SpmmArgs
     int kc;                 // columns computed
     const int *bounds;      // optional precomputed CTA row cuts (gridDim.x+1 entries)
     int tiles;              // column tiles (SWEEP kernels walk them in-kernel)
+    int prefetch;           // bit0: CTA prefetches its own A chunk into L2; bit1: its share of B
+    long long b_bytes;      // bytes of the B operand (0: not contiguous, no prefetch)
     // merge-path kernel only
     int items_per_team;
     int n_teams;
@@ -313,6 +333,26 @@ __global__ void __launch_bounds__(THREADS, SWEEP ? 1 : min_blocks(NV, W, U, 1, T
     __shared__ int s_chunk[2];
     cta_chunk(rp, a.row_begin, a.row_end, a.bounds, s_chunk);
     const int lo = s_chunk[0], hi = s_chunk[1];
+
+    // L2 prefetch by the TMA unit, issued before any work: the CTA's own slice of the A stream and
+    // its share of B. Every later load then finds L2-hit latency instead of a first-touch DRAM miss.
+    if (a.prefetch & 1)
+    {
+        const size_t n0 = (size_t)rp(lo), n1 = (size_t)rp(hi);
+        if (n1 > n0)
+        {
+            const size_t c0 = (n0 * 4) & ~(size_t)15, v0 = (n0 * 8) & ~(size_t)15;
+            bulk_prefetch_l2((const char *)a.colidx + c0, n1 * 4 - c0, threadIdx.x, THREADS);
+            bulk_prefetch_l2((const char *)a.vals + v0, n1 * 8 - v0, threadIdx.x, THREADS);
+        }
+    }
+    if ((a.prefetch & 2) && a.b_bytes > 0 && blockIdx.y == 0)
+    {
+        const size_t share = (((size_t)a.b_bytes + gridDim.x - 1) / gridDim.x + 15) & ~(size_t)15;
+        const size_t b0 = share * blockIdx.x;
+        if (b0 < (size_t)a.b_bytes)
+            bulk_prefetch_l2((const char *)a.B + b0, min(share, (size_t)a.b_bytes - b0), threadIdx.x, THREADS);
+    }
 
     const int lane = threadIdx.x & 31;
     const int lt = lane % T; // lane inside the team

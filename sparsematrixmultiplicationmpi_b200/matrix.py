@@ -142,6 +142,15 @@ class DeviceCSR:
         _cabi.check(_cabi.lib().spmm_csr_rowblock_info(self.handle, C.byref(r), C.byref(n), C.byref(f)))
         return {"rows_per_block": r.value, "union_entries": n.value, "fill_ratio": f.value}
 
+    def build_packed(self, rows_per_unit: int = 1, lanes_per_row: int = 8) -> dict:
+        _cabi.check(_cabi.lib().spmm_csr_build_packed(self.handle, rows_per_unit, lanes_per_row))
+        return self.packed_info()
+
+    def packed_info(self) -> dict:
+        r, l, n, f = C.c_int(), C.c_int(), C.c_longlong(), C.c_double()
+        _cabi.check(_cabi.lib().spmm_csr_packed_info(self.handle, C.byref(r), C.byref(l), C.byref(n), C.byref(f)))
+        return {"rows_per_unit": r.value, "lanes_per_row": l.value, "slots": n.value, "fill_ratio": f.value}
+
     def nnz_range_rows(self, nnz_begin: int, nnz_end: int) -> tuple[int, int]:
         a, b = C.c_int(), C.c_int()
         _cabi.check(_cabi.lib().spmm_nnz_range_rows(self.handle, nnz_begin, nnz_end, C.byref(a), C.byref(b)))

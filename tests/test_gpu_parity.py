@@ -373,3 +373,30 @@ def test_sweep_kernel_variants(oracle, nv, np_, u, th, k):
     tune = {"rows.sweep": 1, "rows.kl": 8, "rows.nv": nv, "rows.np": np_, "rows.unroll": u, "rows.threads": th}
     got = gpu_multiply(spmm.SparseMatrix(va, ci, rp, 3000, 3000), B, k, "rows", tune)
     assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
+
+
+@pytest.mark.parametrize("R,kl", [(1, 8), (1, 16), (2, 8), (2, 16)])
+@pytest.mark.parametrize("k,tune", [(16, {}), (32, {}), (64, {}), (64, {"rows.sweep": 1, "rows.threads": 512}),
+                                    (64, {"rows.nv": 1}), (128, {"rows.sweep": 1, "rows.threads": 256, "rows.nv": 2}),
+                                    (256, {})])
+def test_packed_stream_kernel(oracle, R, kl, k, tune):
+    """Warp-packed A stream (spmm_packed.cu): ragged last slice, empty rows, a long row, padded groups."""
+    if (k // 2) % kl:
+        pytest.skip("k must be a multiple of 2*lanes_per_row")
+    rp, ci, va = random_csr(23, 2503, 2503, 18, long_row=333, empty_every=11, positive=True)
+    m = spmm.SparseMatrix(va, ci, rp, 2503, 2503)
+    B = np.random.default_rng(k).integers(1, 101, (2503, k)).astype(np.float64)
+    _cabi.tune("reset", 0)
+    for key, val in tune.items():
+        _cabi.tune(key, val)
+    try:
+        with spmm.DeviceCSR.from_host(m, 0, 2 if R == 2 else 0) as A:
+            info = A.build_packed(R, kl)
+            assert info["rows_per_unit"] == R and info["lanes_per_row"] == kl and info["fill_ratio"] >= 1.0
+            dB = dev(B)
+            for kernel in ("packed", "auto"):
+                dC = torch.full((2503, k), np.nan, dtype=torch.float64, device="cuda")
+                A.multiply(dB.data_ptr(), k, dC.data_ptr(), kernel)
+                assert_close_rel(dC.cpu().numpy(), oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
+    finally:
+        _cabi.tune("reset", 0)

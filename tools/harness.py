@@ -126,6 +126,14 @@ def variant_list(k, full):
                             v.append((f"sweep nv={nv} np={np_} u={u} th={th} ctas={ctas}", "rows",
                                       {"rows.sweep": 1, "rows.kl": 8, "rows.nv": nv, "rows.np": np_, "rows.unroll": u,
                                        "rows.threads": th, "rows.ctas_per_sm": ctas}))
+    for pf in (0, 1, 2, 3):
+        v.append((f"rows pf={pf}", "rows", {"rows.prefetch": pf}))
+        v.append((f"rows u=4 pf={pf}", "rows", {"rows.prefetch": pf, "rows.unroll": 4}))
+        if k >= 16 and (k // 2) % 32 == 0:
+            v.append((f"sweep nv=4 np=2 u=4 th=512 pf={pf}", "rows", {"rows.sweep": 1, "rows.kl": 8, "rows.nv": 4, "rows.np": 2,
+                                                                    "rows.unroll": 4, "rows.threads": 512, "rows.prefetch": pf}))
+            v.append((f"sweep nv=4 np=1 u=4 th=512 pf={pf}", "rows", {"rows.sweep": 1, "rows.kl": 8, "rows.nv": 4, "rows.np": 1,
+                                                                    "rows.unroll": 4, "rows.threads": 512, "rows.prefetch": pf}))
     for items in (128, 256, 1024, 2048):
         v.append((f"merge items={items}", "merge", {"merge.items": items}))
     return v
@@ -158,6 +166,32 @@ def cfg2(args, emit, dev):
                 A.close()
             del sets
             torch.cuda.empty_cache()
+        if k >= 16 and args.packed:
+            for R, kl in ((1, 8), (1, 16), (2, 8), (2, 16)):
+                if (k // 2) % kl:
+                    continue
+
+                def make(s, R=R, kl=kl):
+                    A = spmm.DeviceCSR.from_host(host, dev.index, 0)
+                    if R == 2:
+                        A.build_rowblocks(2)
+                    A.build_packed(R, kl)
+                    return A
+                sets = operand_sets(make, n, n, k, dev, fp)
+                info = sets[0][0].packed_info()
+                vs = [(f"packed R={R} kl={kl}", "packed", {})]
+                vs += [(f"packed R={R} kl={kl} ctas={c}", "packed", {"rows.ctas_per_sm": c}) for c in (1, 2, 3)]
+                vs += [(f"packed R={R} kl={kl} sweep th={th} ctas={c}", "packed", {"rows.sweep": 1, "rows.threads": th, "rows.ctas_per_sm": c})
+                       for th in (256, 512) for c in (1, 2)]
+                nvs = [nv for nv in (1, 2) if (k // 2) % (kl * nv) == 0 and kl * nv * 2 < k]
+                vs += [(f"packed R={R} kl={kl} nv={nv} sweep th=512", "packed", {"rows.sweep": 1, "rows.threads": 512, "rows.nv": nv})
+                       for nv in nvs]
+                vs += [(f"packed R={R} kl={kl} nv={nv}", "packed", {"rows.nv": nv}) for nv in nvs]
+                run_variants("cfg2", sets, k, vs, args.iters, emit, host.nnz, n, {"packed": info})
+                for A, _, _ in sets:
+                    A.close()
+                del sets
+                torch.cuda.empty_cache()
     return host
 
 
@@ -352,6 +386,7 @@ def main():
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--variants", action="store_true")
     ap.add_argument("--cpu", action="store_true", help="also time the reference CPU code on cfg2")
+    ap.add_argument("--packed", action="store_true", help="also time the warp-packed stream layouts on cfg2")
     ap.add_argument("--only", default="", help="regex: run only the variants whose label matches")
     ap.add_argument("--rowblocks", default="0,2,4", help="row-block layouts to time on cfg2")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "harness.jsonl"))
