@@ -149,10 +149,21 @@ def cpu_reference_run(host, B, k, steps, warmup, max_seconds=60.0):
             "sample": f"full cop20k_A-shaped k={k} multiply, reference {strategy} strategy at P={P} "
                       f"(-O3 -march=x86-64-v3, compat MPI rank-threads), mean of {len(times)} calls",
             "seconds_per_step": t,
-            "sequential_gflops": flops / best[("seq", 1)] / 1e9 if ("seq", 1) in best else None}
+            "sequential_gflops": flops / best[("seq", 1)] / 1e9 if ("seq", 1) in best else None,
+            "rowwise_all_cores_gflops": flops / best[("row", cores)] / 1e9 if ("row", cores) in best else None,
+            "host_cores": os.cpu_count()}
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else this process or its libraries print
+    # (NCCL's version banner, torchrun notices) is sent to stderr.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict) -> None:
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
@@ -191,7 +202,7 @@ def main():
                 "data": "synthetic", "config": config, "cpu_baseline": res,
                 "e2e": {"value": res["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -213,8 +224,10 @@ def main():
     sets = []
     for s in range(OPERAND_SETS):
         A = first if s == 0 else spmm.DeviceCSR.from_host(host, local_rank, 0)
-        if args.kernel in ("auto", "rowblock"):
-            A.build_rowblocks(-1)
+        if args.kernel == "rowblock":
+            A.build_rowblocks(2)
+        elif args.kernel == "packed":
+            A.build_packed(1, 8)
         Bd = torch.randint(1, 101, (n, k), device=dev).double()
         Cd = torch.empty((n, k), dtype=torch.float64, device=dev)
         sets.append((A, Bd, Cd))
@@ -325,7 +338,7 @@ def main():
                 "hbm_gbs_per_gpu": achieved, "kernel_arg": args.kernel}
         if collectives:
             line["collectives"] = collectives
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

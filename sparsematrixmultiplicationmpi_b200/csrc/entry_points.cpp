@@ -124,7 +124,6 @@ spmm_csr_t whole_matrix(const SparseMatrix &m, int device)
         spmm_csr_t h = nullptr;
         ok(spmm_csr_create_host(device, m.numRows, m.numCols, (long long)m.values.size(), m.rowPtr.data(),
                                 m.colIndices.data(), m.values.data(), &h));
-        ok(spmm_csr_build_rowblocks(h, -1));
         return h;
     });
 }
@@ -175,8 +174,7 @@ FatVector sparseMatrixFatVectorMultiplyRowWise(const SparseMatrix &sparseMatrix,
             spmm_csr_t h = nullptr;
             ok(spmm_csr_create_host(device, end - start, sparseMatrix.numCols, (long long)hi - lo, rp.data(),
                                     sparseMatrix.colIndices.data() + lo, sparseMatrix.values.data() + lo, &h));
-            ok(spmm_csr_build_rowblocks(h, -1));
-            return h;
+                return h;
         });
         const std::vector<double> B = pack(fatVector, (size_t)sparseMatrix.numCols, vecCols);
         ok(spmm_multiply_host(A, B.data(), vecCols, local.data(), SPMM_KERNEL_AUTO));

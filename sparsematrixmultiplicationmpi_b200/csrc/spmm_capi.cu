@@ -231,6 +231,7 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "rowblock") t.rowblock = value;
     else if (k == "rows.sweep") t.rows_sweep = value;
     else if (k == "rows.prefetch") t.rows_prefetch = value;
+    else if (k == "rows.tile") t.rows_tile = value;
     else if (k == "rows.threads") t.rows_threads = value;
     else if (k == "rows.unroll") t.rows_unroll = value;
     else if (k == "rows.vec") t.rows_vec = value;

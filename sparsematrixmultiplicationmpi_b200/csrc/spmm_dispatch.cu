@@ -107,7 +107,7 @@ int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_l
         const int want = floor_pow2(std::max(1, (int)(A->sched.mean_len * 0.5)));
         np = std::max(1, std::min(want, 32 / s.kl));
         if (s.kl >= 4)
-            np = std::min(np, 4);
+            np = std::min(np, 2); // measured (profiles/): 2 side-by-side non-zeros beat 4 once a row piece is >= 64 B
     }
     if (t.rows_np > 0)
         np = t.rows_np;

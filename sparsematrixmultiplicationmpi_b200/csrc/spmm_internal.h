@@ -53,6 +53,7 @@ struct Tuning
     int merge_items = 0;    // merge-path items per team
     int rows_sweep = 0;     // 1: one CTA per SM walks the column tiles itself (L1-resident window)
     int rows_threads = 0;   // sweep kernels: 512 or 1024 threads
+    int rows_tile = 0;      // 0 auto, > 0 rows per round-robin tile, -1 never tile (one chunk per CTA)
     int rows_prefetch = -1; // -1 auto; bit0 A chunk, bit1 B share: TMA prefetch into L2 at kernel start
     int rowblock = -1;      // -1 auto, 0 never use the row-block format, 1 always when built
 };

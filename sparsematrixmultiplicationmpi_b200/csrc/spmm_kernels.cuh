@@ -290,6 +290,7 @@ struct SpmmArgs
     int kc;                 // columns computed
     const int *bounds;      // optional precomputed CTA row cuts (gridDim.x+1 entries)
     int tiles;              // column tiles (SWEEP kernels walk them in-kernel)
+    int tile_rows;          // > 0: CTAs take row tiles of this size round-robin (b, b+grid, ...) instead of one chunk
     int prefetch;           // bit0: CTA prefetches its own A chunk into L2; bit1: its share of B
     long long b_bytes;      // bytes of the B operand (0: not contiguous, no prefetch)
     // merge-path kernel only
@@ -331,12 +332,21 @@ __global__ void __launch_bounds__(THREADS, SWEEP ? 1 : min_blocks(NV, W, U, 1, T
 
     const RowClip rp{a.rowptr, a.nnz_lo, a.nnz_hi};
     __shared__ int s_chunk[2];
-    cta_chunk(rp, a.row_begin, a.row_end, a.bounds, s_chunk);
-    const int lo = s_chunk[0], hi = s_chunk[1];
+    // Large matrices: row tiles dealt round-robin, so that at any moment all CTAs of the grid work
+    // inside one window of grid*tile_rows consecutive rows and the B rows they share stay in L2
+    // (one far-apart chunk per CTA would keep hundreds of disjoint B windows alive at once).
+    const bool tiled = a.tile_rows > 0;
+    if (!tiled)
+        cta_chunk(rp, a.row_begin, a.row_end, a.bounds, s_chunk);
+  for (long long t0 = (long long)a.row_begin + (long long)blockIdx.x * a.tile_rows; tiled ? t0 < a.row_end : t0 == (long long)a.row_begin + (long long)blockIdx.x * a.tile_rows;
+       t0 += tiled ? (long long)gridDim.x * a.tile_rows : 1)
+  {
+    const int lo = tiled ? (int)t0 : s_chunk[0];
+    const int hi = tiled ? (int)min((long long)a.row_end, t0 + a.tile_rows) : s_chunk[1];
 
     // L2 prefetch by the TMA unit, issued before any work: the CTA's own slice of the A stream and
     // its share of B. Every later load then finds L2-hit latency instead of a first-touch DRAM miss.
-    if (a.prefetch & 1)
+    if ((a.prefetch & 1) && !tiled)
     {
         const size_t n0 = (size_t)rp(lo), n1 = (size_t)rp(hi);
         if (n1 > n0)
@@ -346,7 +356,7 @@ __global__ void __launch_bounds__(THREADS, SWEEP ? 1 : min_blocks(NV, W, U, 1, T
             bulk_prefetch_l2((const char *)a.vals + v0, n1 * 8 - v0, threadIdx.x, THREADS);
         }
     }
-    if ((a.prefetch & 2) && a.b_bytes > 0 && blockIdx.y == 0)
+    if ((a.prefetch & 2) && a.b_bytes > 0 && blockIdx.y == 0 && !tiled)
     {
         const size_t share = (((size_t)a.b_bytes + gridDim.x - 1) / gridDim.x + 15) & ~(size_t)15;
         const size_t b0 = share * blockIdx.x;
@@ -443,6 +453,7 @@ __global__ void __launch_bounds__(THREADS, SWEEP ? 1 : min_blocks(NV, W, U, 1, T
         js = njs;
         je = nje;
     }
+  }
   }
 }
 

@@ -68,7 +68,13 @@ int launch_rows_full(const spmm_csr_s *A, const SpmmArgs &args, int tiles, int d
     grid = std::max(1LL, std::min(grid, (rows + SLOTS - 1) / SLOTS));
     SpmmArgs a2 = args;
     a2.bounds = nullptr;
-    if (args.row_begin == 0 && args.row_end == A->n_rows && args.nnz_lo == 0 && args.nnz_hi == A->nnz)
+    const Tuning &tn = tuning();
+    // enough rows for >= 16 tiles per CTA: deal tiles round-robin (L2-resident B window), else one chunk per CTA
+    const int tile = tn.rows_tile > 0 ? tn.rows_tile : SLOTS * 8;
+    a2.tile_rows = (tn.rows_tile > 0 || (tn.rows_tile == 0 && rows >= grid * 16LL * tile)) ? tile : 0;
+    if (a2.tile_rows)
+        ;
+    else if (args.row_begin == 0 && args.row_end == A->n_rows && args.nnz_lo == 0 && args.nnz_hi == A->nnz)
     {
         // whole matrix: the equal-cost CTA cuts are part of the handle's schedule
         rc = cached_bounds(A, 0, (int)grid, stream, &a2.bounds, [&](int *out) {
@@ -186,6 +192,7 @@ int launch_sweep_one(const spmm_csr_s *A, const SpmmArgs &args, int tiles, int d
     SpmmArgs a2 = args;
     a2.tiles = tiles;
     a2.bounds = nullptr;
+    a2.tile_rows = 0;
     const Tuning &t = tuning();
     const int per_sm = t.rows_ctas_per_sm > 0 ? t.rows_ctas_per_sm : 1;
     constexpr int SLOTS = (TH / 32) * (32 / (KL * NP));

@@ -66,7 +66,7 @@ class DeviceCSR:
 
     # -- construction --
     @classmethod
-    def from_host(cls, m: SparseMatrix, device: int = 0, rowblocks: int = -1) -> "DeviceCSR":
+    def from_host(cls, m: SparseMatrix, device: int = 0, rowblocks: int = 0) -> "DeviceCSR":
         if m.rowPtr.size != m.numRows + 1:
             raise ValueError("rowPtr must hold numRows+1 offsets")
         h = C.c_void_p()

@@ -63,7 +63,7 @@ def partition_nnz(nnz: int, P: int, r: int) -> tuple[int, int]:
 class CudaCompute:
     """Engine of the product path: CSR shards in HBM, multiply through libspmm_b200.so."""
 
-    def __init__(self, device: int | None = None, kernel: str = "auto", rowblocks: int = -1):
+    def __init__(self, device: int | None = None, kernel: str = "auto", rowblocks: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("sparsematrixmultiplicationmpi_b200 needs a CUDA device (no CPU fallback)")
         _cabi.lib()  # fail loudly if the extension is not built

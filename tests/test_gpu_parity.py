@@ -400,3 +400,13 @@ def test_packed_stream_kernel(oracle, R, kl, k, tune):
                 assert_close_rel(dC.cpu().numpy(), oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
     finally:
         _cabi.tune("reset", 0)
+
+
+@pytest.mark.parametrize("tile", [32, 100, 4096])
+@pytest.mark.parametrize("k", [1, 16, 64])
+def test_round_robin_row_tiles(oracle, tile, k):
+    """rows.tile: CTAs take row tiles b, b+grid, ... (the large-matrix schedule) instead of one chunk each."""
+    rp, ci, va = random_csr(29, 5003, 5003, 12, long_row=777, empty_every=9, positive=True)
+    B = np.random.default_rng(k).integers(1, 101, (5003, k)).astype(np.float64)
+    got = gpu_multiply(spmm.SparseMatrix(va, ci, rp, 5003, 5003), B, k, "rows", {"rows.tile": tile})
+    assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)

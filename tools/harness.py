@@ -221,8 +221,10 @@ def cfg4(args, emit, dev, n=1 << 25, npr=32, hb=4096, k=16):
     A = spmm.DeviceCSR.banded(n, npr, hb, seed=7, device=dev.index)
     sets = [(A, torch.randint(1, 101, (n, k), device=dev).double(), torch.empty((n, k), dtype=torch.float64, device=dev))]
     vs = [("auto", "auto", {}), ("rows", "rows", {}), ("merge", "merge", {})]
+    vs += [("rows one chunk per CTA", "rows", {"rows.tile": -1})]
     if args.variants:
         vs += [(f"rows np={p} u={u}", "rows", {"rows.np": p, "rows.unroll": u}) for p in (1, 2, 4) for u in (1, 2, 4)]
+        vs += [(f"rows tile={t}", "rows", {"rows.tile": t}) for t in (64, 128, 512, 1024, 4096)]
     run_variants("cfg4", sets, k, vs, max(3, args.iters // 20), emit, A.nnz, n)
     A.close()
 
