@@ -38,7 +38,8 @@ enum spmm_kernel
     SPMM_KERNEL_ROWS = 1,  /* (sub-)warp-per-row teams over contiguous row chunks */
     SPMM_KERNEL_MERGE = 2, /* nnz-balanced merge-path with deterministic carry fix-up */
     SPMM_KERNEL_ROWBLOCK = 3, /* R consecutive rows per team over the union of their columns (needs spmm_csr_build_rowblocks) */
-    SPMM_KERNEL_PACKED = 4    /* warp-packed coalesced A stream (needs spmm_csr_build_packed) */
+    SPMM_KERNEL_PACKED = 4,   /* warp-packed coalesced A stream (needs spmm_csr_build_packed) */
+    SPMM_KERNEL_STAGED = 5    /* CSR rows with the id/value stream staged through shared memory by cp.async (k multiple of 16, rows <= 2048 long) */
 };
 
 const char *spmm_last_error(void);

@@ -13,9 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SPMM_B200_LIB") or os.path.join(HERE, "libspmm_b200.so")  # override: diagnostic builds only
 
 SPMM_OK, SPMM_ERR_INVALID, SPMM_ERR_CUDA, SPMM_ERR_NOMEM, SPMM_ERR_UNSUPPORTED = range(5)
-KERNEL_AUTO, KERNEL_ROWS, KERNEL_MERGE, KERNEL_ROWBLOCK, KERNEL_PACKED = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_ROWS, KERNEL_MERGE, KERNEL_ROWBLOCK, KERNEL_PACKED, KERNEL_STAGED = 0, 1, 2, 3, 4, 5
 KERNELS = {"auto": KERNEL_AUTO, "rows": KERNEL_ROWS, "merge": KERNEL_MERGE, "rowblock": KERNEL_ROWBLOCK,
-           "packed": KERNEL_PACKED}
+           "packed": KERNEL_PACKED, "staged": KERNEL_STAGED}
 
 
 class SpmmError(RuntimeError):

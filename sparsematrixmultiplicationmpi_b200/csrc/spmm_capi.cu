@@ -177,8 +177,9 @@ int make_handle(int device, int n_rows, int n_cols, long long nnz, spmm_csr_s **
 int alloc_arrays(spmm_csr_s *A)
 {
     SPMM_CUDA(cudaMalloc(&A->d_rowptr, sizeof(int) * ((size_t)A->n_rows + 1)));
-    SPMM_CUDA(cudaMalloc(&A->d_colidx, sizeof(int) * (size_t)std::max<long long>(A->nnz, 1)));
-    SPMM_CUDA(cudaMalloc(&A->d_vals, sizeof(double) * (size_t)std::max<long long>(A->nnz, 1)));
+    // + 8 elements: the staged kernel copies whole 16-byte pieces and may touch up to 3 ids / 1 value past nnz
+    SPMM_CUDA(cudaMalloc(&A->d_colidx, sizeof(int) * ((size_t)std::max<long long>(A->nnz, 1) + 8)));
+    SPMM_CUDA(cudaMalloc(&A->d_vals, sizeof(double) * ((size_t)std::max<long long>(A->nnz, 1) + 8)));
     A->owns = true;
     return SPMM_OK;
 }
@@ -232,6 +233,7 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "rows.sweep") t.rows_sweep = value;
     else if (k == "rows.prefetch") t.rows_prefetch = value;
     else if (k == "rows.tile") t.rows_tile = value;
+    else if (k == "rows.staged") t.rows_staged = value;
     else if (k == "rows.threads") t.rows_threads = value;
     else if (k == "rows.unroll") t.rows_unroll = value;
     else if (k == "rows.vec") t.rows_vec = value;
@@ -403,7 +405,7 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
     SPMM_REQUIRE(d_B != nullptr || A->nnz == 0, "d_B is NULL");
     SPMM_CUDA(cudaSetDevice(A->device));
     cudaStream_t s = (cudaStream_t)stream;
-    SPMM_REQUIRE(kernel >= SPMM_KERNEL_AUTO && kernel <= SPMM_KERNEL_PACKED, "unknown kernel id");
+    SPMM_REQUIRE(kernel >= SPMM_KERNEL_AUTO && kernel <= SPMM_KERNEL_STAGED, "unknown kernel id");
     SPMM_REQUIRE(kernel != SPMM_KERNEL_PACKED || A->pk_R != 0, "packed kernel requested but spmm_csr_build_packed was not called");
     SPMM_REQUIRE(kernel != SPMM_KERNEL_ROWBLOCK || A->rb_R != 0, "row-block kernel requested but spmm_csr_build_rowblocks was not called");
     if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)

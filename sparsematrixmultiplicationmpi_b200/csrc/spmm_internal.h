@@ -53,6 +53,7 @@ struct Tuning
     int merge_items = 0;    // merge-path items per team
     int rows_sweep = 0;     // 1: one CTA per SM walks the column tiles itself (L1-resident window)
     int rows_threads = 0;   // sweep kernels: 512 or 1024 threads
+    int rows_staged = 0;    // 1: AUTO may pick the smem-staged row kernel
     int rows_tile = 0;      // 0 auto, > 0 rows per round-robin tile, -1 never tile (one chunk per CTA)
     int rows_prefetch = -1; // -1 auto; bit0 A chunk, bit1 B share: TMA prefetch into L2 at kernel start
     int rowblock = -1;      // -1 auto, 0 never use the row-block format, 1 always when built
@@ -108,7 +109,7 @@ namespace spmm
 // rows [row_begin,row_end), each clipped to the non-zero range [nnz_lo,nnz_hi); row c_row0 is stored at d_C[0]
 int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
                 const double *d_B, long long ldb, double *d_C, long long ldc, int kc, int derived,
-                cudaStream_t stream); // derived: 0 CSR kernel only, 1 any derived layout on the handle, 3 row-block, 4 packed
+                cudaStream_t stream); // derived: 0 CSR row kernel only, 1 best available, 3 row-block, 4 packed, 5 staged
 int launch_merge(spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
                  const double *d_B, long long ldb, double *d_C, long long ldc, int kc, cudaStream_t stream);
 bool rowblock_shape_ok(int w, int kl, int nv, int tiles, int kc);
@@ -119,6 +120,9 @@ bool packed_shape_ok(const spmm_csr_s *A, int w, int kl, int nv, int tiles, int 
 int launch_packed(const spmm_csr_s *A, int nv, int tiles, const double *d_B, long long ldb, double *d_C, long long ldc,
                   cudaStream_t stream);
 void free_packed(spmm_csr_s *A);
+bool staged_shape_ok(const spmm_csr_s *A, int w, int kl, int nv, int tiles, int kc);
+int launch_staged(const spmm_csr_s *A, int nv, int tiles, const double *d_B, long long ldb, double *d_C, long long ldc,
+                  cudaStream_t stream);
 // CTA cuts cached on the handle; `fill` launches the kernel that computes grid+1 cuts into its argument
 int cached_bounds(const spmm_csr_s *A, int kind, int grid, cudaStream_t stream, const int **out,
                   const std::function<void(int *)> &fill);

@@ -53,6 +53,12 @@ __device__ __forceinline__ double ld_stream_f64(const double *p)
     asm("ld.global.nc" SPMM_A_HINT ".f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ int ld_b_i32(const int *p)
+{
+    int v;
+    asm("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ double ld_b1(const double *p)
 {
     double v;
@@ -306,7 +312,7 @@ struct SpmmArgs
 // serialises every B load behind the FMA of the previous one (ncu: 100 % long-scoreboard stalls).
 constexpr int min_blocks(int nv, int w, int u, int rows, int threads)
 {
-    const int est = 44 + nv * w * 2 * (rows + u) + 6 * u;
+    const int est = 24 + nv * w * 2 * (rows + u) + 6 * u;
     const int mb = 65536 / (threads * est);
     return mb < 1 ? 1 : (mb > 8 ? 8 : mb);
 }
@@ -338,11 +344,12 @@ __global__ void __launch_bounds__(THREADS, SWEEP ? 1 : min_blocks(NV, W, U, 1, T
     const bool tiled = a.tile_rows > 0;
     if (!tiled)
         cta_chunk(rp, a.row_begin, a.row_end, a.bounds, s_chunk);
-  for (long long t0 = (long long)a.row_begin + (long long)blockIdx.x * a.tile_rows; tiled ? t0 < a.row_end : t0 == (long long)a.row_begin + (long long)blockIdx.x * a.tile_rows;
-       t0 += tiled ? (long long)gridDim.x * a.tile_rows : 1)
+  // chunk mode: exactly one pass; tile mode: tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int n_tiles = tiled ? (a.row_end - a.row_begin + a.tile_rows - 1) / a.tile_rows : (int)blockIdx.x + 1;
+  for (int tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x)
   {
-    const int lo = tiled ? (int)t0 : s_chunk[0];
-    const int hi = tiled ? (int)min((long long)a.row_end, t0 + a.tile_rows) : s_chunk[1];
+    const int lo = tiled ? a.row_begin + tile_id * a.tile_rows : s_chunk[0];
+    const int hi = tiled ? min(a.row_end, lo + a.tile_rows) : s_chunk[1];
 
     // L2 prefetch by the TMA unit, issued before any work: the CTA's own slice of the A stream and
     // its share of B. Every later load then finds L2-hit latency instead of a first-touch DRAM miss.
@@ -409,6 +416,15 @@ __global__ void __launch_bounds__(THREADS, SWEEP ? 1 : min_blocks(NV, W, U, 1, T
             while (true)
             {
                 S b[U];
+#if defined(SPMM_ABLATE) && (SPMM_ABLATE & 8) // diagnostic: real index dependency, but every B row folded into 64 rows (all L1 hits)
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    b[u].template load<FULL>(Bk + (long long)(c[u] & 63) * a.ldb, mask);
+#elif defined(SPMM_ABLATE) && (SPMM_ABLATE & 16) // diagnostic: B rows folded into a 16 MB window (L2 hits, L1 misses)
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    b[u].template load<FULL>(Bk + (long long)((c[u] * 7919) & 32767) * a.ldb, mask);
+#else
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     b[u].template load<FULL>(Bk + (long long)c[u] * a.ldb, mask);
@@ -439,6 +455,7 @@ __global__ void __launch_bounds__(THREADS, SWEEP ? 1 : min_blocks(NV, W, U, 1, T
                 j = jn;
             }
         }
+#endif
         if constexpr (NP > 1)
         {
 #pragma unroll
@@ -447,7 +464,11 @@ __global__ void __launch_bounds__(THREADS, SWEEP ? 1 : min_blocks(NV, W, U, 1, T
                 for (int i = 0; i < NV * W; ++i)
                     acc.v[i] += __shfl_xor_sync(0xffffffffu, acc.v[i], off);
         }
+#if defined(SPMM_ABLATE) && (SPMM_ABLATE & 32) // diagnostic: no C stores (kept alive by an impossible condition)
+        if (valid && g == 0 && acc.v[0] == -1.2345e300)
+#else
         if (valid && g == 0)
+#endif
             acc.store(a.C + (long long)(row - a.c_row0) * a.ldc + tile0 + kl * W, mask);
         row = nrow;
         js = njs;

@@ -410,3 +410,30 @@ def test_round_robin_row_tiles(oracle, tile, k):
     B = np.random.default_rng(k).integers(1, 101, (5003, k)).astype(np.float64)
     got = gpu_multiply(spmm.SparseMatrix(va, ci, rp, 5003, 5003), B, k, "rows", {"rows.tile": tile})
     assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
+
+
+@pytest.mark.parametrize("k,tune", [(16, {}), (32, {"rows.unroll": 4}), (64, {}), (64, {"rows.nv": 1, "rows.threads": 256}),
+                                    (64, {"rows.nv": 2, "rows.threads": 1024, "rows.unroll": 1}), (128, {"rows.ctas_per_sm": 2}),
+                                    (192, {})])
+@pytest.mark.parametrize("shape", ["fem", "long_rows", "mostly_empty", "tiny"])
+def test_staged_kernel(oracle, k, tune, shape):
+    """A stream staged through a shared-memory ring (spmm_staged.cu): rows crossing tile borders, rows near the
+    2048-element limit, super-tiles of only empty rows, matrices smaller than one CTA chunk."""
+    cfg = {"fem": (31, 40000, 40000, 21, None, 97), "long_rows": (32, 3000, 3000, 300, 2048, 5),
+           "mostly_empty": (33, 9000, 9000, 0.02, 50, 0), "tiny": (34, 7, 7, 3, None, 0)}[shape]
+    seed, n, nc, mean, long_row, empty_every = cfg
+    rp, ci, va = random_csr(seed, n, nc, mean, long_row=long_row, empty_every=empty_every, positive=True)
+    if k > 64 and shape == "long_rows":
+        pytest.skip("covered at k <= 64")
+    B = np.random.default_rng(k).integers(1, 101, (nc, k)).astype(np.float64)
+    got = gpu_multiply(spmm.SparseMatrix(va, ci, rp, n, nc), B, k, "staged", tune)
+    assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
+
+
+def test_staged_kernel_refuses_long_rows():
+    rp, ci, va = random_csr(35, 50, 5000, 5, long_row=3000, positive=True)
+    with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, 50, 5000), 0, 0) as A:
+        B = torch.ones((5000, 16), dtype=torch.float64, device="cuda")
+        Cd = torch.empty((50, 16), dtype=torch.float64, device="cuda")
+        with pytest.raises(_cabi.SpmmError):
+            A.multiply(B.data_ptr(), 16, Cd.data_ptr(), "staged")

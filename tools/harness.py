@@ -126,6 +126,15 @@ def variant_list(k, full):
                             v.append((f"sweep nv={nv} np={np_} u={u} th={th} ctas={ctas}", "rows",
                                       {"rows.sweep": 1, "rows.kl": 8, "rows.nv": nv, "rows.np": np_, "rows.unroll": u,
                                        "rows.threads": th, "rows.ctas_per_sm": ctas}))
+    if k >= 16 and (k // 2) % 8 == 0:
+        for nv in (1, 2, 4):
+            if (k // 2) % (8 * nv):
+                continue
+            for u in (1, 2, 4):
+                for th in (256, 512, 1024):
+                    for ctas in ((1, 2) if th <= 512 else (1,)):
+                        v.append((f"staged nv={nv} u={u} th={th} ctas={ctas}", "staged",
+                                  {"rows.nv": nv, "rows.unroll": u, "rows.threads": th, "rows.ctas_per_sm": ctas}))
     for pf in (0, 1, 2, 3):
         v.append((f"rows pf={pf}", "rows", {"rows.prefetch": pf}))
         v.append((f"rows u=4 pf={pf}", "rows", {"rows.prefetch": pf, "rows.unroll": 4}))
