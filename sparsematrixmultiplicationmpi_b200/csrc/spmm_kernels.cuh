@@ -416,7 +416,13 @@ __global__ void __launch_bounds__(THREADS, SWEEP ? 1 : min_blocks(NV, W, U, 1, T
             while (true)
             {
                 S b[U];
-#if defined(SPMM_ABLATE) && (SPMM_ABLATE & 8) // diagnostic: real index dependency, but every B row folded into 64 rows (all L1 hits)
+#if defined(SPMM_ABLATE) && (SPMM_ABLATE & 2) // diagnostic: no B gather
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int i = 0; i < NV * W; ++i)
+                        b[u].v[i] = (double)c[u];
+#elif defined(SPMM_ABLATE) && (SPMM_ABLATE & 8) // diagnostic: real index dependency, but every B row folded into 64 rows (all L1 hits)
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     b[u].template load<FULL>(Bk + (long long)(c[u] & 63) * a.ldb, mask);
@@ -428,6 +434,7 @@ __global__ void __launch_bounds__(THREADS, SWEEP ? 1 : min_blocks(NV, W, U, 1, T
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     b[u].template load<FULL>(Bk + (long long)c[u] * a.ldb, mask);
+#endif
                 const int jn = j + NP * U;
                 const bool more = jn < je;
                 int cn[U];
@@ -455,7 +462,6 @@ __global__ void __launch_bounds__(THREADS, SWEEP ? 1 : min_blocks(NV, W, U, 1, T
                 j = jn;
             }
         }
-#endif
         if constexpr (NP > 1)
         {
 #pragma unroll

@@ -144,9 +144,21 @@ __global__ void __launch_bounds__(THREADS_, 1) spmm_staged_kernel(const StagedAr
                         for (int j = js; j < je; j += U)
                         {
                             S b[U];
+#if defined(SPMM_ABLATE) && (SPMM_ABLATE & 2) // diagnostic: no B gather
+#pragma unroll
+                            for (int u = 0; u < U; ++u)
+#pragma unroll
+                                for (int i = 0; i < NV * W; ++i)
+                                    b[u].v[i] = (double)c[u];
+#elif defined(SPMM_ABLATE) && (SPMM_ABLATE & 8) // diagnostic: every B row folded into 64 rows (all L1 hits)
+#pragma unroll
+                            for (int u = 0; u < U; ++u)
+                                b[u].template load<true>(Bk + (long long)(c[u] & 63) * a.ldb, 0xffffffffu);
+#else
 #pragma unroll
                             for (int u = 0; u < U; ++u)
                                 b[u].template load<true>(Bk + (long long)c[u] * a.ldb, 0xffffffffu);
+#endif
                             int cn[U];
                             double xn[U];
 #pragma unroll

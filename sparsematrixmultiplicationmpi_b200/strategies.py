@@ -84,6 +84,13 @@ class CudaCompute:
             A.multiply(B.data_ptr(), k, out.data_ptr(), self.kernel, torch.cuda.current_stream(self.device).cuda_stream)
         return out
 
+    def multiply_rows(self, A: DeviceCSR, row_begin: int, row_end: int, B: torch.Tensor, k: int, out: torch.Tensor):
+        """out[row_end-row_begin, k] = A[row_begin:row_end, :] * B (a row block of the shard, RowWise.cpp:36-50)."""
+        if row_end > row_begin and k:
+            A.multiply_rows(row_begin, row_end, B.data_ptr(), k, out.data_ptr(), self.kernel,
+                            torch.cuda.current_stream(self.device).cuda_stream)
+        return out
+
     def multiply_slab(self, A: DeviceCSR, B: torch.Tensor, k: int, k_begin: int, k_count: int, out: torch.Tensor):
         """Columns [k_begin, k_begin+k_count) of out = A * B, both with leading dimension k."""
         if A.n_rows and k_count:
@@ -158,6 +165,34 @@ class RowWise:
         """The reference call: local rows, then Gatherv to rank 0; None on the other ranks."""
         return self.gather(self.multiply_local(B))
 
+    def multiply_all_gather_overlapped(self, B: torch.Tensor, chunks: int = 4) -> torch.Tensor:
+        """Full C on every rank with the gather of row chunk c running over NVLink while chunk c+1 is
+        being multiplied: the local rows are cut into `chunks` pieces, each computed straight into its
+        slot of a chunk-major send buffer and all-gathered asynchronously as soon as it is ready.
+        Needs equal row counts on every rank (pad the matrix otherwise); falls back to all_gather()."""
+        if self.P == 1 or len(set(self.counts)) != 1 or chunks <= 1:
+            return self.all_gather(self.multiply_local(B))
+        rows = self.counts[0]
+        cb = -(-rows // chunks)
+        out = torch.empty((self.n_rows, self.k), dtype=torch.float64, device=B.device)
+        works = []
+        stage = []
+        for c in range(chunks):
+            r0, r1 = min(rows, c * cb), min(rows, (c + 1) * cb)
+            if r1 <= r0:
+                break
+            send = torch.empty((r1 - r0, self.k), dtype=torch.float64, device=B.device)
+            self.compute.multiply_rows(self.A, r0, r1, B, self.k, send)
+            recv = torch.empty((self.P * (r1 - r0), self.k), dtype=torch.float64, device=B.device)
+            works.append(dist.all_gather_into_tensor(recv, send, group=self.group, async_op=True))
+            stage.append((r0, r1, recv, send))
+        for w in works:
+            w.wait()
+        view = out.view(self.P, rows, self.k)
+        for r0, r1, recv, _ in stage:  # chunk-major -> row-major: one strided copy per chunk
+            view[:, r0:r1].copy_(recv.view(self.P, r1 - r0, self.k))
+        return out
+
 
 class ColumnBlocks:
     """Rank r owns columns J_r of A (contiguous, RowWise-style split of numCols) and rows J_r of B.
@@ -202,6 +237,33 @@ class ColumnBlocks:
             out.copy_(partial[:self.block])
             return out
         dist.reduce_scatter_tensor(out, partial, op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+    def multiply_reduce_scatter_overlapped(self, B_local: torch.Tensor, chunks: int = 4) -> torch.Tensor:
+        """Same result as reduce_scatter(multiply_local(B)) — this rank's block of C — but the partial
+        C is produced in reduce-scatter chunk order: for chunk c the rows c*cb..(c+1)*cb of EVERY rank's
+        block are multiplied into one contiguous (P x cb x k) buffer, whose reduce-scatter over NVLink
+        is started asynchronously while chunk c+1 is being multiplied."""
+        if self.P == 1 or chunks <= 1:
+            return self.reduce_scatter(self.multiply_local(B_local))
+        cb = -(-self.block // chunks)
+        out = torch.empty((self.block, self.k), dtype=torch.float64, device=B_local.device)
+        works, keep = [], []
+        for c in range(chunks):
+            b0, b1 = min(self.block, c * cb), min(self.block, (c + 1) * cb)
+            if b1 <= b0:
+                break
+            part = torch.empty((self.P, b1 - b0, self.k), dtype=torch.float64, device=B_local.device)
+            for p in range(self.P):
+                r0, r1 = min(self.n_rows, p * self.block + b0), min(self.n_rows, p * self.block + b1)
+                if r1 - r0 < b1 - b0:
+                    part[p, max(0, r1 - r0):].zero_()
+                self.compute.multiply_rows(self.A, r0, r1, B_local, self.k, part[p, :max(0, r1 - r0)])
+            works.append(dist.reduce_scatter_tensor(out[b0:b1], part.view(-1, self.k), op=dist.ReduceOp.SUM,
+                                                    group=self.group, async_op=True))
+            keep.append(part)
+        for w in works:
+            w.wait()
         return out
 
     def run(self, B_local: torch.Tensor) -> torch.Tensor | None:

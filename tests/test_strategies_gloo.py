@@ -42,6 +42,13 @@ class OracleCompute:
         out.copy_(t)
         return out
 
+    def multiply_rows(self, A, row_begin, row_end, B, k, out):
+        m = A.m
+        if row_end > row_begin:
+            blk = m.row_block(row_begin, row_end)
+            out.copy_(torch.from_numpy(self.o.spmm(blk.rowPtr, blk.colIndices, blk.values, B.numpy(), k)))
+        return out
+
     def multiply_slab(self, A, B, k, k_begin, k_count, out):
         m = A.m
         if k_count:
@@ -68,7 +75,12 @@ def _worker(rank, world, port, case, results):
         blk = spmm.ColumnBlocks.from_host(eng, m, k)
         out["colblk"] = blk.run(blk.local_B(Bt))
         out["colslab"] = spmm.ColumnSlabs.from_host(eng, m, k).run(Bt)
+        extra = {"colblk_overlap": blk.multiply_reduce_scatter_overlapped(blk.local_B(Bt), chunks=3),
+                 "colblk_plain": blk.reduce_scatter(blk.multiply_local(blk.local_B(Bt))),
+                 "row_overlap": row.multiply_all_gather_overlapped(Bt, chunks=3)}
+        assert torch.equal(extra["colblk_overlap"], extra["colblk_plain"])  # same sums in the same order
         out["nnz"] = spmm.NonZeroRanges.from_host(eng, m, k).run(Bt)
+        results[f"row_overlap_{rank}"] = extra["row_overlap"].numpy().copy()
         if rank == 0:
             results.update({name: t.numpy().copy() for name, t in out.items()})
         else:
@@ -108,6 +120,8 @@ def test_strategies_world(oracle, world, case):
     assert np.array_equal(results["row_allgather"], seq)
     for r in range(1, world):
         assert np.array_equal(results[f"allgather_{r}"], seq)
+    for r in range(world):
+        assert np.array_equal(results[f"row_overlap_{r}"], seq)
     # non-zero ranges: partial sums of cut rows added in rank order == the oracle's rank-order reduce
     assert np.array_equal(results["nnz"], oracle.spmm(rowptr, colidx, vals, B, k, "nnz", world))
     # column blocks regroup the sum by column block: equal up to FP64 summation order
