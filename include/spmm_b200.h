@@ -39,7 +39,8 @@ enum spmm_kernel
     SPMM_KERNEL_MERGE = 2, /* nnz-balanced merge-path with deterministic carry fix-up */
     SPMM_KERNEL_ROWBLOCK = 3, /* R consecutive rows per team over the union of their columns (needs spmm_csr_build_rowblocks) */
     SPMM_KERNEL_PACKED = 4,   /* warp-packed coalesced A stream (needs spmm_csr_build_packed) */
-    SPMM_KERNEL_STAGED = 5    /* CSR rows with the id/value stream staged through shared memory by cp.async (k multiple of 16, rows <= 2048 long) */
+    SPMM_KERNEL_STAGED = 5,   /* CSR rows with the id/value stream staged through shared memory by cp.async (k multiple of 16, rows <= 2048 long) */
+    SPMM_KERNEL_TILED = 6     /* row tiles whose B rows are staged in shared memory by TMA (needs spmm_csr_build_tiles; even k) */
 };
 
 const char *spmm_last_error(void);
@@ -97,6 +98,20 @@ int spmm_csr_rowblock_info(spmm_csr_t A, int *rows_per_block, long long *union_e
  * whose k is a multiple of 2*lanes_per_row. */
 int spmm_csr_build_packed(spmm_csr_t A, int rows_per_unit, int lanes_per_row);
 int spmm_csr_packed_info(spmm_csr_t A, int *rows_per_unit, int *lanes_per_row, long long *slots, double *fill_ratio);
+/* Optional fourth layout, the one AUTO prefers for k >= 16 when neighbouring rows share columns:
+ * tiles of rows_per_tile consecutive rows walked in order by one CTA that keeps a window of B-row
+ * boxes (box_rows consecutive rows of B each, brought in by one TMA box copy) in shared memory;
+ * non-zeros re-encoded as 16-byte records addressing that window, stragglers staged row by row
+ * (spmm_tiled.cu). rows_per_tile: 0 drops it, -1 picks the tile height
+ * that stages the fewest B rows among those that fit shared memory (none if no shape fits: the
+ * call still succeeds and the CSR kernels stay in charge), else a multiple of 4 in [4,256].
+ * box_rows: 0 (= 16), 4, 8, 16 or 32. The CSR arrays are untouched. The reference has no derived
+ * layouts; this serves SparseMatrixFatVectorMultiply.cpp:17-28. */
+int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows);
+/* reuse = non-zeros per B row staged in shared memory (per pass over the matrix); single_fraction =
+ * share of the non-zeros whose B row is staged on its own. Zeros when no layout is built. */
+int spmm_csr_tile_info(spmm_csr_t A, int *rows_per_tile, int *box_rows, int *window_slots, int *max_records,
+                       double *reuse, double *single_fraction);
 /* Sub-matrix A[:, col_begin:col_end) with local column ids (column-block strategy,
  * north_star reading of sparseMatrixFatVectorMultiplyColumnWise). Built on the device. */
 int spmm_csr_column_block(spmm_csr_t A, int col_begin, int col_end, spmm_csr_t *out);
@@ -168,7 +183,7 @@ int spmm_gen_fat_vector_device(int device, double *d_out, long long n_elems, lon
                                unsigned long long seed, void *stream);
 
 /* Measurement knob (not needed for correct results): override the automatic team shape.
- * keys: rows.kl rows.nv rows.np rows.unroll rows.vec rows.ctas_per_sm merge.items rowblock reset */
+ * keys: rows.kl rows.nv rows.np rows.unroll rows.vec rows.ctas_per_sm merge.items rowblock tiled tiled.kt tiled.ncw tiled.unroll tiled.thr tiled.chunk tiled.depth tiled.pool tiled.prefetch reset */
 int spmm_tune_set(const char *key, int value);
 
 #ifdef __cplusplus

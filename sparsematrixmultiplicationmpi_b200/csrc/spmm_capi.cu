@@ -234,6 +234,15 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "rows.prefetch") t.rows_prefetch = value;
     else if (k == "rows.tile") t.rows_tile = value;
     else if (k == "rows.staged") t.rows_staged = value;
+    else if (k == "tiled") t.tiled = value;
+    else if (k == "tiled.kt") t.tiled_kt = value;
+    else if (k == "tiled.ncw") t.tiled_ncw = value;
+    else if (k == "tiled.unroll") t.tiled_unroll = value;
+    else if (k == "tiled.thr") t.tiled_thr = value;
+    else if (k == "tiled.chunk") t.tiled_chunk = value;
+    else if (k == "tiled.depth") t.tiled_depth = value;
+    else if (k == "tiled.pool") t.tiled_pool = value;
+    else if (k == "tiled.prefetch") t.tiled_prefetch = value;
     else if (k == "rows.threads") t.rows_threads = value;
     else if (k == "rows.unroll") t.rows_unroll = value;
     else if (k == "rows.vec") t.rows_vec = value;
@@ -334,6 +343,7 @@ int spmm_csr_destroy(spmm_csr_t A)
     }
     free_rowblocks(A);
     free_packed(A);
+    free_tiles(A);
     drop_bounds(A, -1);
     cudaFree(A->d_B);
     cudaFree(A->d_C);
@@ -405,11 +415,22 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
     SPMM_REQUIRE(d_B != nullptr || A->nnz == 0, "d_B is NULL");
     SPMM_CUDA(cudaSetDevice(A->device));
     cudaStream_t s = (cudaStream_t)stream;
-    SPMM_REQUIRE(kernel >= SPMM_KERNEL_AUTO && kernel <= SPMM_KERNEL_STAGED, "unknown kernel id");
+    SPMM_REQUIRE(kernel >= SPMM_KERNEL_AUTO && kernel <= SPMM_KERNEL_TILED, "unknown kernel id");
+    SPMM_REQUIRE(kernel != SPMM_KERNEL_TILED || A->tl_T != 0, "tiled kernel requested but spmm_csr_build_tiles was not called (or found no fitting tile shape)");
     SPMM_REQUIRE(kernel != SPMM_KERNEL_PACKED || A->pk_R != 0, "packed kernel requested but spmm_csr_build_packed was not called");
     SPMM_REQUIRE(kernel != SPMM_KERNEL_ROWBLOCK || A->rb_R != 0, "row-block kernel requested but spmm_csr_build_rowblocks was not called");
     if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)
         return launch_merge(A, 0, A->n_rows, 0, A->nnz, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
+    // AUTO builds the tile layout the first time a multiply can use it (k >= 16, even, mid-sized matrix with
+    // regular rows): one-off, a few milliseconds, 16 bytes per non-zero next to the CSR. spmm_tune_set("tiled", 0)
+    // or an explicit spmm_csr_build_tiles(A, 0, 0) keeps the CSR kernels.
+    if (kernel == SPMM_KERNEL_AUTO && !A->tl_tried && A->tl_T == 0 && tuning().tiled != 0 && k_count >= 16 &&
+        k_count % 2 == 0 && A->nnz >= 200000 && A->nnz <= (64ll << 20))
+    {
+        A->tl_tried = true;
+        if (spmm_csr_build_tiles(A, -1, 0) != SPMM_OK)
+            free_tiles(A); // not fatal: the CSR kernels stay in charge
+    }
     return launch_rows(A, 0, A->n_rows, 0, A->nnz, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count,
                        kernel == SPMM_KERNEL_ROWS ? 0 : (kernel == SPMM_KERNEL_AUTO ? 1 : kernel), s);
 }

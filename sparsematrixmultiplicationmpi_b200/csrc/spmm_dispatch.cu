@@ -84,6 +84,20 @@ int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_l
     const bool whole = row_begin == 0 && row_end == A->n_rows && nnz_lo == 0 && nnz_hi == A->nnz && c_row0 == 0;
     if (derived && whole)
     {
+        if (derived == 6 || (derived == 1 && A->tl_T && t.tiled != 0))
+        {
+            // tile layout: worth it once a B row piece is >= 128 bytes and rows of a tile share B rows
+            const bool fits = tiled_shape_ok(A, d_B, ldb, d_C, ldc, kc);
+            const double staged = (double)A->tl_box_rows_loaded + (double)A->tl_single_rows;
+            const double reuse = staged > 0 ? (double)A->nnz / staged : 0.0;
+            if (fits && (derived == 6 || t.tiled == 1 || (kc >= 16 && reuse >= 2.0 && A->tl_drains * 20 <= A->tl_tiles)))
+                return launch_tiled(A, d_B, ldb, d_C, ldc, kc, stream);
+            if (derived == 6)
+            {
+                set_error("tiled kernel: needs even k, even leading dimensions and 16-byte aligned B and C");
+                return SPMM_ERR_UNSUPPORTED;
+            }
+        }
         Shape ps = s;
         if (A->pk_R && A->pk_kl != s.kl && (kc % (2 * A->pk_kl) == 0) && s.w == 2)
         {

@@ -57,6 +57,15 @@ struct Tuning
     int rows_tile = 0;      // 0 auto, > 0 rows per round-robin tile, -1 never tile (one chunk per CTA)
     int rows_prefetch = -1; // -1 auto; bit0 A chunk, bit1 B share: TMA prefetch into L2 at kernel start
     int rowblock = -1;      // -1 auto, 0 never use the row-block format, 1 always when built
+    int tiled = -1;         // -1 auto, 0 never use the tile layout, 1 always when built
+    int tiled_kt = 0;       // tiled kernel: k-tile width (16, 32)
+    int tiled_ncw = 0;      // consumer warps (8, 12, 16)
+    int tiled_unroll = 0;   // records in flight per team (2, 4)
+    int tiled_thr = 0;      // build: non-zeros a box needs in a tile to be loaded as a box (else single rows)
+    int tiled_chunk = 0;    // build: tiles per chunk
+    int tiled_depth = 0;    // build: work items in flight (2..8)
+    int tiled_pool = 0;     // build: rows of the singles pool
+    int tiled_prefetch = -1; // launch: tiles ahead whose blob is prefetched into L2 (-1 auto)
 };
 Tuning &tuning();
 
@@ -95,6 +104,13 @@ struct spmm_csr_s
     long long pk_groups = 0;
     int *d_sptr = nullptr, *d_pcol = nullptr;
     double *d_pval = nullptr;
+    // B-staged row tiles (spmm_tiled.cu), optional
+    int tl_T = 0, tl_BR = 0, tl_tiles = 0, tl_NS = 0, tl_POOL = 0, tl_max_recs = 0, tl_chunk = 0, tl_kt = 0, tl_depth = 0, tl_drains = 0;
+    long long tl_box_rows_loaded = 0, tl_single_rows = 0; // B rows staged per pass over the matrix
+    bool tl_tried = false;                                // AUTO already attempted the lazy build
+    unsigned char *d_tblob = nullptr;
+    void *d_tdesc = nullptr, *d_tloads = nullptr;
+    int *d_tsingles = nullptr;
     // precomputed CTA cuts per (kind, grid size): kind 0 = rows of the CSR, 1 = row blocks, 2 = packed slices
     mutable std::map<long long, int *> bounds;
     // merge-path scratch (carry rows), grown on demand
@@ -109,7 +125,7 @@ namespace spmm
 // rows [row_begin,row_end), each clipped to the non-zero range [nnz_lo,nnz_hi); row c_row0 is stored at d_C[0]
 int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
                 const double *d_B, long long ldb, double *d_C, long long ldc, int kc, int derived,
-                cudaStream_t stream); // derived: 0 CSR row kernel only, 1 best available, 3 row-block, 4 packed, 5 staged
+                cudaStream_t stream); // derived: 0 CSR row kernel only, 1 best available, 3 row-block, 4 packed, 5 staged, 6 tiled
 int launch_merge(spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
                  const double *d_B, long long ldb, double *d_C, long long ldc, int kc, cudaStream_t stream);
 bool rowblock_shape_ok(int w, int kl, int nv, int tiles, int kc);
@@ -120,6 +136,10 @@ bool packed_shape_ok(const spmm_csr_s *A, int w, int kl, int nv, int tiles, int 
 int launch_packed(const spmm_csr_s *A, int nv, int tiles, const double *d_B, long long ldb, double *d_C, long long ldc,
                   cudaStream_t stream);
 void free_packed(spmm_csr_s *A);
+bool tiled_shape_ok(const spmm_csr_s *A, const double *d_B, long long ldb, const double *d_C, long long ldc, int kc);
+int launch_tiled(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int kc,
+                 cudaStream_t stream);
+void free_tiles(spmm_csr_s *A);
 bool staged_shape_ok(const spmm_csr_s *A, int w, int kl, int nv, int tiles, int kc);
 int launch_staged(const spmm_csr_s *A, int nv, int tiles, const double *d_B, long long ldb, double *d_C, long long ldc,
                   cudaStream_t stream);

@@ -171,9 +171,15 @@ struct Slice
     }
     __device__ __forceinline__ void fma(double a, const Slice &b)
     {
+#if defined(SPMM_ABLATE) && (SPMM_ABLATE & 64) // diagnostic: one integer op per loaded double instead of a DFMA
+#pragma unroll
+        for (int i = 0; i < NV * W; ++i)
+            v[i] = __longlong_as_double(__double_as_longlong(v[i]) ^ __double_as_longlong(b.v[i]) ^ __double_as_longlong(a));
+#else
 #pragma unroll
         for (int i = 0; i < NV * W; ++i)
             v[i] = ::fma(a, b.v[i], v[i]);
+#endif
     }
 };
 

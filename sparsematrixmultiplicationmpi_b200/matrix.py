@@ -151,6 +151,18 @@ class DeviceCSR:
         _cabi.check(_cabi.lib().spmm_csr_packed_info(self.handle, C.byref(r), C.byref(l), C.byref(n), C.byref(f)))
         return {"rows_per_unit": r.value, "lanes_per_row": l.value, "slots": n.value, "fill_ratio": f.value}
 
+    def build_tiles(self, rows_per_tile: int = -1, box_rows: int = 0) -> dict:
+        """Row tiles with TMA-staged B rows (spmm_tiled.cu); -1 = largest tile that fits shared memory."""
+        _cabi.check(_cabi.lib().spmm_csr_build_tiles(self.handle, rows_per_tile, box_rows))
+        return self.tile_info()
+
+    def tile_info(self) -> dict:
+        t, b, ns, mr, r, sf = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_double(), C.c_double()
+        _cabi.check(_cabi.lib().spmm_csr_tile_info(self.handle, C.byref(t), C.byref(b), C.byref(ns), C.byref(mr),
+                                                   C.byref(r), C.byref(sf)))
+        return {"rows_per_tile": t.value, "box_rows": b.value, "window_slots": ns.value, "max_records": mr.value,
+                "reuse": r.value, "single_fraction": sf.value}
+
     def nnz_range_rows(self, nnz_begin: int, nnz_end: int) -> tuple[int, int]:
         a, b = C.c_int(), C.c_int()
         _cabi.check(_cabi.lib().spmm_nnz_range_rows(self.handle, nnz_begin, nnz_end, C.byref(a), C.byref(b)))

@@ -437,3 +437,128 @@ def test_staged_kernel_refuses_long_rows():
         Cd = torch.empty((50, 16), dtype=torch.float64, device="cuda")
         with pytest.raises(_cabi.SpmmError):
             A.multiply(B.data_ptr(), 16, Cd.data_ptr(), "staged")
+
+
+# ---------------------------------------------------------------- row tiles with TMA-staged B rows (spmm_tiled.cu)
+def banded_csr(seed, n, mean_len, half_band, planes=(0,), long_row=None, empty_every=0):
+    """FEM-like rows: columns cluster in windows of +-half_band around i + p for each plane offset p."""
+    rng = np.random.default_rng(seed)
+    lens = rng.poisson(mean_len, n)
+    if empty_every:
+        lens[::empty_every] = 0
+    if long_row is not None:
+        lens[n // 2] = long_row
+    rowptr = np.concatenate(([0], np.cumsum(lens))).astype(np.int32)
+    rows = np.repeat(np.arange(n), lens)
+    centre = rows + rng.choice(np.asarray(planes), rows.size)
+    col = np.clip(centre + rng.integers(-half_band, half_band + 1, rows.size), 0, n - 1).astype(np.int32)
+    for i in range(n):
+        col[rowptr[i]:rowptr[i + 1]].sort()
+    return rowptr, col, 0.5 + rng.random(rows.size)
+
+
+def tiled_multiply(m, B, k, T, BR, tune=None, kernel="tiled"):
+    _cabi.tune("reset", 0)
+    for key, val in (tune or {}).items():
+        _cabi.tune(key, val)
+    try:
+        with spmm.DeviceCSR.from_host(m, 0) as A:
+            info = A.build_tiles(T, BR)
+            dB = dev(B)
+            dC = torch.full((m.numRows, k), np.nan, dtype=torch.float64, device="cuda")
+            A.multiply(dB.data_ptr(), k, dC.data_ptr(), kernel, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            return dC.cpu().numpy(), info
+    finally:
+        _cabi.tune("reset", 0)
+
+
+TILED_SHAPES = {
+    # name: (n, mean_len, half_band, planes, long_row, empty_every)
+    "fem3": (6000, 22, 12, (-700, 0, 700), None, 0),
+    "fem_hub_empty": (5003, 18, 20, (-300, 0, 300), 900, 7),
+    "narrow": (3001, 5, 3, (0,), None, 3),
+    "tiny": (5, 3, 2, (0,), None, 0),
+}
+
+
+@pytest.mark.parametrize("shape", list(TILED_SHAPES))
+@pytest.mark.parametrize("k", [2, 8, 16, 30, 32, 64, 100])
+def test_tiled_kernel_vs_oracle(oracle, shape, k):
+    n, mean, hb, planes, long_row, ee = TILED_SHAPES[shape]
+    rp, ci, va = banded_csr(31, n, mean, hb, planes, long_row, ee)
+    B = np.random.default_rng(k).integers(1, 101, (n, k)).astype(np.float64)
+    got, info = tiled_multiply(spmm.SparseMatrix(va, ci, rp, n, n), B, k, -1, 0)
+    assert info["rows_per_tile"] > 0 and info["reuse"] > 0
+    assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
+
+
+@pytest.mark.parametrize("T,BR", [(8, 4), (16, 16), (64, 8), (64, 32), (128, 16), (248, 16)])
+@pytest.mark.parametrize("tune", [{}, {"tiled.kt": 32}, {"tiled.kt": 32, "tiled.ncw": 12, "tiled.depth": 2},
+                                  {"tiled.ncw": 16, "tiled.unroll": 2, "tiled.depth": 8}, {"tiled.ncw": 4, "tiled.unroll": 8},
+                                  {"tiled.thr": 1, "tiled.chunk": 3}, {"tiled.thr": 100, "tiled.depth": 3}])
+def test_tiled_shapes_and_teams(oracle, T, BR, tune):
+    """Explicit tile heights / box heights x k-tile, warps, pipeline depth, box threshold (all boxes .. all single
+    rows), chunk length: split rows (the 900-long row: 8 segments folded by shuffles), empty rows, ragged last
+    tile and k-tile (k=48 with k-tile 32), window wrap-around across passes."""
+    n, k = 3003, 48
+    rp, ci, va = banded_csr(37, n, 14, 16, (-200, 0, 200), 900, 11)
+    B = np.random.default_rng(3).integers(1, 101, (n, k)).astype(np.float64)
+    try:
+        got, info = tiled_multiply(spmm.SparseMatrix(va, ci, rp, n, n), B, k, T, BR, tune)
+    except _cabi.SpmmError as e:
+        assert e.status == _cabi.SPMM_ERR_UNSUPPORTED  # this tile shape needs more shared memory than an SM has
+        return
+    assert info["rows_per_tile"] == T and info["box_rows"] == BR
+    assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
+
+
+def test_tiled_auto_dispatch_and_refusals(oracle):
+    # scattered columns: no tile shape fits -> build succeeds with no layout, AUTO keeps the CSR kernels
+    rp, ci, va = random_csr(41, 4000, 400000, 30, positive=True)
+    m = spmm.SparseMatrix(va, ci, rp, 4000, 400000)
+    B = np.random.default_rng(4).integers(1, 101, (400000, 16)).astype(np.float64)
+    got, info = tiled_multiply(m, B, 16, -1, 0, kernel="auto")
+    assert_close_rel(got, oracle.spmm(rp, ci, va, B, 16), tol=REL_TOL)
+    with spmm.DeviceCSR.from_host(m, 0) as A:
+        if A.build_tiles(-1)["rows_per_tile"] == 0:
+            dB, dC = dev(B), torch.zeros((4000, 16), dtype=torch.float64, device="cuda")
+            with pytest.raises(_cabi.SpmmError):
+                A.multiply(dB.data_ptr(), 16, dC.data_ptr(), "tiled")
+    # odd k: the tiled kernel refuses, AUTO falls through to the row kernels
+    rp, ci, va = banded_csr(43, 2000, 20, 10)
+    m = spmm.SparseMatrix(va, ci, rp, 2000, 2000)
+    B = np.random.default_rng(5).integers(1, 101, (2000, 33)).astype(np.float64)
+    got, info = tiled_multiply(m, B, 33, -1, 0, kernel="auto")
+    assert info["rows_per_tile"] > 0
+    assert_close_rel(got, oracle.spmm(rp, ci, va, B, 33), tol=REL_TOL)
+    with pytest.raises(_cabi.SpmmError):
+        tiled_multiply(m, B, 33, -1, 0, kernel="tiled")
+    # AUTO with the layout built and k >= 16 takes the tiled kernel: same numbers as asking for it
+    B = np.random.default_rng(6).integers(1, 101, (2000, 64)).astype(np.float64)
+    a, _ = tiled_multiply(m, B, 64, -1, 0, kernel="auto")
+    b, _ = tiled_multiply(m, B, 64, -1, 0, kernel="tiled")
+    assert np.array_equal(a, b)
+    assert_close_rel(a, oracle.spmm(rp, ci, va, B, 64), tol=REL_TOL)
+
+
+def test_tiled_mixed_sign_duplicates_and_strided(oracle, golden_multiply):
+    g = golden_multiply
+    rp, ci, va, B = g["k8_rowptr"], g["k8_colidx"], g["k8_vals"], g["k8_B"]
+    n = len(rp) - 1
+    got, info = tiled_multiply(spmm.SparseMatrix(va, ci, rp, n, n), B, 8, 32, 16)
+    assert_close_rel(got, g["k8_C_seq"], rp, ci, va, B)
+    # k-slab of a wider B/C (ColumnWise.cpp:25-48): columns [16, 48) of 64 through the strided entry point
+    rp, ci, va = banded_csr(47, 2500, 20, 10, (-100, 0, 100))
+    m = spmm.SparseMatrix(va, ci, rp, 2500, 2500)
+    B = np.random.default_rng(7).integers(1, 101, (2500, 64)).astype(np.float64)
+    with spmm.DeviceCSR.from_host(m, 0) as A:
+        assert A.build_tiles(-1)["rows_per_tile"] > 0
+        dB, dC = dev(B), torch.zeros((2500, 64), dtype=torch.float64, device="cuda")
+        _cabi.check(_cabi.lib().spmm_multiply_strided_device(A.handle, dB.data_ptr(), 64, dC.data_ptr(), 64, 16, 32,
+                                                             _cabi.KERNEL_TILED, None))
+        torch.cuda.synchronize()
+        out = dC.cpu().numpy()
+    ref = oracle.spmm(rp, ci, va, B, 64)
+    assert_close_rel(out[:, 16:48], ref[:, 16:48], tol=REL_TOL)
+    assert not out[:, :16].any() and not out[:, 48:].any()

@@ -175,6 +175,46 @@ def cfg2(args, emit, dev):
                 A.close()
             del sets
             torch.cuda.empty_cache()
+        if k >= 2 and k % 2 == 0 and args.tiles:
+            for spec in args.tiles.split(","):
+                f = [int(x) for x in spec.split("x")]
+                T, BR = f[0], f[1]
+                kt = f[2] if len(f) > 2 else 0
+                thr = f[3] if len(f) > 3 else 0
+                depth = f[4] if len(f) > 4 else 0
+
+                def make(s, T=T, BR=BR, kt=kt, thr=thr, depth=depth):
+                    A = spmm.DeviceCSR.from_host(host, dev.index, 0)
+                    _cabi.tune("reset", 0)
+                    _cabi.tune("tiled.kt", kt)
+                    _cabi.tune("tiled.thr", thr)
+                    _cabi.tune("tiled.depth", depth)
+                    try:
+                        A.build_tiles(T, BR)
+                    finally:
+                        _cabi.tune("reset", 0)
+                    return A
+                try:
+                    sets = operand_sets(make, n, n, k, dev, fp)
+                except Exception as e:
+                    emit({"config": "cfg2", "k": k, "tiles": spec, "error": str(e)[:200]})
+                    continue
+                info = sets[0][0].tile_info()
+                if not info["rows_per_tile"]:
+                    emit({"config": "cfg2", "k": k, "tiles": spec, "error": "no tile shape fits", "info": info})
+                    continue
+                base = f"tiled {spec} T={info['rows_per_tile']} NS={info['window_slots']}"
+                vs = [(base, "tiled", {})]
+                if args.variants:
+                    vs += [(f"{base} ncw={ncw} u={u}", "tiled", {"tiled.ncw": ncw, "tiled.unroll": u})
+                           for ncw, u in ((4, 8), (8, 2), (8, 8), (12, 2), (12, 4), (16, 2), (16, 4))]
+                    vs += [(f"{base} ncw=16 u=4 pf={pf}", "tiled", {"tiled.ncw": 16, "tiled.unroll": 4, "tiled.prefetch": pf})
+                           for pf in (2, 4, 8, 16)]
+                run_variants("cfg2", sets, k, vs, args.iters, emit, host.nnz, n, {"tiles": info})
+                for A, _, _ in sets:
+                    A.close()
+                del sets
+                torch.cuda.empty_cache()
         if k >= 16 and args.packed:
             for R, kl in ((1, 8), (1, 16), (2, 8), (2, 16)):
                 if (k // 2) % kl:
@@ -404,6 +444,7 @@ def main():
     ap.add_argument("--variants", action="store_true")
     ap.add_argument("--cpu", action="store_true", help="also time the reference CPU code on cfg2")
     ap.add_argument("--packed", action="store_true", help="also time the warp-packed stream layouts on cfg2")
+    ap.add_argument("--tiles", default="", help="cfg2: tile layouts to time, e.g. -1x16,64x16,32x8x32x2 (rows_per_tile x box_rows [x k-tile [x box threshold [x depth]]])")
     ap.add_argument("--only", default="", help="regex: run only the variants whose label matches")
     ap.add_argument("--rowblocks", default="0,2,4", help="row-block layouts to time on cfg2")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "harness.jsonl"))
