@@ -16,8 +16,8 @@
 //     boxes (hub couplings, stragglers) get one "single" B row each in a small ring pool. For FEM-like
 //     rows the window slides with the tiles: a B row is fetched from L2 about once per band and chunk
 //     instead of once per non-zero.
-//   * every non-zero becomes a 16-byte record {value, slab row}; slab row = slot*BR + column%BR, or a
-//     pool row. The rows of a tile are grouped into "units" of 8 rows of similar length (one row per
+//   * every non-zero becomes a value (8 bytes) and a 16-bit slab row id (rows padded to 4 ids); slab row =
+//     slot*BR + column%BR, or a pool row. The rows of a tile are grouped into "units" of 8 rows of similar length (one row per
 //     team of 4 lanes); a row of 48+ non-zeros becomes a unit of its own, cut in 8 segments. Header,
 //     unit table and records of a tile form one contiguous 16-byte aligned blob; per tile there is a
 //     load list (box, slot) and a singles list (column).
@@ -98,6 +98,12 @@ enum
 };
 
 __host__ __device__ inline int units_cap(int T) { return (T + UW - 1) / UW + TB_SPLITCAP; }
+// Byte offset of tile t's blob (first non-zero e0): a closed form that leaves room for the header, the padded
+// value stream (8 e) and the padded id stream (2 (e + 3T) at most) of every earlier tile.
+__host__ __device__ inline unsigned long long blob_offset(int t, long long e0, int hdr_bytes, int T)
+{
+    return (unsigned long long)t * (unsigned long long)(hdr_bytes + 8 * T + 48) + ((10ull * (unsigned long long)e0 + 15ull) & ~15ull);
+}
 
 // Builder: one CTA per chunk, tiles replayed in order. DRY: only count.
 template <bool DRY>
@@ -120,7 +126,9 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
     __shared__ int s_ubox[TB_UMAX], s_ucnt[TB_UMAX], s_uslot[TB_UMAX];
     __shared__ int s_slot_box[TB_NSMAX], s_slot_stamp[TB_NSMAX];
     __shared__ int s_rp[TB_MAXT + 1];
-    __shared__ unsigned s_units[(TB_MAXT / UW + 1 + TB_SPLITCAP) * UW];
+    __shared__ unsigned s_units[(TB_MAXT / UW + 1 + TB_SPLITCAP) * UW]; // word 0 of the unit entries
+    __shared__ int s_uidx[(TB_MAXT / UW + 1 + TB_SPLITCAP) * UW];      // word 1: first slot of the row (segment) in the id stream
+    __shared__ int s_ioff[TB_MAXT + 1];                                 // id-stream offset of each row (rows padded to 4 ids)
     __shared__ int s_nload, s_nsplit, s_pool_ptr, s_drain;
     __shared__ int s_recent[TB_DMAX]; // singles of the last `depth` tiles
 
@@ -268,11 +276,22 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
             if (s_rp[r + 1] - s_rp[r] >= TB_SPLIT)
                 atomicAdd(&s_nsplit, 1);
         __syncthreads();
+        // id stream: every row starts at a multiple of 4 ids, so a team reads 4 ids with one 8-byte load
+        for (int r = threadIdx.x; r <= nr; r += TB_THREADS)
+        {
+            int o = 0;
+            for (int q = 0; q < r; ++q)
+                o += (s_rp[q + 1] - s_rp[q] + 3) & ~3;
+            s_ioff[r] = o;
+        }
         const int n_split = min(s_nsplit, TB_SPLITCAP);
         const int n_normal_units = (nr - n_split + UW - 1) / UW;
         const int n_units = n_normal_units + n_split;
         for (int i = threadIdx.x; i < n_units * UW; i += TB_THREADS)
+        {
             s_units[i] = UE_PAD_ROW << 23; // padding entry: no row, no records
+            s_uidx[i] = 0;
+        }
         __syncthreads();
         for (int r = threadIdx.x; r < nr; r += TB_THREADS)
         {
@@ -287,12 +306,13 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
             }
             if (srank >= 0 && srank < TB_SPLITCAP)
             {
-                const int seg = (len + UW - 1) / UW;
+                const int seg = (((len + UW - 1) / UW) + 3) & ~3; // segments start at multiples of 4 ids
                 for (int j = 0; j < UW; ++j)
                 {
                     const int b = min(j * seg, len), e = min(b + seg, len);
                     s_units[(n_normal_units + srank) * UW + j] =
                         (unsigned)(s_rp[r] + b) | ((unsigned)(e - b) << 13) | ((unsigned)r << 23) | 0x80000000u;
+                    s_uidx[(n_normal_units + srank) * UW + j] = s_ioff[r] + b;
                 }
             }
             else
@@ -312,6 +332,7 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
                 if (len > 0x3FF)
                     atomicOr(status + ST_FAIL, 8); // more than TB_SPLITCAP very long rows in one tile
                 s_units[rank] = (unsigned)s_rp[r] | ((unsigned)(len & 0x3FF) << 13) | ((unsigned)r << 23);
+                s_uidx[rank] = s_ioff[r];
             }
         }
         __syncthreads();
@@ -384,24 +405,31 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
         if (DRY)
             continue;
 
-        const unsigned off16 = (unsigned)(((unsigned long long)t * p.hdr_bytes + 16ull * (unsigned long long)e0) >> 4);
+        // blob = header | unit table | values (8 bytes per non-zero) | slab-row ids (2 bytes, rows padded to 4 ids)
+        const int n_ids = s_ioff[nr];
+        const unsigned val_bytes = ((unsigned)n * 8u + 15u) & ~15u, id_bytes = ((unsigned)n_ids * 2u + 15u) & ~15u;
+        const unsigned off16 = (unsigned)(blob_offset(t, e0, p.hdr_bytes, p.T) >> 4);
         unsigned char *mine = blob + ((unsigned long long)off16 << 4);
         if (threadIdx.x == 0)
         {
             TileDesc d;
             d.off16 = off16;
-            d.bytes = (unsigned)(p.hdr_bytes + 16 * n);
+            d.bytes = (unsigned)p.hdr_bytes + val_bytes + id_bytes;
             d.counts = (unsigned)s_nload | ((unsigned)ns_total << 16) | ((unsigned)fence << 29);
             d.pool_start = pool_start;
             tdesc[t] = d;
-            *reinterpret_cast<int4 *>(mine) = make_int4(n, n_units, nr, 0);
+            *reinterpret_cast<int4 *>(mine) = make_int4(n, n_units, nr, (int)((unsigned)p.hdr_bytes + val_bytes));
         }
-        unsigned *units_out = reinterpret_cast<unsigned *>(mine + 16);
-        for (int i = threadIdx.x; i < (p.hdr_bytes - 16) / 4; i += TB_THREADS)
-            units_out[i] = i < n_units * UW ? s_units[i] : (UE_PAD_ROW << 23);
-        int4 *rec_out = reinterpret_cast<int4 *>(mine + p.hdr_bytes);
+        uint2 *units_out = reinterpret_cast<uint2 *>(mine + 16);
+        for (int i = threadIdx.x; i < (p.hdr_bytes - 16) / 8; i += TB_THREADS)
+            units_out[i] = i < n_units * UW ? make_uint2(s_units[i], (unsigned)s_uidx[i]) : make_uint2(UE_PAD_ROW << 23, 0u);
+        double *val_out = reinterpret_cast<double *>(mine + p.hdr_bytes);
+        unsigned short *id_out = reinterpret_cast<unsigned short *>(mine + p.hdr_bytes + val_bytes);
+        for (int i = threadIdx.x; i < (int)(id_bytes / 2); i += TB_THREADS)
+            id_out[i] = 0; // padding ids are never used for arithmetic; keep them inside the slab
         if (threadIdx.x < ns_total - ns_real)
             singles[(size_t)t * p.POOL + ns_real + threadIdx.x] = 0; // padding rows: any valid B row
+        __syncthreads(); // id padding written before the real ids
 #pragma unroll
         for (int i = 0; i < TB_ITEMS; ++i)
         {
@@ -415,8 +443,18 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
                 sr = p.NS * BR + (pool_start + spos) % p.POOL;
                 ++spos;
             }
-            const long long vb = __double_as_longlong(vals[e0 + j]);
-            rec_out[j] = make_int4((int)(vb & 0xFFFFFFFFll), (int)(vb >> 32), sr, 0);
+            // row holding record j: last local row with s_rp[r] <= j (skips empty rows)
+            int lo = 0, hi = nr;
+            while (hi - lo > 1)
+            {
+                const int mid = (lo + hi) >> 1;
+                if (s_rp[mid] <= j)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            val_out[j] = vals[e0 + j];
+            id_out[s_ioff[lo] + (j - s_rp[lo])] = (unsigned short)sr;
         }
     }
     if (threadIdx.x == 0)
@@ -479,10 +517,16 @@ __device__ __forceinline__ double2 lds128d(unsigned addr)
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ unsigned lds32(unsigned addr)
+__device__ __forceinline__ uint2 lds64u(unsigned addr)
 {
-    unsigned v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds64d(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
 }
 
@@ -721,32 +765,46 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
         const unsigned blob = s_blob + st * a.blob_stride;
         mbar_wait(full + 8 * st, use & 1);
         const long long c1 = TCLK();
-        const int n_units = (int)lds32(blob + 4);
+        const int4 hdr = lds128i(blob);
+        const int n_units = hdr.y;
         const unsigned units = blob + 16;
-        const unsigned recs = blob + a.hdr_bytes;
+        const unsigned vals_s = blob + a.hdr_bytes, ids_s = blob + (unsigned)hdr.w;
         double *__restrict__ Ck = a.C + (long long)cur.t * a.T * a.ldc + k0;
 
         // units round-robin over the warps, rotated by the item so the remainder moves around
         for (int u = (warp + w) % NCW; !T_NO_COMPUTE && u < n_units; u += NCW)
         {
-            const unsigned e = lds32(units + (u * UW + tw) * 4);
-            const int begin = e & 0x1FFF, len = (e >> 13) & 0x3FF, row = (e >> 23) & 0xFF;
-            const bool split = (e >> 31) != 0;
+            const uint2 e = lds64u(units + (u * UW + tw) * 8);
+            const int begin = e.x & 0x1FFF, len = (e.x >> 13) & 0x3FF, row = (e.x >> 23) & 0xFF;
+            const bool split = (e.x >> 31) != 0;
             const int maxlen = __reduce_max_sync(0xFFFFFFFFu, len);
             double2 acc[NL];
 #pragma unroll
             for (int i = 0; i < NL; ++i)
                 acc[i] = make_double2(0.0, 0.0);
-            const unsigned rbase = recs + begin * 16;
+            const unsigned vbase = vals_s + begin * 8, ibase = ids_s + e.y * 2;
             for (int i = 0; i < maxlen; i += U)
             {
-                int4 r[U];
+                static_assert(U % 4 == 0, "ids are read four at a time");
+                double v[U];
+                unsigned id[U];
+#pragma unroll
+                for (int g = 0; g < U; g += 4)
+                {
+                    uint2 four = make_uint2(0u, 0u);
+                    if (i + g < len)
+                        four = lds64u(ibase + (i + g) * 2);
+                    id[g] = four.x & 0xFFFFu;
+                    id[g + 1] = four.x >> 16;
+                    id[g + 2] = four.y & 0xFFFFu;
+                    id[g + 3] = four.y >> 16;
+                }
 #pragma unroll
                 for (int q = 0; q < U; ++q)
                 {
-                    r[q] = make_int4(0, 0, 0, 0);
+                    v[q] = 0.0;
                     if (i + q < len)
-                        r[q] = lds128i(rbase + (i + q) * 16);
+                        v[q] = lds64d(vbase + (i + q) * 8);
                 }
                 double2 b[U][NL];
 #pragma unroll
@@ -756,17 +814,16 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
                     {
                         b[q][x] = make_double2(0.0, 0.0);
                         if (i + q < len)
-                            b[q][x] = lds128d(s_slab + (unsigned)r[q].z * (KT * 8) + colo[x] * 8);
+                            b[q][x] = lds128d(s_slab + id[q] * (KT * 8) + colo[x] * 8);
                     }
 #pragma unroll
                 for (int q = 0; q < U; ++q)
                 {
-                    const double v = __hiloint2double(r[q].y, r[q].x);
 #pragma unroll
                     for (int x = 0; x < NL; ++x)
                     {
-                        acc[x].x = fma(v, b[q][x].x, acc[x].x);
-                        acc[x].y = fma(v, b[q][x].y, acc[x].y);
+                        acc[x].x = fma(v[q], b[q][x].x, acc[x].x);
+                        acc[x].y = fma(v[q], b[q][x].y, acc[x].y);
                     }
                 }
             }
@@ -876,7 +933,7 @@ int lg2(int x)
     return l;
 }
 
-unsigned hdr_bytes_of(int T) { return 16u + 32u * (unsigned)units_cap(T); }
+unsigned hdr_bytes_of(int T) { return 16u + 64u * (unsigned)units_cap(T); }
 
 struct TiledSmem
 {
@@ -886,7 +943,7 @@ struct TiledSmem
 TiledSmem tiled_smem(int kt, int depth, int T, int BR, int NS, int POOL, int max_recs)
 {
     TiledSmem m;
-    m.blob_stride = (hdr_bytes_of(T) + 16ull * max_recs + 127) & ~127ull;
+    m.blob_stride = (hdr_bytes_of(T) + 10ull * max_recs + 6ull * T + 32 + 127) & ~127ull; // values + ids (rows padded to 4)
     m.slab_off = (BLOB_OFF + (size_t)depth * m.blob_stride + 1023) & ~1023ull;
     m.slab_bytes = ((size_t)NS * BR + (size_t)POOL) * kt * 8;
     m.total = m.slab_off + m.slab_bytes + 1024; // + slack: the kernel aligns its base to 1024
@@ -982,15 +1039,16 @@ int launch_tiled_ncw(const spmm_csr_s *A, int ncw, int u, const double *d_B, lon
         return launch_tiled_t<KT, N, UU>(A, d_B, ldb, d_C, ldc, kc, s);
     SPMM_TILED_CASE(4, 4)
     SPMM_TILED_CASE(4, 8)
-    SPMM_TILED_CASE(8, 2)
     SPMM_TILED_CASE(8, 4)
     SPMM_TILED_CASE(8, 8)
-    SPMM_TILED_CASE(12, 2)
     SPMM_TILED_CASE(12, 4)
-    SPMM_TILED_CASE(16, 2)
+    SPMM_TILED_CASE(12, 8)
     SPMM_TILED_CASE(16, 4)
+    SPMM_TILED_CASE(16, 8)
+    SPMM_TILED_CASE(20, 4)
+    SPMM_TILED_CASE(24, 4)
 #undef SPMM_TILED_CASE
-    set_error("tiled kernel: consumer warps x unroll must be one of 4x4 4x8 8x2 8x4 8x8 12x2 12x4 16x2 16x4");
+    set_error("tiled kernel: consumer warps x unroll must be one of 4x4 4x8 8x4 8x8 12x4 12x8 16x4 16x8 20x4 24x4");
     return SPMM_ERR_INVALID;
 }
 
@@ -1138,7 +1196,11 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
         if (fixed.total + 8ull * BR * kt * 8 > (size_t)SMEM_CAP)
             continue;
         p.NS = (int)std::min<size_t>(TB_NSMAX, ((size_t)SMEM_CAP - fixed.total) / ((size_t)BR * kt * 8));
+        if (tn.tiled_ns > 0)
+            p.NS = std::min(p.NS, tn.tiled_ns);
         p.POOL = pool;
+        if ((long long)p.NS * BR + p.POOL > 65535)
+            continue; // slab rows are 16-bit ids
         rc = build_tiles_once(A, p, true, &res);
         if (rc)
             return rc;
@@ -1173,7 +1235,7 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
         }
         return SPMM_OK; // no tile shape fits: the CSR kernels stay in charge
     }
-    const unsigned long long blob_bytes = (unsigned long long)p.n_tiles * p.hdr_bytes + 16ull * (unsigned long long)A->nnz;
+    const unsigned long long blob_bytes = blob_offset(p.n_tiles, A->nnz, p.hdr_bytes, p.T) + 64;
     SPMM_REQUIRE((blob_bytes >> 4) < (1ull << 32), "matrix too large for the tile layout");
     SPMM_CUDA(cudaMalloc(&A->d_tblob, blob_bytes + 16));
     SPMM_CUDA(cudaMalloc(&A->d_tdesc, sizeof(TileDesc) * (size_t)p.n_tiles));

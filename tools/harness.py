@@ -182,13 +182,17 @@ def cfg2(args, emit, dev):
                 kt = f[2] if len(f) > 2 else 0
                 thr = f[3] if len(f) > 3 else 0
                 depth = f[4] if len(f) > 4 else 0
+                ns_cap = f[5] if len(f) > 5 else 0
+                pool = f[6] if len(f) > 6 else 0
 
-                def make(s, T=T, BR=BR, kt=kt, thr=thr, depth=depth):
+                def make(s, T=T, BR=BR, kt=kt, thr=thr, depth=depth, ns_cap=ns_cap, pool=pool):
                     A = spmm.DeviceCSR.from_host(host, dev.index, 0)
                     _cabi.tune("reset", 0)
                     _cabi.tune("tiled.kt", kt)
                     _cabi.tune("tiled.thr", thr)
                     _cabi.tune("tiled.depth", depth)
+                    _cabi.tune("tiled.ns", ns_cap)
+                    _cabi.tune("tiled.pool", pool)
                     try:
                         A.build_tiles(T, BR)
                     finally:
@@ -207,7 +211,7 @@ def cfg2(args, emit, dev):
                 vs = [(base, "tiled", {})]
                 if args.variants:
                     vs += [(f"{base} ncw={ncw} u={u}", "tiled", {"tiled.ncw": ncw, "tiled.unroll": u})
-                           for ncw, u in ((4, 8), (8, 2), (8, 8), (12, 2), (12, 4), (16, 2), (16, 4))]
+                           for ncw, u in ((8, 4), (8, 8), (12, 4), (12, 8), (16, 4), (16, 8), (20, 4), (24, 4))]
                     vs += [(f"{base} ncw=16 u=4 pf={pf}", "tiled", {"tiled.ncw": 16, "tiled.unroll": 4, "tiled.prefetch": pf})
                            for pf in (2, 4, 8, 16)]
                 run_variants("cfg2", sets, k, vs, args.iters, emit, host.nnz, n, {"tiles": info})
