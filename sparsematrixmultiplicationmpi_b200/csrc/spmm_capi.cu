@@ -243,6 +243,7 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "tiled.depth") t.tiled_depth = value;
     else if (k == "tiled.pool") t.tiled_pool = value;
     else if (k == "tiled.ns") t.tiled_ns = value;
+    else if (k == "tiled.npw") t.tiled_npw = value;
     else if (k == "tiled.prefetch") t.tiled_prefetch = value;
     else if (k == "rows.threads") t.rows_threads = value;
     else if (k == "rows.unroll") t.rows_unroll = value;

@@ -66,6 +66,7 @@ struct Tuning
     int tiled_depth = 0;    // build: work items in flight (2..8)
     int tiled_pool = 0;     // build: rows of the singles pool
     int tiled_ns = 0;       // build: cap on the window slots
+    int tiled_npw = 0;      // launch: producer warps (4, 8)
     int tiled_prefetch = -1; // launch: tiles ahead whose blob is prefetched into L2 (-1 auto)
 };
 Tuning &tuning();

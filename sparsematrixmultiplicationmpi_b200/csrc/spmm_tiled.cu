@@ -60,7 +60,6 @@ constexpr int TB_SPLITCAP = 8;                // split units per tile (further l
 constexpr int TB_DMAX = 8;                    // work items in flight
 constexpr int UW = 8;                         // rows per unit = teams per warp
 constexpr int TL = 4;                         // lanes per team
-constexpr int NPW = 4;                        // producer warps
 constexpr int SMEM_CAP = 232448;              // 227 KB opt-in limit per CTA on sm_100
 
 // unit entry: begin (13 bits) | len (10 bits) << 13 | row (8 bits) << 23 | split << 31
@@ -567,7 +566,7 @@ struct TiledArgs
 // smem map: [0,64) full barriers | [64,128) empty barriers | pad to 1024 | blob[depth] | slab (1024-aligned)
 constexpr unsigned BLOB_OFF = 1024;
 
-template <int KT, int NCW, int U>
+template <int KT, int NCW, int U, int NPW>
 __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const TiledArgs a,
                                                                          const __grid_constant__ CUtensorMap box_map,
                                                                          const __grid_constant__ CUtensorMap row_map)
@@ -950,11 +949,11 @@ TiledSmem tiled_smem(int kt, int depth, int T, int BR, int NS, int POOL, int max
     return m;
 }
 
-template <int KT, int NCW, int U>
+template <int KT, int NCW, int U, int NPW>
 int launch_tiled_t(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int kc,
                    cudaStream_t stream)
 {
-    auto kern = spmm_tiled_kernel<KT, NCW, U>;
+    auto kern = spmm_tiled_kernel<KT, NCW, U, NPW>;
     const TiledSmem m = tiled_smem(KT, A->tl_depth, A->tl_T, A->tl_BR, A->tl_NS, A->tl_POOL, A->tl_max_recs);
     if (m.total > (size_t)SMEM_CAP)
     {
@@ -1031,12 +1030,21 @@ int launch_tiled_t(const spmm_csr_s *A, const double *d_B, long long ldb, double
 }
 
 template <int KT>
-int launch_tiled_ncw(const spmm_csr_s *A, int ncw, int u, const double *d_B, long long ldb, double *d_C, long long ldc,
-                     int kc, cudaStream_t s)
+int launch_tiled_ncw(const spmm_csr_s *A, int ncw, int u, int npw, const double *d_B, long long ldb, double *d_C,
+                     long long ldc, int kc, cudaStream_t s)
 {
+    if (npw == 8)
+    {
+        if (ncw == 12 && u == 4)
+            return launch_tiled_t<KT, 12, 4, 8>(A, d_B, ldb, d_C, ldc, kc, s);
+        if (ncw == 16 && u == 4)
+            return launch_tiled_t<KT, 16, 4, 8>(A, d_B, ldb, d_C, ldc, kc, s);
+        set_error("tiled kernel: 8 producer warps go with 12 or 16 consumer warps and unroll 4");
+        return SPMM_ERR_INVALID;
+    }
 #define SPMM_TILED_CASE(N, UU) \
     if (ncw == N && u == UU)   \
-        return launch_tiled_t<KT, N, UU>(A, d_B, ldb, d_C, ldc, kc, s);
+        return launch_tiled_t<KT, N, UU, 4>(A, d_B, ldb, d_C, ldc, kc, s);
     SPMM_TILED_CASE(4, 4)
     SPMM_TILED_CASE(4, 8)
     SPMM_TILED_CASE(8, 4)
@@ -1123,10 +1131,11 @@ int launch_tiled(const spmm_csr_s *A, const double *d_B, long long ldb, double *
     const int kt = t.tiled_kt > 0 ? t.tiled_kt : A->tl_kt;
     const int ncw = t.tiled_ncw > 0 ? t.tiled_ncw : 16;
     const int u = t.tiled_unroll > 0 ? t.tiled_unroll : 4;
+    const int npw = t.tiled_npw == 8 ? 8 : 4;
     if (kt == 16)
-        return launch_tiled_ncw<16>(A, ncw, u, d_B, ldb, d_C, ldc, kc, stream);
+        return launch_tiled_ncw<16>(A, ncw, u, npw, d_B, ldb, d_C, ldc, kc, stream);
     if (kt == 32)
-        return launch_tiled_ncw<32>(A, ncw, u, d_B, ldb, d_C, ldc, kc, stream);
+        return launch_tiled_ncw<32>(A, ncw, u, npw, d_B, ldb, d_C, ldc, kc, stream);
     set_error("tiled kernel: k-tile must be 16 or 32");
     return SPMM_ERR_INVALID;
 }

@@ -212,8 +212,8 @@ def cfg2(args, emit, dev):
                 if args.variants:
                     vs += [(f"{base} ncw={ncw} u={u}", "tiled", {"tiled.ncw": ncw, "tiled.unroll": u})
                            for ncw, u in ((8, 4), (8, 8), (12, 4), (12, 8), (16, 4), (16, 8), (20, 4), (24, 4))]
-                    vs += [(f"{base} ncw=16 u=4 pf={pf}", "tiled", {"tiled.ncw": 16, "tiled.unroll": 4, "tiled.prefetch": pf})
-                           for pf in (2, 4, 8, 16)]
+                    vs += [(f"{base} ncw={ncw} u=4 npw=8", "tiled", {"tiled.ncw": ncw, "tiled.unroll": 4, "tiled.npw": 8})
+                           for ncw in (12, 16)]
                 run_variants("cfg2", sets, k, vs, args.iters, emit, host.nnz, n, {"tiles": info})
                 for A, _, _ in sets:
                     A.close()
