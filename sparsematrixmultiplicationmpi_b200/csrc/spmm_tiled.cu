@@ -53,7 +53,7 @@ constexpr int TB_THREADS = 512;
 constexpr int TB_ITEMS = 12;
 constexpr int TB_CAP = TB_THREADS * TB_ITEMS; // records per tile the builder can sort
 constexpr int TB_UMAX = 1024;                 // distinct boxes per tile the builder tracks
-constexpr int TB_NSMAX = 128;                 // window slots
+constexpr int TB_NSMAX = 192;                 // window slots
 constexpr int TB_MAXT = 248;                  // rows per tile (row field of a unit entry: 0xFF = padding)
 constexpr int TB_SPLIT = 48;                  // rows this long become a unit of their own
 constexpr int TB_SPLITCAP = 8;                // split units per tile (further long rows stay whole)
@@ -692,6 +692,11 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
             }
             if (!T_NO_STAGE && pw + NPW * lane < n_loads)
                 tma_box(s_slab + (unsigned)m.ld.y * box_bytes, &box_map, k0, m.ld.x, bar);
+            for (int i = pw + NPW * (lane + 32); !T_NO_STAGE && i < n_loads; i += NPW * 32) // more than NPW*32 boxes: rare
+            {
+                const int2 e = a.loads[(size_t)cur.t * a.NS + i];
+                tma_box(s_slab + (unsigned)e.y * box_bytes, &box_map, k0, e.x, bar);
+            }
             const long long c1a = TCLK();
             // single rows, four per gather (the builder pads the list and keeps a group inside the pool ring)
             const unsigned pool = s_slab + (unsigned)(a.NS * a.BR) * (KT * 8);
