@@ -1175,7 +1175,7 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
     BuildParams p = {};
     p.n_rows = A->n_rows;
     p.lgBR = lg2(BR);
-    p.thr = tn.tiled_thr > 0 ? tn.tiled_thr : std::max(2, BR / 2);
+    p.thr = tn.tiled_thr > 0 ? tn.tiled_thr : std::max(2, BR / 4);
     p.depth = depth;
     BuildResult res;
     const int auto_cand[] = {64, 48, 32, 16};
