@@ -277,7 +277,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": recorded_traffic(k), "peak_kind": peak_kind, "algorithmic_bytes_per_launch": abytes,
                 "frac_of_8TBs_nominal": achieved / 8000.0,
-                "kernel": "spmm_tiled_kernel" if tiles["rows_per_tile"] and k >= 16 and args.kernel in ("auto", "tiled")
+                "kernel": "spmm_tiled_kernel" if tiles["rows_per_tile"] and k >= 8 and k % 2 == 0 and args.kernel in ("auto", "tiled")
                 else "spmm_rowblock_kernel" if rb["rows_per_block"] and args.kernel in ("auto", "rowblock")
                 else ("spmm_merge_kernel" if args.kernel == "merge" else "spmm_rows_kernel"),
                 "tiles": tiles, "rowblock": rb}

@@ -423,10 +423,10 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
     SPMM_REQUIRE(kernel != SPMM_KERNEL_ROWBLOCK || A->rb_R != 0, "row-block kernel requested but spmm_csr_build_rowblocks was not called");
     if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)
         return launch_merge(A, 0, A->n_rows, 0, A->nnz, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
-    // AUTO builds the tile layout the first time a multiply can use it (k >= 16, even, mid-sized matrix with
+    // AUTO builds the tile layout the first time a multiply can use it (k >= 8, even, mid-sized matrix with
     // regular rows): one-off, a few milliseconds, 16 bytes per non-zero next to the CSR. spmm_tune_set("tiled", 0)
     // or an explicit spmm_csr_build_tiles(A, 0, 0) keeps the CSR kernels.
-    if (kernel == SPMM_KERNEL_AUTO && !A->tl_tried && A->tl_T == 0 && tuning().tiled != 0 && k_count >= 16 &&
+    if (kernel == SPMM_KERNEL_AUTO && !A->tl_tried && A->tl_T == 0 && tuning().tiled != 0 && k_count >= 8 &&
         k_count % 2 == 0 && A->nnz >= 200000 && A->nnz <= (64ll << 20))
     {
         A->tl_tried = true;

@@ -86,11 +86,11 @@ int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_l
     {
         if (derived == 6 || (derived == 1 && A->tl_T && t.tiled != 0))
         {
-            // tile layout: worth it once a B row piece is >= 128 bytes and rows of a tile share B rows
+            // tile layout: measured faster than the CSR kernels from k = 8 up when rows of a tile share B rows (profiles/r1_tiled.md)
             const bool fits = tiled_shape_ok(A, d_B, ldb, d_C, ldc, kc);
             const double staged = (double)A->tl_box_rows_loaded + (double)A->tl_single_rows;
             const double reuse = staged > 0 ? (double)A->nnz / staged : 0.0;
-            if (fits && (derived == 6 || t.tiled == 1 || (kc >= 16 && reuse >= 2.0 && A->tl_drains * 20 <= A->tl_tiles)))
+            if (fits && (derived == 6 || t.tiled == 1 || (kc >= 8 && reuse >= 2.0 && A->tl_drains * 20 <= A->tl_tiles)))
                 return launch_tiled(A, d_B, ldb, d_C, ldc, kc, stream);
             if (derived == 6)
             {
