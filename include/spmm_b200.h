@@ -121,6 +121,15 @@ int spmm_csr_column_block(spmm_csr_t A, int col_begin, int col_end, spmm_csr_t *
 /* C[n_rows x k] = A * B[n_cols x k], everything resident on the device. */
 int spmm_multiply_device(spmm_csr_t A, const double *d_B, int k, double *d_C, int kernel, void *stream);
 
+/* Row-wise strategy with the gather fused into the multiply (RowWise.cpp:36-50 + the MPI_Gatherv of :85-87,
+ * or an all-gather): the C rows of this shard (n_rows x k, contiguous) are stored from registers to every one of
+ * the n_dst (1..8) destinations — d_C_list[0] usually the local copy, the others peer GPUs' buffers mapped into
+ * this process over NVLink (CUDA IPC / symmetric memory), each already offset to the shard's first row.
+ * kernel: AUTO, ROWS, MERGE or TILED. No NCCL call, no staging copy; the caller synchronises the ranks
+ * afterwards (a barrier) before anybody reads its buffer. */
+int spmm_multiply_scatter_device(spmm_csr_t A, const double *d_B, int k, int n_dst, double *const *d_C_list,
+                                 int kernel, void *stream);
+
 /* Strided form: B has leading dimension ldb, C has ldc; columns [k_begin, k_begin+k_count)
  * of B/C are computed (the k-slab split of ColumnWise.cpp:25-48). */
 int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, double *d_C, int ldc,

@@ -12,6 +12,7 @@
 #include <string>
 
 #include "spmm_internal.h"
+#include "spmm_kernels.cuh"
 
 namespace spmm
 {
@@ -435,6 +436,45 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
     }
     return launch_rows(A, 0, A->n_rows, 0, A->nnz, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count,
                        kernel == SPMM_KERNEL_ROWS ? 0 : (kernel == SPMM_KERNEL_AUTO ? 1 : kernel), s);
+}
+
+int spmm_multiply_scatter_device(spmm_csr_t A, const double *d_B, int k, int n_dst, double *const *d_C_list, int kernel,
+                                 void *stream)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(k >= 0, "k is negative");
+    SPMM_REQUIRE(n_dst >= 1 && n_dst <= 1 + SPMM_MAX_EXTRA, "n_dst must be between 1 and 8");
+    SPMM_REQUIRE(d_C_list != nullptr, "d_C_list is NULL");
+    SPMM_REQUIRE(kernel == SPMM_KERNEL_AUTO || kernel == SPMM_KERNEL_ROWS || kernel == SPMM_KERNEL_MERGE ||
+                     kernel == SPMM_KERNEL_TILED,
+                 "scatter multiply: kernel must be auto, rows, merge or tiled");
+    if (A->n_rows == 0 || k == 0)
+        return SPMM_OK;
+    ExtraDst x;
+    for (int i = 0; i < n_dst; ++i)
+    {
+        SPMM_REQUIRE(d_C_list[i] != nullptr, "a destination pointer is NULL");
+        SPMM_REQUIRE(((uintptr_t)d_C_list[i] - (uintptr_t)d_C_list[0]) % 16 == 0,
+                     "destinations must be congruent modulo 16 bytes (same vector width for every copy)");
+        if (i)
+            x.off[x.n++] = (long long)(((intptr_t)d_C_list[i] - (intptr_t)d_C_list[0]) / (intptr_t)sizeof(double));
+    }
+    SPMM_REQUIRE(d_B != nullptr || A->nnz == 0, "d_B is NULL");
+    SPMM_REQUIRE(kernel != SPMM_KERNEL_TILED || A->tl_T != 0, "tiled kernel requested but spmm_csr_build_tiles was not called");
+    SPMM_CUDA(cudaSetDevice(A->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    double *d_C = d_C_list[0];
+    if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)
+        return launch_merge(A, 0, A->n_rows, 0, A->nnz, 0, d_B, k, d_C, k, k, s, &x);
+    if (kernel == SPMM_KERNEL_AUTO && !A->tl_tried && A->tl_T == 0 && tuning().tiled != 0 && k >= 8 && k % 2 == 0 &&
+        A->nnz >= 200000 && A->nnz <= (64ll << 20))
+    {
+        A->tl_tried = true;
+        if (spmm_csr_build_tiles(A, -1, 0) != SPMM_OK)
+            free_tiles(A);
+    }
+    return launch_rows(A, 0, A->n_rows, 0, A->nnz, 0, d_B, k, d_C, k, k,
+                       kernel == SPMM_KERNEL_ROWS ? 0 : (kernel == SPMM_KERNEL_AUTO ? 1 : kernel), s, &x);
 }
 
 int spmm_multiply_device(spmm_csr_t A, const double *d_B, int k, double *d_C, int kernel, void *stream)

@@ -74,7 +74,7 @@ Shape pick_shape(const double *d_B, long long ldb, const double *d_C, long long 
 
 int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
                 const double *d_B, long long ldb, double *d_C, long long ldc, int kc, int derived,
-                cudaStream_t stream)
+                cudaStream_t stream, const ExtraDst *extra)
 {
     if (row_end <= row_begin || kc <= 0)
         return SPMM_OK;
@@ -91,13 +91,15 @@ int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_l
             const double staged = (double)A->tl_box_rows_loaded + (double)A->tl_single_rows;
             const double reuse = staged > 0 ? (double)A->nnz / staged : 0.0;
             if (fits && (derived == 6 || t.tiled == 1 || (kc >= 8 && reuse >= 2.0 && A->tl_drains * 20 <= A->tl_tiles)))
-                return launch_tiled(A, d_B, ldb, d_C, ldc, kc, stream);
+                return launch_tiled(A, d_B, ldb, d_C, ldc, kc, stream, extra);
             if (derived == 6)
             {
                 set_error("tiled kernel: needs even k, even leading dimensions and 16-byte aligned B and C");
                 return SPMM_ERR_UNSUPPORTED;
             }
         }
+        if (extra && extra->n)
+            derived = 0; // the other derived layouts store to one destination only
         Shape ps = s;
         if (A->pk_R && A->pk_kl != s.kl && (kc % (2 * A->pk_kl) == 0) && s.w == 2)
         {
@@ -150,6 +152,8 @@ int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_l
         np = std::max(1, std::min(t.rows_np, 32 / s.kl)); // sweep shapes allow NP > 1 with NV > 1
 
     SpmmArgs args = {};
+    if (extra)
+        args.extra = *extra;
     args.rowptr = A->d_rowptr;
     args.colidx = A->d_colidx;
     args.vals = A->d_vals;
@@ -181,7 +185,8 @@ int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_l
 }
 
 int launch_merge(spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
-                 const double *d_B, long long ldb, double *d_C, long long ldc, int kc, cudaStream_t stream)
+                 const double *d_B, long long ldb, double *d_C, long long ldc, int kc, cudaStream_t stream,
+                 const ExtraDst *extra)
 {
     if (row_end <= row_begin || kc <= 0)
         return SPMM_OK;
@@ -216,6 +221,8 @@ int launch_merge(spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, lo
     }
 
     SpmmArgs args = {};
+    if (extra)
+        args.extra = *extra;
     args.rowptr = A->d_rowptr;
     args.colidx = A->d_colidx;
     args.vals = A->d_vals;

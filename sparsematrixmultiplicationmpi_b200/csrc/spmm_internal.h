@@ -127,9 +127,10 @@ namespace spmm
 // rows [row_begin,row_end), each clipped to the non-zero range [nnz_lo,nnz_hi); row c_row0 is stored at d_C[0]
 int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
                 const double *d_B, long long ldb, double *d_C, long long ldc, int kc, int derived,
-                cudaStream_t stream); // derived: 0 CSR row kernel only, 1 best available, 3 row-block, 4 packed, 5 staged, 6 tiled
+                cudaStream_t stream, const struct ExtraDst *extra = nullptr); // derived: 0 CSR row kernel only, 1 best available, 3 row-block, 4 packed, 5 staged, 6 tiled
 int launch_merge(spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
-                 const double *d_B, long long ldb, double *d_C, long long ldc, int kc, cudaStream_t stream);
+                 const double *d_B, long long ldb, double *d_C, long long ldc, int kc, cudaStream_t stream,
+                 const struct ExtraDst *extra = nullptr);
 bool rowblock_shape_ok(int w, int kl, int nv, int tiles, int kc);
 int launch_rowblock(const spmm_csr_s *A, int w, int kl, int nv, int tiles, const double *d_B, long long ldb,
                     double *d_C, long long ldc, cudaStream_t stream);
@@ -140,7 +141,7 @@ int launch_packed(const spmm_csr_s *A, int nv, int tiles, const double *d_B, lon
 void free_packed(spmm_csr_s *A);
 bool tiled_shape_ok(const spmm_csr_s *A, const double *d_B, long long ldb, const double *d_C, long long ldc, int kc);
 int launch_tiled(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int kc,
-                 cudaStream_t stream);
+                 cudaStream_t stream, const struct ExtraDst *extra = nullptr);
 void free_tiles(spmm_csr_s *A);
 bool staged_shape_ok(const spmm_csr_s *A, int w, int kl, int nv, int tiles, int kc);
 int launch_staged(const spmm_csr_s *A, int nv, int tiles, const double *d_B, long long ldb, double *d_C, long long ldc,

@@ -288,8 +288,19 @@ static __global__ void chunk_bounds_kernel(const int *rowptr, int n_rows, int nn
     bounds[b] = r;
 }
 
+// Extra destinations of the C rows a launch produces (peer GPUs' buffers mapped over NVLink): element offsets
+// relative to the primary C pointer, same leading dimension. The kernel stores every finished row piece to all
+// of them from registers — the row-wise strategy's gather / all-gather fused into the multiply.
+constexpr int SPMM_MAX_EXTRA = 7;
+struct ExtraDst
+{
+    int n = 0;
+    long long off[SPMM_MAX_EXTRA] = {0, 0, 0, 0, 0, 0, 0};
+};
+
 struct SpmmArgs
 {
+    ExtraDst extra;
     const int *rowptr;
     const int *colidx;
     const double *vals;
@@ -481,7 +492,12 @@ __global__ void __launch_bounds__(THREADS, SWEEP ? 1 : min_blocks(NV, W, U, 1, T
 #else
         if (valid && g == 0)
 #endif
-            acc.store(a.C + (long long)(row - a.c_row0) * a.ldc + tile0 + kl * W, mask);
+        {
+            double *const cp = a.C + (long long)(row - a.c_row0) * a.ldc + tile0 + kl * W;
+            acc.store(cp, mask);
+            for (int d = 0; d < a.extra.n; ++d)
+                acc.store(cp + a.extra.off[d], mask);
+        }
         row = nrow;
         js = njs;
         je = nje;
@@ -604,7 +620,12 @@ __global__ void __launch_bounds__(THREADS, min_blocks(NV, W, U, 1, THREADS)) spm
         {
             // the row-end item: this team closes `row`
             if (fresh)
-                acc.store(a.C + (long long)(row - a.c_row0) * a.ldc + tile0 + kl * W, mask);
+            {
+                double *const cp = a.C + (long long)(row - a.c_row0) * a.ldc + tile0 + kl * W;
+                acc.store(cp, mask);
+                for (int d = 0; d < a.extra.n; ++d)
+                    acc.store(cp + a.extra.off[d], mask);
+            }
             else
             {
                 acc.store_plain(carry_head);
@@ -673,7 +694,10 @@ __global__ void __launch_bounds__(THREADS) spmm_merge_fixup_kernel(const SpmmArg
         else
             break;
     }
-    acc.store(a.C + (long long)(row - a.c_row0) * a.ldc + tile0 + kl * W, mask);
+    double *const dst = a.C + (long long)(row - a.c_row0) * a.ldc + tile0 + kl * W;
+    acc.store(dst, mask);
+    for (int d = 0; d < a.extra.n; ++d)
+        acc.store(dst + a.extra.off[d], mask);
 }
 
 } // namespace spmm

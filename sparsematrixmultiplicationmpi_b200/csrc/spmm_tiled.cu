@@ -550,6 +550,7 @@ __device__ __forceinline__ double lds64d(unsigned addr)
 struct TiledArgs
 {
     long long *prof; // TPROF builds: 12 counters per CTA
+    ExtraDst extra;  // peer copies of C (element offsets from C)
     const unsigned char *blob;
     const TileDesc *tdesc;
     const int2 *loads;
@@ -853,7 +854,11 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
 #pragma unroll
                     for (int x = 0; x < NL; ++x)
                         if (k0 + (x * TL + l) * 2 < a.kc)
+                        {
                             st_c2(cr + (x * TL + l) * 2, al[x].x, al[x].y);
+                            for (int d = 0; d < a.extra.n; ++d)
+                                st_c2(cr + a.extra.off[d] + (x * TL + l) * 2, al[x].x, al[x].y);
+                        }
                 }
             }
             else if (row != (int)UE_PAD_ROW)
@@ -862,7 +867,11 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
 #pragma unroll
                 for (int x = 0; x < NL; ++x)
                     if (k0 + colo[x] < a.kc)
+                    {
                         st_c2(cr + colo[x], acc[x].x, acc[x].y);
+                        for (int d = 0; d < a.extra.n; ++d)
+                            st_c2(cr + a.extra.off[d] + colo[x], acc[x].x, acc[x].y);
+                    }
             }
         }
         __syncwarp();
@@ -956,7 +965,7 @@ TiledSmem tiled_smem(int kt, int depth, int T, int BR, int NS, int POOL, int max
 
 template <int KT, int NCW, int U, int NPW>
 int launch_tiled_t(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int kc,
-                   cudaStream_t stream)
+                   cudaStream_t stream, const ExtraDst &extra)
 {
     auto kern = spmm_tiled_kernel<KT, NCW, U, NPW>;
     const TiledSmem m = tiled_smem(KT, A->tl_depth, A->tl_T, A->tl_BR, A->tl_NS, A->tl_POOL, A->tl_max_recs);
@@ -989,6 +998,7 @@ int launch_tiled_t(const spmm_csr_s *A, const double *d_B, long long ldb, double
     a.singles = A->d_tsingles;
     a.B = d_B;
     a.C = d_C;
+    a.extra = extra;
     a.ldb = ldb;
     a.ldc = ldc;
     a.n_tiles = A->tl_tiles;
@@ -1036,20 +1046,20 @@ int launch_tiled_t(const spmm_csr_s *A, const double *d_B, long long ldb, double
 
 template <int KT>
 int launch_tiled_ncw(const spmm_csr_s *A, int ncw, int u, int npw, const double *d_B, long long ldb, double *d_C,
-                     long long ldc, int kc, cudaStream_t s)
+                     long long ldc, int kc, cudaStream_t s, const ExtraDst &x)
 {
     if (npw == 8)
     {
         if (ncw == 12 && u == 4)
-            return launch_tiled_t<KT, 12, 4, 8>(A, d_B, ldb, d_C, ldc, kc, s);
+            return launch_tiled_t<KT, 12, 4, 8>(A, d_B, ldb, d_C, ldc, kc, s, x);
         if (ncw == 16 && u == 4)
-            return launch_tiled_t<KT, 16, 4, 8>(A, d_B, ldb, d_C, ldc, kc, s);
+            return launch_tiled_t<KT, 16, 4, 8>(A, d_B, ldb, d_C, ldc, kc, s, x);
         set_error("tiled kernel: 8 producer warps go with 12 or 16 consumer warps and unroll 4");
         return SPMM_ERR_INVALID;
     }
 #define SPMM_TILED_CASE(N, UU) \
     if (ncw == N && u == UU)   \
-        return launch_tiled_t<KT, N, UU, 4>(A, d_B, ldb, d_C, ldc, kc, s);
+        return launch_tiled_t<KT, N, UU, 4>(A, d_B, ldb, d_C, ldc, kc, s, x);
     SPMM_TILED_CASE(4, 4)
     SPMM_TILED_CASE(4, 8)
     SPMM_TILED_CASE(8, 4)
@@ -1130,17 +1140,18 @@ bool tiled_shape_ok(const spmm_csr_s *A, const double *d_B, long long ldb, const
 }
 
 int launch_tiled(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int kc,
-                 cudaStream_t stream)
+                 cudaStream_t stream, const ExtraDst *extra)
 {
+    const ExtraDst x = extra ? *extra : ExtraDst();
     const Tuning &t = tuning();
     const int kt = t.tiled_kt > 0 ? t.tiled_kt : A->tl_kt;
     const int ncw = t.tiled_ncw > 0 ? t.tiled_ncw : 16;
     const int u = t.tiled_unroll > 0 ? t.tiled_unroll : 4;
     const int npw = t.tiled_npw == 8 ? 8 : 4;
     if (kt == 16)
-        return launch_tiled_ncw<16>(A, ncw, u, npw, d_B, ldb, d_C, ldc, kc, stream);
+        return launch_tiled_ncw<16>(A, ncw, u, npw, d_B, ldb, d_C, ldc, kc, stream, x);
     if (kt == 32)
-        return launch_tiled_ncw<32>(A, ncw, u, npw, d_B, ldb, d_C, ldc, kc, stream);
+        return launch_tiled_ncw<32>(A, ncw, u, npw, d_B, ldb, d_C, ldc, kc, stream, x);
     set_error("tiled kernel: k-tile must be 16 or 32");
     return SPMM_ERR_INVALID;
 }

@@ -151,6 +151,13 @@ class DeviceCSR:
         _cabi.check(_cabi.lib().spmm_csr_packed_info(self.handle, C.byref(r), C.byref(l), C.byref(n), C.byref(f)))
         return {"rows_per_unit": r.value, "lanes_per_row": l.value, "slots": n.value, "fill_ratio": f.value}
 
+    def multiply_scatter(self, d_B: int, k: int, d_C_list, kernel: str = "auto", stream: int = 0) -> None:
+        """C = A*B stored to every pointer of d_C_list (local and NVLink-mapped peer buffers): the row-wise
+        strategy's gather fused into the multiply (spmm_multiply_scatter_device)."""
+        arr = (C.c_void_p * len(d_C_list))(*[C.c_void_p(int(p)) for p in d_C_list])
+        _cabi.check(_cabi.lib().spmm_multiply_scatter_device(self.handle, C.c_void_p(d_B), k, len(d_C_list), arr,
+                                                             _cabi.KERNELS[kernel], C.c_void_p(stream)))
+
     def build_tiles(self, rows_per_tile: int = -1, box_rows: int = 0) -> dict:
         """Row tiles with TMA-staged B rows (spmm_tiled.cu); -1 = largest tile that fits shared memory."""
         _cabi.check(_cabi.lib().spmm_csr_build_tiles(self.handle, rows_per_tile, box_rows))

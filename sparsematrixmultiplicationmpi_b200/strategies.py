@@ -165,6 +165,46 @@ class RowWise:
         """The reference call: local rows, then Gatherv to rank 0; None on the other ranks."""
         return self.gather(self.multiply_local(B))
 
+    # ---- gather fused into the multiply: C rows stored straight into the peers' buffers over NVLink ----
+    def _symmetric_C(self, device: torch.device):
+        """One (n_rows x k) result buffer per rank, mapped into every rank (torch symmetric memory = CUDA IPC /
+        fabric handles over NVLink); cached on the plan."""
+        if getattr(self, "_symm", None) is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            group = self.group if self.group is not None else dist.group.WORLD
+            buf = symm_mem.empty((self.n_rows, self.k), dtype=torch.float64, device=device)
+            hdl = symm_mem.rendezvous(buf, group)
+            self._symm = (buf, hdl)
+        return self._symm
+
+    def _scatter(self, B: torch.Tensor, peers: list[int]) -> torch.Tensor:
+        buf, hdl = self._symmetric_C(B.device)
+        off = self.start * self.k * 8  # this rank's rows start here in every copy of C
+        ptrs = [int(hdl.buffer_ptrs[p]) + off for p in peers]
+        if self.end > self.start and self.k:
+            self.A.multiply_scatter(B.data_ptr(), self.k, ptrs, self.compute.kernel,
+                                    torch.cuda.current_stream(B.device).cuda_stream)
+        hdl.barrier(channel=0)  # every rank's stores have landed before anybody reads its copy
+        return buf
+
+    def multiply_all_gather_p2p(self, B: torch.Tensor) -> torch.Tensor:
+        """Full C on every rank without a collective: the multiply kernel stores each finished row piece from
+        registers to all P copies of C (its own first, then the peers in ring order so that the NVLink ports
+        are used evenly). The returned tensor is the plan's symmetric buffer: it is overwritten by the next call."""
+        if self.P == 1:
+            return self.multiply_local(B)
+        if self.P > 8:
+            return self.all_gather(self.multiply_local(B))
+        return self._scatter(B, [(self.rank + i) % self.P for i in range(self.P)])
+
+    def run_p2p(self, B: torch.Tensor) -> torch.Tensor | None:
+        """The reference call (result on rank 0 only, RowWise.cpp:85-87) with the Gatherv fused into the multiply:
+        every rank stores its rows directly into rank 0's buffer."""
+        if self.P == 1:
+            return self.multiply_local(B)
+        buf = self._scatter(B, [0])
+        return buf if self.rank == 0 else None
+
     def multiply_all_gather_overlapped(self, B: torch.Tensor, chunks: int = 4) -> torch.Tensor:
         """Full C on every rank with the gather of row chunk c running over NVLink while chunk c+1 is
         being multiplied: the local rows are cut into `chunks` pieces, each computed straight into its

@@ -562,3 +562,39 @@ def test_tiled_mixed_sign_duplicates_and_strided(oracle, golden_multiply):
     ref = oracle.spmm(rp, ci, va, B, 64)
     assert_close_rel(out[:, 16:48], ref[:, 16:48], tol=REL_TOL)
     assert not out[:, :16].any() and not out[:, 48:].any()
+
+
+# ---------------------------------------------------------------- multiply with the gather fused in (spmm_multiply_scatter_device)
+@pytest.mark.parametrize("kernel,k", [("rows", 5), ("rows", 64), ("merge", 32), ("tiled", 64), ("tiled", 24), ("auto", 16)])
+def test_scatter_multiply_same_device(oracle, kernel, k):
+    """Every destination receives the same C (on one GPU the 'peers' are three buffers of the same device)."""
+    rp, ci, va = banded_csr(53, 3001, 19, 12, (-150, 0, 150), long_row=400, empty_every=9)
+    m = spmm.SparseMatrix(va, ci, rp, 3001, 3001)
+    B = np.random.default_rng(k).integers(1, 101, (3001, k)).astype(np.float64)
+    ref = oracle.spmm(rp, ci, va, B, k)
+    with spmm.DeviceCSR.from_host(m, 0) as A:
+        if kernel == "tiled":
+            assert A.build_tiles(-1)["rows_per_tile"] > 0
+        dB = dev(B)
+        outs = [torch.full((3001, k), np.nan, dtype=torch.float64, device="cuda") for _ in range(3)]
+        A.multiply_scatter(dB.data_ptr(), k, [o.data_ptr() for o in outs], kernel, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        for o in outs:
+            assert_close_rel(o.cpu().numpy(), ref, tol=REL_TOL)
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+        with pytest.raises(_cabi.SpmmError):
+            A.multiply_scatter(dB.data_ptr(), k, [o.data_ptr() for o in outs] * 3, kernel)  # 9 destinations
+
+
+def test_rowwise_p2p_two_gpus():
+    """RowWise with the gather / all-gather fused into the multiply over NVLink peer stores (needs 2 GPUs)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multi_gpu_p2p.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", script],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "p2p ok" in r.stdout
