@@ -325,6 +325,39 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             out[name + "_ms"] = float(t.item())
         out["bytes"] = N_ROWS * world * k * 8
+
+        # the same all-gather fused into the multiply (C rows stored from registers into every peer's buffer
+        # over NVLink, spmm_multiply_scatter_device) against multiply + NCCL all-gather, both timed as one unit
+        def timed_unit(fn, iters=10):
+            for _ in range(3):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                fn()
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b) / iters], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        A0, B0, C0 = sets[0]
+        out["multiply+all_gather_nccl_ms"] = timed_unit(
+            lambda: (A0.multiply(B0.data_ptr(), k, C0.data_ptr(), args.kernel, stream),
+                     dist.all_gather_into_tensor(Call, C0)))
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            sym = symm_mem.empty((N_ROWS * world, k), dtype=torch.float64, device=dev)
+            hdl = symm_mem.rendezvous(sym, dist.group.WORLD)
+            ptrs = [int(hdl.buffer_ptrs[(rank + i) % world]) + rank * N_ROWS * k * 8 for i in range(world)]
+            out["multiply+all_gather_fused_p2p_ms"] = timed_unit(
+                lambda: (A0.multiply_scatter(B0.data_ptr(), k, ptrs, args.kernel if args.kernel in ("auto", "rows", "merge", "tiled") else "auto", stream),
+                         hdl.barrier(channel=0)))
+            torch.cuda.synchronize()
+            out["fused_p2p_matches_nccl"] = bool(torch.equal(sym, Call))
+        except Exception as e:  # symmetric memory unavailable on this box: report, do not fail the bench line
+            out["multiply+all_gather_fused_p2p_error"] = str(e)[:200]
         collectives = out
         del plan_counts
 

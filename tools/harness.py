@@ -349,11 +349,17 @@ def multi_gpu(args, emit, dev, rank, world):
         t_all = timed(lambda: plan.all_gather(plan.multiply_local(plan.broadcast_B(B), C)), 5)
         t_kg = timed(lambda: plan.all_gather(plan.multiply_local(B, C)), 5)
         t_ov = {c: timed(lambda c=c: plan.multiply_all_gather_overlapped(B, chunks=c), 5) for c in (2, 4, 8)}
+        # gather fused into the multiply: C rows stored from registers into every peer's buffer over NVLink
+        t_p2p = timed(lambda: plan.multiply_all_gather_p2p(B), 5)
+        t_root = timed(lambda: plan.run_p2p(B), 5)
+        t_nccl_root = timed(lambda: plan.gather(plan.multiply_local(B, C)), 5)
         nnz = n * npr
         if rank == 0:
             emit({"config": "cfg4", "strategy": "row-wise", "n_gpus": world, "k": k, "kernel_ms": t_k,
                   "broadcast_B_ms": t_b, "all_gather_C_ms": t_g, "bcast+kernel+gather_ms": t_all,
                   "kernel+gather_ms": t_kg, "kernel+gather_overlapped_ms": t_ov,
+                  "fused_p2p_all_gather_ms": t_p2p, "fused_p2p_gather_to_root_ms": t_root,
+                  "kernel+nccl_gather_to_root_ms": t_nccl_root,
                   "kernel_gflops": 2.0 * nnz * k / (t_k * 1e-3) / 1e9,
                   "kernel_algo_GBs_per_gpu": abytes(e - s, nnz // world, k, b_rows=(e - s) + 2 * hb) / (t_k * 1e-3) / 1e9,
                   "frac_measured_peak_per_gpu": abytes(e - s, nnz // world, k, b_rows=(e - s) + 2 * hb) / (t_k * 1e-3) / 1e9 / pk,
