@@ -135,8 +135,9 @@ int spmm_multiply_scatter_device(spmm_csr_t A, const double *d_B, int k, int n_d
 int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, double *d_C, int ldc,
                                  int k_begin, int k_count, int kernel, void *stream);
 
-/* Host-buffer form, the call the C++ entry points make: copies B up through pinned
- * staging, multiplies, copies C back. B: n_cols*k doubles, C: n_rows*k doubles. */
+/* Host-buffer form, the call the C++ entry points make: copies B up, multiplies, copies C back.
+ * B: n_cols*k doubles, C: n_rows*k doubles. Operands of 16 MB and more with k >= 32 go in two
+ * k-slabs so that the upload of the second overlaps the download of the first (PCIe is full duplex). */
 int spmm_multiply_host(spmm_csr_t A, const double *B, int k, double *C, int kernel);
 
 /* ---- a4: row block [row_begin,row_end) (RowWise.cpp:26-50). d_C_local holds
@@ -192,7 +193,7 @@ int spmm_gen_fat_vector_device(int device, double *d_out, long long n_elems, lon
                                unsigned long long seed, void *stream);
 
 /* Measurement knob (not needed for correct results): override the automatic team shape.
- * keys: rows.kl rows.nv rows.np rows.unroll rows.vec rows.ctas_per_sm merge.items rowblock tiled tiled.kt tiled.ncw tiled.unroll tiled.thr tiled.chunk tiled.depth tiled.pool tiled.ns tiled.npw tiled.prefetch reset */
+ * keys: rows.kl rows.nv rows.np rows.unroll rows.vec rows.ctas_per_sm merge.items rowblock tiled tiled.kt tiled.ncw tiled.unroll tiled.thr tiled.chunk tiled.depth tiled.pool tiled.ns tiled.npw tiled.prefetch host.slabs reset */
 int spmm_tune_set(const char *key, int value);
 
 #ifdef __cplusplus

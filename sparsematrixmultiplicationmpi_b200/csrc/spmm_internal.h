@@ -67,6 +67,7 @@ struct Tuning
     int tiled_pool = 0;     // build: rows of the singles pool
     int tiled_ns = 0;       // build: cap on the window slots
     int tiled_npw = 0;      // launch: producer warps (4, 8)
+    int host_slabs = 0;     // host-buffer multiply: k-slabs in the PCIe pipeline (0 auto, 1 none)
     int tiled_prefetch = -1; // launch: tiles ahead whose blob is prefetched into L2 (-1 auto)
 };
 Tuning &tuning();
@@ -96,6 +97,8 @@ struct spmm_csr_s
     double *d_B = nullptr, *d_C = nullptr;
     size_t d_B_elems = 0, d_C_elems = 0;
     cudaStream_t stream = nullptr; // owned, for host-buffer calls
+    cudaStream_t stream_up = nullptr, stream_down = nullptr; // k-slab pipeline of the host-buffer multiply
+    cudaEvent_t ev_up[8] = {}, ev_done[8] = {};
     // row-block union format (spmm_rowblock.cu), optional
     int rb_R = 0, rb_blocks = 0;
     long long rb_entries = 0;

@@ -598,3 +598,23 @@ def test_rowwise_p2p_two_gpus():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "p2p ok" in r.stdout
+
+
+@pytest.mark.parametrize("slabs", [0, 1, 2, 4])
+def test_host_multiply_k_slab_pipeline(oracle, slabs):
+    """spmm_multiply_host with the k-slab PCIe pipeline (host.slabs): same C as the single-shot path and the oracle."""
+    n, k = 40_000, 64  # 2 x 20 MB: above the size from which AUTO pipelines
+    rp, ci, va = banded_csr(59, n, 9, 30, (-500, 0, 500))
+    m = spmm.SparseMatrix(va, ci, rp, n, n)
+    B = np.random.default_rng(8).integers(1, 101, (n, k)).astype(np.float64)
+    ref = oracle.spmm(rp, ci, va, B, k)
+    _cabi.tune("reset", 0)
+    _cabi.tune("host.slabs", slabs)
+    try:
+        with spmm.DeviceCSR.from_host(m, 0) as A:
+            got = A.multiply_host(B, k, "auto")
+            assert_close_rel(got, ref, tol=REL_TOL)
+            again = A.multiply_host(B, k, "rows")
+            assert_close_rel(again, ref, tol=REL_TOL)
+    finally:
+        _cabi.tune("reset", 0)
