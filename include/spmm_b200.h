@@ -161,6 +161,13 @@ int spmm_multiply_nnz_range_device(spmm_csr_t A, long long nnz_begin, long long 
 int spmm_multiply_nnz_range_host(spmm_csr_t A, long long nnz_begin, long long nnz_end, int first_row, int last_row,
                                  const double *B, int k, double *C_local, int kernel);
 
+/* ---- a5, column-block strategy (north_star reading of ColumnWise.cpp): the reduce of the partial C
+ * blocks without NCCL. d_out[0..n_elems) = sum over i of d_src_list[i][0..n_elems), added in list order (pass the
+ * ranks' partial blocks in ascending rank order: the sum is then reproducible and equals the oracle's rank-order
+ * reduce bit for bit). The sources may be peer GPUs' buffers mapped over NVLink; n_src <= 8, n_elems even. ---- */
+int spmm_reduce_blocks_device(int device, int n_src, const double *const *d_src_list, long long n_elems,
+                              double *d_out, void *stream);
+
 /* ---- partition formulas (bit-for-bit the reference's integer arithmetic) ---- */
 void spmm_partition_rows(int n_rows, int n_ranks, int rank, int *begin, int *end);           /* RowWise.cpp:26-29 */
 void spmm_partition_cols(int k, int n_ranks, int rank, int *begin, int *end);                /* ColumnWise.cpp:25-28 */

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "spmm_multiply_nnz_range_host": (_i, [_p, _ll, _ll, _i, _i, _p, _i, _p, _i]),
     "spmm_nnz_range_rows": (_i, [_p, _ll, _ll, _pi, _pi]),
     "spmm_multiply_nnz_range_device": (_i, [_p, _ll, _ll, _i, _i, _p, _i, _p, _i, _p]),
+    "spmm_reduce_blocks_device": (_i, [_i, _i, C.POINTER(_p), _ll, _p, _p]),
     "spmm_partition_rows": (None, [_i, _i, _i, _pi, _pi]),
     "spmm_partition_cols": (None, [_i, _i, _i, _pi, _pi]),
     "spmm_partition_nnz": (None, [_ll, _i, _i, _pll, _pll]),
@@ -102,6 +103,12 @@ def lib() -> C.CDLL:
 def check(status: int) -> None:
     if status != SPMM_OK:
         raise SpmmError(status, (lib().spmm_last_error() or b"").decode())
+
+
+def reduce_blocks(device: int, src_ptrs, n_elems: int, out_ptr: int, stream: int = 0) -> None:
+    """out = sum of the source blocks in list order (peer buffers over NVLink allowed); spmm_reduce_blocks_device."""
+    arr = (C.c_void_p * len(src_ptrs))(*[C.c_void_p(int(p)) for p in src_ptrs])
+    check(lib().spmm_reduce_blocks_device(device, len(src_ptrs), arr, n_elems, C.c_void_p(out_ptr), C.c_void_p(stream)))
 
 
 def partition_rows(n_rows: int, n_ranks: int, rank: int) -> tuple[int, int]:

@@ -577,6 +577,53 @@ int spmm_multiply_nnz_range_device(spmm_csr_t A, long long nnz_begin, long long 
 
 } // extern "C"
 
+// Column-block strategy without NCCL: this rank's block of C = sum over ranks of their partial blocks, read straight from
+// the peers' buffers over NVLink (P2P loads) and added in ascending rank order — the order of the reference's MPI_Reduce on
+// a single communicator walk and of the oracle, so the result is reproducible bit for bit.
+struct ReduceSrc
+{
+    const double *p[8];
+};
+__global__ void __launch_bounds__(256) reduce_blocks_kernel(const ReduceSrc src, int n_src, double *__restrict__ out,
+                                                            long long n_pairs)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += stride)
+    {
+        double2 acc = __ldcs(reinterpret_cast<const double2 *>(src.p[0]) + i);
+        for (int r = 1; r < n_src; ++r)
+        {
+            const double2 v = __ldcs(reinterpret_cast<const double2 *>(src.p[r]) + i);
+            acc.x += v.x;
+            acc.y += v.y;
+        }
+        reinterpret_cast<double2 *>(out)[i] = acc;
+    }
+}
+
+extern "C" int spmm_reduce_blocks_device(int device, int n_src, const double *const *d_src_list, long long n_elems,
+                                         double *d_out, void *stream)
+{
+    SPMM_REQUIRE(n_src >= 1 && n_src <= 8, "n_src must be between 1 and 8");
+    SPMM_REQUIRE(d_src_list != nullptr && d_out != nullptr, "source list / output is NULL");
+    SPMM_REQUIRE(n_elems >= 0 && n_elems % 2 == 0, "n_elems must be even (16-byte accesses)");
+    if (n_elems == 0)
+        return SPMM_OK;
+    ReduceSrc src = {};
+    for (int i = 0; i < n_src; ++i)
+    {
+        SPMM_REQUIRE(d_src_list[i] != nullptr && (uintptr_t)d_src_list[i] % 16 == 0, "sources must be 16-byte aligned");
+        src.p[i] = d_src_list[i];
+    }
+    SPMM_REQUIRE((uintptr_t)d_out % 16 == 0, "output must be 16-byte aligned");
+    SPMM_CUDA(cudaSetDevice(device));
+    const long long pairs = n_elems / 2;
+    const int grid = (int)std::min<long long>((pairs + 255) / 256, (long long)device_props(device).sm_count * 8);
+    reduce_blocks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, n_src, d_out, pairs);
+    SPMM_CUDA(cudaGetLastError());
+    return SPMM_OK;
+}
+
 // Host-buffer plumbing shared by the *_host entry points: B up, launch, C_local down.
 template <typename Launch>
 static int host_call(spmm_csr_t A, const double *B, size_t nb, double *C, size_t nc, Launch launch)

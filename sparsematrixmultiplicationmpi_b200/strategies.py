@@ -279,6 +279,28 @@ class ColumnBlocks:
         dist.reduce_scatter_tensor(out, partial, op=dist.ReduceOp.SUM, group=self.group)
         return out
 
+    def multiply_reduce_scatter_p2p(self, B_local: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """This rank's block of C without NCCL: every rank multiplies into a partial C that lives in symmetric memory
+        (mapped into all ranks over NVLink), then reads block `rank` of every peer's partial with P2P loads and adds
+        them in ascending rank order (spmm_reduce_blocks_device) — deterministic, the oracle's order."""
+        if self.P == 1 or self.P > 8 or (self.block * self.k) % 2:
+            return self.reduce_scatter(self.multiply_local(B_local), out)
+        if getattr(self, "_symm", None) is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            group = self.group if self.group is not None else dist.group.WORLD
+            buf = symm_mem.empty((self.block * self.P, self.k), dtype=torch.float64, device=B_local.device)
+            self._symm = (buf, symm_mem.rendezvous(buf, group))
+        partial, hdl = self._symm
+        if out is None:
+            out = torch.empty((self.block, self.k), dtype=torch.float64, device=B_local.device)
+        hdl.barrier(channel=0)  # nobody still reads the partial of the previous call
+        self.multiply_local(B_local, partial)
+        hdl.barrier(channel=0)  # every partial is complete
+        off = self.rank * self.block * self.k * 8
+        _cabi.reduce_blocks(B_local.device.index, [int(hdl.buffer_ptrs[p]) + off for p in range(self.P)],
+                            self.block * self.k, out.data_ptr(), torch.cuda.current_stream(B_local.device).cuda_stream)
+        return out
+
     def multiply_reduce_scatter_overlapped(self, B_local: torch.Tensor, chunks: int = 4) -> torch.Tensor:
         """Same result as reduce_scatter(multiply_local(B)) — this rank's block of C — but the partial
         C is produced in reduce-scatter chunk order: for chunk c the rows c*cb..(c+1)*cb of EVERY rank's

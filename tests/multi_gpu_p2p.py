@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import pyoracle  # noqa: E402
 import sparsematrixmultiplicationmpi_b200 as spmm  # noqa: E402
 from sparsematrixmultiplicationmpi_b200 import generators as gen  # noqa: E402
-from sparsematrixmultiplicationmpi_b200.strategies import CudaCompute, RowWise  # noqa: E402
+from sparsematrixmultiplicationmpi_b200.strategies import ColumnBlocks, CudaCompute, RowWise  # noqa: E402
 
 
 def main():
@@ -44,6 +44,17 @@ def main():
             assert np.array_equal(root.cpu().numpy(), nccl), "gather-to-root p2p mismatch"
         else:
             assert root is None
+        dist.barrier()
+        # column blocks: partial C reduced by P2P loads in rank order against NCCL reduce-scatter
+        cb = ColumnBlocks.from_host(eng, host, k)
+        Bl = torch.from_numpy(np.ascontiguousarray(B[cb.col_start:cb.col_end])).cuda()
+        mine_nccl = cb.reduce_scatter(cb.multiply_local(Bl)).cpu().numpy()
+        for _ in range(2):  # twice: the symmetric partial buffer is reused
+            mine_p2p = cb.multiply_reduce_scatter_p2p(Bl).cpu().numpy()
+        r0 = rank * cb.block
+        want = ref[r0:r0 + cb.block]
+        assert np.all(np.abs(mine_p2p[:want.shape[0]] - want) <= 1e-12 * np.abs(want)), f"rank {rank}: p2p reduce mismatch k={k}"
+        assert np.all(np.abs(mine_p2p - mine_nccl) <= 1e-12 * np.abs(mine_nccl) + 1e-300)
         dist.barrier()
     if rank == 0:
         print("p2p ok: world", P)

@@ -618,3 +618,17 @@ def test_host_multiply_k_slab_pipeline(oracle, slabs):
             assert_close_rel(again, ref, tol=REL_TOL)
     finally:
         _cabi.tune("reset", 0)
+
+
+def test_reduce_blocks_rank_order():
+    """spmm_reduce_blocks_device: sources added in list order (the column-block strategy's reduce over peer buffers)."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    srcs = [torch.randn(100_002, dtype=torch.float64, device="cuda", generator=g) * 10.0 ** (3 * i) for i in range(5)]
+    out = torch.empty_like(srcs[0])
+    _cabi.reduce_blocks(0, [t.data_ptr() for t in srcs], out.numel(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    want = srcs[0].clone()
+    for t in srcs[1:]:
+        want += t  # ((s0 + s1) + s2) + ...
+    assert torch.equal(out, want)
+    with pytest.raises(_cabi.SpmmError):
+        _cabi.reduce_blocks(0, [t.data_ptr() for t in srcs], 7, out.data_ptr())  # odd element count

@@ -381,10 +381,12 @@ def multi_gpu(args, emit, dev, rank, world):
         t_r = timed(lambda: plan.reduce_scatter(partial, mine), 5)
         t_all = timed(lambda: plan.reduce_scatter(plan.multiply_local(Bl, partial), mine), 5)
         t_ov = {c: timed(lambda c=c: plan.multiply_reduce_scatter_overlapped(Bl, chunks=c), 5) for c in (2, 4, 8)}
+        t_p2p = timed(lambda: plan.multiply_reduce_scatter_p2p(Bl, mine), 5)
         nnz = n * npr
         if rank == 0:
             emit({"config": "cfg5", "strategy": "column blocks + reduce-scatter", "n_gpus": world, "k": k,
                   "kernel_ms": t_k, "reduce_scatter_ms": t_r, "kernel+reduce_scatter_ms": t_all,
+                  "kernel+p2p_rank_order_reduce_ms": t_p2p,
                   "kernel+reduce_scatter_overlapped_ms": t_ov,
                   "gflops_total_overlapped": 2.0 * nnz * k / (min(t_ov.values()) * 1e-3) / 1e9,
                   "gflops_total": 2.0 * nnz * k / (t_all * 1e-3) / 1e9,
