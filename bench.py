@@ -229,7 +229,7 @@ def main():
         elif args.kernel == "packed":
             A.build_packed(1, 8)
         elif args.kernel in ("auto", "tiled"):
-            A.build_tiles(-1)  # what AUTO does by itself on its first k>=16 multiply; done here so it is outside any timing
+            A.build_tiles(-1, 0, k)  # what AUTO does by itself on its first k>=16 multiply; done here so it is outside any timing
         Bd = torch.randint(1, 101, (n, k), device=dev).double()
         Cd = torch.empty((n, k), dtype=torch.float64, device=dev)
         sets.append((A, Bd, Cd))

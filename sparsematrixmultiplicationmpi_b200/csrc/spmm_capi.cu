@@ -244,6 +244,7 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "tiled.depth") t.tiled_depth = value;
     else if (k == "tiled.pool") t.tiled_pool = value;
     else if (k == "tiled.ns") t.tiled_ns = value;
+    else if (k == "tiled.ksplit") t.tiled_ksplit = value;
     else if (k == "tiled.npw") t.tiled_npw = value;
     else if (k == "host.slabs") t.host_slabs = value;
     else if (k == "tiled.prefetch") t.tiled_prefetch = value;
@@ -438,11 +439,23 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
     // AUTO builds the tile layout the first time a multiply can use it (k >= 8, even, mid-sized matrix with
     // regular rows): one-off, a few milliseconds, 16 bytes per non-zero next to the CSR. spmm_tune_set("tiled", 0)
     // or an explicit spmm_csr_build_tiles(A, 0, 0) keeps the CSR kernels.
+    if (kernel == SPMM_KERNEL_AUTO && A->tl_auto && A->tl_T != 0 && A->tl_ksplit > std::max(1, (k_count + 15) / 16))
+    {
+        free_tiles(A); // built for a wider k: its long chunks would leave SMs idle here, build again for this k
+        A->tl_tried = false;
+    }
     if (kernel == SPMM_KERNEL_AUTO && !A->tl_tried && A->tl_T == 0 && tuning().tiled != 0 && k_count >= 8 &&
         k_count % 2 == 0 && A->nnz >= 200000 && A->nnz <= (64ll << 20))
     {
         A->tl_tried = true;
-        if (spmm_csr_build_tiles(A, -1, 0) != SPMM_OK)
+        // many k-tiles: longer chunks shared by several CTAs (one k-tile group each), fewer window warm-ups
+        const int saved = tuning().tiled_ksplit;
+        if (saved == 0)
+            tuning().tiled_ksplit = k_count >= 64 ? 4 : (k_count >= 32 ? 2 : 1);
+        const int brc = spmm_csr_build_tiles(A, -1, 0);
+        tuning().tiled_ksplit = saved;
+        A->tl_auto = true;
+        if (brc != SPMM_OK)
             free_tiles(A); // not fatal: the CSR kernels stay in charge
     }
     return launch_rows(A, 0, A->n_rows, 0, A->nnz, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count,
@@ -481,7 +494,12 @@ int spmm_multiply_scatter_device(spmm_csr_t A, const double *d_B, int k, int n_d
         A->nnz >= 200000 && A->nnz <= (64ll << 20))
     {
         A->tl_tried = true;
-        if (spmm_csr_build_tiles(A, -1, 0) != SPMM_OK)
+        const int saved = tuning().tiled_ksplit;
+        if (saved == 0)
+            tuning().tiled_ksplit = k >= 64 ? 4 : (k >= 32 ? 2 : 1);
+        const int brc = spmm_csr_build_tiles(A, -1, 0);
+        tuning().tiled_ksplit = saved;
+        if (brc != SPMM_OK)
             free_tiles(A);
     }
     return launch_rows(A, 0, A->n_rows, 0, A->nnz, 0, d_B, k, d_C, k, k,

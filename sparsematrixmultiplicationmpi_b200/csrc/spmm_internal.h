@@ -66,6 +66,7 @@ struct Tuning
     int tiled_depth = 0;    // build: work items in flight (2..8)
     int tiled_pool = 0;     // build: rows of the singles pool
     int tiled_ns = 0;       // build: cap on the window slots
+    int tiled_ksplit = 0;   // build: CTAs that share one chunk, each taking a group of k-tiles (0/1 none)
     int tiled_npw = 0;      // launch: producer warps (4, 8)
     int host_slabs = 0;     // host-buffer multiply: k-slabs in the PCIe pipeline (0 auto, 1 none)
     int tiled_prefetch = -1; // launch: tiles ahead whose blob is prefetched into L2 (-1 auto)
@@ -110,9 +111,10 @@ struct spmm_csr_s
     int *d_sptr = nullptr, *d_pcol = nullptr;
     double *d_pval = nullptr;
     // B-staged row tiles (spmm_tiled.cu), optional
-    int tl_T = 0, tl_BR = 0, tl_tiles = 0, tl_NS = 0, tl_POOL = 0, tl_max_recs = 0, tl_chunk = 0, tl_kt = 0, tl_depth = 0, tl_drains = 0;
+    int tl_T = 0, tl_BR = 0, tl_tiles = 0, tl_NS = 0, tl_POOL = 0, tl_max_recs = 0, tl_chunk = 0, tl_kt = 0, tl_depth = 0, tl_drains = 0, tl_ksplit = 0;
     long long tl_box_rows_loaded = 0, tl_single_rows = 0; // B rows staged per pass over the matrix
     bool tl_tried = false;                                // AUTO already attempted the lazy build
+    bool tl_auto = false;                                 // the layout was built by AUTO (it may rebuild it for another k)
     unsigned char *d_tblob = nullptr;
     void *d_tdesc = nullptr, *d_tloads = nullptr;
     int *d_tsingles = nullptr;

@@ -558,7 +558,7 @@ struct TiledArgs
     const double *B;
     double *C;
     long long ldb, ldc;
-    int n_tiles, n_chunks, tiles_per_chunk, T, BR, NS, POOL, kc, nkt, depth, prefetch;
+    int n_tiles, n_chunks /* shares: chunks x ksplit */, ksplit, tiles_per_chunk, T, BR, NS, POOL, kc, nkt, depth, prefetch;
     unsigned hdr_bytes;   // header + unit table bytes of a blob
     unsigned blob_stride; // bytes reserved per blob buffer in smem
     unsigned slab_off;    // offset of the slab (window slots, then the singles pool) from the aligned smem base
@@ -593,32 +593,46 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
     }
     __syncthreads();
 
-    // work items in loop order: for chunk (blockIdx.x, += gridDim.x) / for k-tile / for tile of the chunk
+    // work items in loop order: for share (blockIdx.x, += gridDim.x) / for k-tile of the share / for tile of the chunk.
+    // A share = a chunk x one of `ksplit` groups of consecutive k-tiles: with many k-tiles the chunks are made ksplit
+    // times longer and ksplit CTAs walk each of them, so the window is warmed up once per CTA instead of once per k-tile.
     struct Work
     {
-        int c, kt, t, t_begin, t_end;
+        int c, kt, kt_end, t, t_begin, t_end;
     };
     auto work_chunk = [&](Work &x) {
-        x.t_begin = x.c * a.tiles_per_chunk;
+        const int chunk = x.c / a.ksplit, part = x.c % a.ksplit;
+        x.t_begin = chunk * a.tiles_per_chunk;
         x.t_end = min(a.n_tiles, x.t_begin + a.tiles_per_chunk);
         x.t = x.t_begin;
-        x.kt = 0;
+        const int per = (a.nkt + a.ksplit - 1) / a.ksplit;
+        x.kt = min(a.nkt, part * per);
+        x.kt_end = min(a.nkt, x.kt + per);
+        if (x.kt >= x.kt_end) // fewer k-tiles than sharers: this share is empty
+            x.t = x.t_end = x.t_begin;
     };
     auto work_next = [&](Work &x) {
         if (++x.t < x.t_end)
             return;
         x.t = x.t_begin;
-        if (++x.kt < a.nkt)
+        if (++x.kt < x.kt_end)
             return;
-        x.c += gridDim.x;
-        if (x.c < a.n_chunks)
+        for (x.c += gridDim.x; x.c < a.n_chunks; x.c += gridDim.x)
+        {
             work_chunk(x);
+            if (x.t < x.t_end)
+                return;
+        }
     };
     Work cur;
-    cur.c = blockIdx.x;
+    for (cur.c = blockIdx.x; cur.c < a.n_chunks; cur.c += gridDim.x)
+    {
+        work_chunk(cur);
+        if (cur.t < cur.t_end)
+            break;
+    }
     if (cur.c >= a.n_chunks)
         return;
-    work_chunk(cur);
 
     if (warp >= NCW)
     {
@@ -1003,7 +1017,8 @@ int launch_tiled_t(const spmm_csr_s *A, const double *d_B, long long ldb, double
     a.ldc = ldc;
     a.n_tiles = A->tl_tiles;
     a.tiles_per_chunk = A->tl_chunk;
-    a.n_chunks = (A->tl_tiles + A->tl_chunk - 1) / A->tl_chunk;
+    a.ksplit = std::max(1, A->tl_ksplit);
+    a.n_chunks = ((A->tl_tiles + A->tl_chunk - 1) / A->tl_chunk) * a.ksplit;
     a.T = A->tl_T;
     a.BR = A->tl_BR;
     a.NS = A->tl_NS;
@@ -1129,7 +1144,7 @@ void free_tiles(spmm_csr_s *A)
     A->d_tdesc = nullptr;
     A->d_tloads = nullptr;
     A->d_tsingles = nullptr;
-    A->tl_T = A->tl_BR = A->tl_tiles = A->tl_NS = A->tl_POOL = A->tl_max_recs = A->tl_chunk = A->tl_kt = A->tl_depth = 0;
+    A->tl_T = A->tl_BR = A->tl_tiles = A->tl_NS = A->tl_POOL = A->tl_max_recs = A->tl_chunk = A->tl_kt = A->tl_depth = A->tl_ksplit = 0;
     A->tl_box_rows_loaded = A->tl_single_rows = 0;
 }
 
@@ -1174,6 +1189,7 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
     SPMM_CUDA(cudaSetDevice(A->device));
     free_tiles(A);
     A->tl_tried = true; // an explicit call (build or drop) settles it: AUTO does not try again
+    A->tl_auto = false;
     if (rows_per_tile == 0 || A->n_rows == 0 || A->nnz == 0)
         return SPMM_OK;
     const Tuning &tn = tuning();
@@ -1182,6 +1198,7 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
     const int sms = device_props(A->device).sm_count;
     // measured on the cop20k_A shape (profiles/r1_tiled.md): tall tiles and a wide window beat a deeper pipeline
     const int depth = (tn.tiled_depth >= 2 && tn.tiled_depth <= TB_DMAX) ? tn.tiled_depth : 2;
+    const int ksplit = std::max(1, std::min(8, tn.tiled_ksplit)); // CTAs per chunk (set from k by AUTO / the Python wrapper)
 
     BuildParams p = {};
     p.n_rows = A->n_rows;
@@ -1201,8 +1218,9 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
         p.hdr_bytes = (int)hdr_bytes_of(T);
         // chunks: a multiple of the SM count, about 48 tiles each (window warm-up amortised, work balanced)
         const int per_sm = std::max(1, (int)((p.n_tiles + (long long)sms * 48 - 1) / ((long long)sms * 48)));
+        const int n_chunks_want = std::max(1, sms * per_sm / ksplit); // ksplit CTAs share a chunk (one k-tile group each)
         p.tiles_per_chunk =
-            tn.tiled_chunk > 0 ? tn.tiled_chunk : std::max(1, (p.n_tiles + sms * per_sm - 1) / (sms * per_sm));
+            tn.tiled_chunk > 0 ? tn.tiled_chunk : std::max(1, (p.n_tiles + n_chunks_want - 1) / n_chunks_want);
         // dry run with the largest window: record maximum and singles of this tile height
         p.NS = TB_NSMAX;
         p.POOL = 1 << 20;
@@ -1284,6 +1302,7 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
     A->tl_chunk = p.tiles_per_chunk;
     A->tl_kt = kt;
     A->tl_depth = depth;
+    A->tl_ksplit = ksplit;
     A->tl_drains = res.status[ST_DRAINS];
     A->tl_box_rows_loaded = (long long)res.totals[TOT_LOADS] * BR;
     A->tl_single_rows = (long long)res.totals[TOT_SINGLES];

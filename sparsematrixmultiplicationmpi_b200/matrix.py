@@ -158,9 +158,17 @@ class DeviceCSR:
         _cabi.check(_cabi.lib().spmm_multiply_scatter_device(self.handle, C.c_void_p(d_B), k, len(d_C_list), arr,
                                                              _cabi.KERNELS[kernel], C.c_void_p(stream)))
 
-    def build_tiles(self, rows_per_tile: int = -1, box_rows: int = 0) -> dict:
-        """Row tiles with TMA-staged B rows (spmm_tiled.cu); -1 = largest tile that fits shared memory."""
-        _cabi.check(_cabi.lib().spmm_csr_build_tiles(self.handle, rows_per_tile, box_rows))
+    def build_tiles(self, rows_per_tile: int = -1, box_rows: int = 0, k: int = 0) -> dict:
+        """Row tiles with TMA-staged B rows (spmm_tiled.cu); -1 = tallest tile that fits shared memory.
+        k (optional): the number of B columns the layout will mostly be used with — from 32 columns up the chunks are
+        made longer and shared by 2 or 4 CTAs, each taking a group of k-tiles (what AUTO does on its own)."""
+        if k > 0:
+            _cabi.tune("tiled.ksplit", 4 if k >= 64 else (2 if k >= 32 else 1))
+        try:
+            _cabi.check(_cabi.lib().spmm_csr_build_tiles(self.handle, rows_per_tile, box_rows))
+        finally:
+            if k > 0:
+                _cabi.tune("tiled.ksplit", 0)
         return self.tile_info()
 
     def tile_info(self) -> dict:

@@ -496,7 +496,8 @@ def test_tiled_kernel_vs_oracle(oracle, shape, k):
 @pytest.mark.parametrize("T,BR", [(8, 4), (16, 16), (64, 8), (64, 32), (128, 16), (248, 16)])
 @pytest.mark.parametrize("tune", [{}, {"tiled.kt": 32}, {"tiled.kt": 32, "tiled.ncw": 12, "tiled.depth": 2},
                                   {"tiled.ncw": 16, "tiled.unroll": 8, "tiled.depth": 8}, {"tiled.ncw": 4, "tiled.unroll": 8},
-                                  {"tiled.thr": 1, "tiled.chunk": 3}, {"tiled.thr": 100, "tiled.depth": 3}])
+                                  {"tiled.thr": 1, "tiled.chunk": 3}, {"tiled.thr": 100, "tiled.depth": 3},
+                                  {"tiled.ksplit": 2}, {"tiled.ksplit": 4, "tiled.kt": 32}, {"tiled.ksplit": 3, "tiled.chunk": 5}])
 def test_tiled_shapes_and_teams(oracle, T, BR, tune):
     """Explicit tile heights / box heights x k-tile, warps, pipeline depth, box threshold (all boxes .. all single
     rows), chunk length: split rows (the 900-long row: 8 segments folded by shuffles), empty rows, ragged last
