@@ -1203,14 +1203,14 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
     BuildParams p = {};
     p.n_rows = A->n_rows;
     p.lgBR = lg2(BR);
-    p.thr = tn.tiled_thr > 0 ? tn.tiled_thr : std::max(2, BR / 4);
+    p.thr = tn.tiled_thr > 0 ? tn.tiled_thr : std::max(2, 3 * BR / 8);
     p.depth = depth;
     BuildResult res;
-    const int auto_cand[] = {64, 48, 32, 16};
+    const int auto_cand[] = {96, 80, 72, 64, 48, 32, 16};
     int chosen = 0;
     BuildParams best = {};
     double best_score = 0.0;
-    for (int ci = 0; ci < (rows_per_tile > 0 ? 1 : 4); ++ci)
+    for (int ci = 0; ci < (rows_per_tile > 0 ? 1 : 7); ++ci)
     {
         const int T = rows_per_tile > 0 ? rows_per_tile : auto_cand[ci];
         p.T = T;
