@@ -1210,7 +1210,9 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
     int chosen = 0;
     BuildParams best = {};
     double best_score = 0.0;
-    for (int ci = 0; ci < (rows_per_tile > 0 ? 1 : 7); ++ci)
+    // short chunks (one CTA per chunk walks every k-tile) favour 64-row tiles, long shared chunks taller ones (measured)
+    const int first_cand = ksplit > 1 ? 0 : 3;
+    for (int ci = first_cand; ci < (rows_per_tile > 0 ? first_cand + 1 : 7); ++ci)
     {
         const int T = rows_per_tile > 0 ? rows_per_tile : auto_cand[ci];
         p.T = T;
