@@ -40,7 +40,8 @@ enum spmm_kernel
     SPMM_KERNEL_ROWBLOCK = 3, /* R consecutive rows per team over the union of their columns (needs spmm_csr_build_rowblocks) */
     SPMM_KERNEL_PACKED = 4,   /* warp-packed coalesced A stream (needs spmm_csr_build_packed) */
     SPMM_KERNEL_STAGED = 5,   /* CSR rows with the id/value stream staged through shared memory by cp.async (k multiple of 16, rows <= 2048 long) */
-    SPMM_KERNEL_TILED = 6     /* row tiles whose B rows are staged in shared memory by TMA (needs spmm_csr_build_tiles; even k) */
+    SPMM_KERNEL_TILED = 6,    /* row tiles whose B rows are staged in shared memory by TMA (needs spmm_csr_build_tiles; even k) */
+    SPMM_KERNEL_UNION = 7     /* blocks of 2 or 4 rows over the union of their columns, B rows staged by TMA gather4 (needs spmm_csr_build_union; even k) */
 };
 
 const char *spmm_last_error(void);
@@ -112,6 +113,18 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows);
  * share of the non-zeros whose B row is staged on its own. Zeros when no layout is built. */
 int spmm_csr_tile_info(spmm_csr_t A, int *rows_per_tile, int *box_rows, int *window_slots, int *max_records,
                        double *reuse, double *single_fraction);
+/* Optional fifth layout (spmm_union.cu): rows_per_block (2 or 4; -1 = 2) consecutive rows are walked
+ * over the ascending union of their column lists so that one B row read from shared memory feeds several rows from
+ * registers; B rows are staged one by one (TMA gather4) in a least-recently-used window, the k-tile is 32 columns.
+ * `k` is the column count the layout is cut for (chunks = SMs / k-tiles). 0 drops the layout. Built on the host from a
+ * copy of the CSR arrays (one-off per matrix); fails with SPMM_ERR_UNSUPPORTED on rows that are not sorted by column or
+ * longer than 16,320 union entries. B must be finite (absent union entries are 0.0 values). Serves
+ * SparseMatrixFatVectorMultiply.cpp:17-28. */
+int spmm_csr_build_union(spmm_csr_t A, int rows_per_block, int k);
+/* union_per_nnz = B-row reads per non-zero; padding = slot steps per union entry; staged_per_row = B rows brought into
+ * shared memory per matrix row and pass. Zeros when no layout is built. */
+int spmm_csr_union_info(spmm_csr_t A, int *rows_per_block, int *k_tile, int *window_rows, double *union_per_nnz,
+                        double *padding, double *staged_per_row);
 /* Sub-matrix A[:, col_begin:col_end) with local column ids (column-block strategy,
  * north_star reading of sparseMatrixFatVectorMultiplyColumnWise). Built on the device. */
 int spmm_csr_column_block(spmm_csr_t A, int col_begin, int col_end, spmm_csr_t *out);

@@ -248,6 +248,10 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "tiled.npw") t.tiled_npw = value;
     else if (k == "host.slabs") t.host_slabs = value;
     else if (k == "tiled.prefetch") t.tiled_prefetch = value;
+    else if (k == "union.slots") t.union_slots = value;
+    else if (k == "union.split") t.union_split = value;
+    else if (k == "union.auto") t.union_auto = value;
+    else if (k == "union.debug") t.union_debug = value;
     else if (k == "rows.threads") t.rows_threads = value;
     else if (k == "rows.unroll") t.rows_unroll = value;
     else if (k == "rows.vec") t.rows_vec = value;
@@ -349,6 +353,7 @@ int spmm_csr_destroy(spmm_csr_t A)
     free_rowblocks(A);
     free_packed(A);
     free_tiles(A);
+    free_union(A);
     drop_bounds(A, -1);
     cudaFree(A->d_B);
     cudaFree(A->d_C);
@@ -430,8 +435,15 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
     SPMM_REQUIRE(d_B != nullptr || A->nnz == 0, "d_B is NULL");
     SPMM_CUDA(cudaSetDevice(A->device));
     cudaStream_t s = (cudaStream_t)stream;
-    SPMM_REQUIRE(kernel >= SPMM_KERNEL_AUTO && kernel <= SPMM_KERNEL_TILED, "unknown kernel id");
+    SPMM_REQUIRE(kernel >= SPMM_KERNEL_AUTO && kernel <= SPMM_KERNEL_UNION, "unknown kernel id");
     SPMM_REQUIRE(kernel != SPMM_KERNEL_TILED || A->tl_T != 0, "tiled kernel requested but spmm_csr_build_tiles was not called (or found no fitting tile shape)");
+    if (kernel == SPMM_KERNEL_UNION)
+    {
+        SPMM_REQUIRE(A->un != nullptr, "union kernel requested but spmm_csr_build_union was not called (or the layout does not fit)");
+        SPMM_REQUIRE(k_begin % 2 == 0 && union_shape_ok(A, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count),
+                     "union kernel: needs even k, even leading dimensions and 16-byte aligned B and C");
+        return launch_union(A, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
+    }
     SPMM_REQUIRE(kernel != SPMM_KERNEL_PACKED || A->pk_R != 0, "packed kernel requested but spmm_csr_build_packed was not called");
     SPMM_REQUIRE(kernel != SPMM_KERNEL_ROWBLOCK || A->rb_R != 0, "row-block kernel requested but spmm_csr_build_rowblocks was not called");
     if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)

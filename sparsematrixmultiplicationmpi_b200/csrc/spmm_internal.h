@@ -70,6 +70,10 @@ struct Tuning
     int tiled_npw = 0;      // launch: producer warps (4, 8)
     int host_slabs = 0;     // host-buffer multiply: k-slabs in the PCIe pipeline (0 auto, 1 none)
     int tiled_prefetch = -1; // launch: tiles ahead whose blob is prefetched into L2 (-1 auto)
+    int union_slots = 0;    // union layout: slots per item (4: 8-lane teams, 8: 4-lane teams)
+    int union_split = 0;    // union layout: blocks with more union entries are cut into segments of about this length
+    int union_debug = 0;    // diagnostics, wrong results by design (see spmm_union.cu)
+    int union_auto = -1;    // -1 auto, 0 AUTO never builds / uses the union layout
 };
 Tuning &tuning();
 
@@ -80,6 +84,19 @@ struct DeviceProps
 };
 const DeviceProps &device_props(int device);
 
+} // namespace spmm
+
+namespace spmm
+{
+// union layout on the device (spmm_union.cu; built on the host by spmm_union_build.cu)
+struct UnionDev
+{
+    int R = 0, KT = 0, SL = 0, NCW = 0, D = 0, NG = 0, n_chunks = 0, n_items = 0, nkt = 0, ring_bytes = 0, slab_off = 0, drains = 0, maxg = 0, NPW = 4;
+    long long staged_rows = 0, union_entries = 0, slot_steps = 0;
+    unsigned char *d_blob = nullptr;
+    void *d_items = nullptr, *d_gcols = nullptr;
+    int *d_chunk_first = nullptr, *d_gslot = nullptr;
+};
 } // namespace spmm
 
 struct spmm_csr_s
@@ -118,6 +135,9 @@ struct spmm_csr_s
     unsigned char *d_tblob = nullptr;
     void *d_tdesc = nullptr, *d_tloads = nullptr;
     int *d_tsingles = nullptr;
+    // row blocks over union columns with a gather4-staged window (spmm_union.cu), optional
+    spmm::UnionDev *un = nullptr;
+    bool un_tried = false; // AUTO already attempted the lazy build
     // precomputed CTA cuts per (kind, grid size): kind 0 = rows of the CSR, 1 = row blocks, 2 = packed slices
     mutable std::map<long long, int *> bounds;
     // merge-path scratch (carry rows), grown on demand
@@ -148,6 +168,10 @@ bool tiled_shape_ok(const spmm_csr_s *A, const double *d_B, long long ldb, const
 int launch_tiled(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int kc,
                  cudaStream_t stream, const struct ExtraDst *extra = nullptr);
 void free_tiles(spmm_csr_s *A);
+bool union_shape_ok(const spmm_csr_s *A, const double *d_B, long long ldb, const double *d_C, long long ldc, int kc);
+int launch_union(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int kc,
+                 cudaStream_t stream, const struct ExtraDst *extra = nullptr);
+void free_union(spmm_csr_s *A);
 bool staged_shape_ok(const spmm_csr_s *A, int w, int kl, int nv, int tiles, int kc);
 int launch_staged(const spmm_csr_s *A, int nv, int tiles, const double *d_B, long long ldb, double *d_C, long long ldc,
                   cudaStream_t stream);

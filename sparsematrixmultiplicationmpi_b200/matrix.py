@@ -178,6 +178,20 @@ class DeviceCSR:
         return {"rows_per_tile": t.value, "box_rows": b.value, "window_slots": ns.value, "max_records": mr.value,
                 "reuse": r.value, "single_fraction": sf.value}
 
+    def build_union(self, rows_per_block: int = -1, k: int = 64) -> dict:
+        """Blocks of 2 or 4 rows over the union of their columns, B rows staged by TMA gather4 (spmm_union.cu);
+        k = the number of B columns the layout is cut for. 0 rows per block drops the layout."""
+        _cabi.check(_cabi.lib().spmm_csr_build_union(self.handle, rows_per_block, k))
+        return self.union_info()
+
+    def union_info(self) -> dict:
+        r, kt, wr = C.c_int(), C.c_int(), C.c_int()
+        u, p, st = C.c_double(), C.c_double(), C.c_double()
+        _cabi.check(_cabi.lib().spmm_csr_union_info(self.handle, C.byref(r), C.byref(kt), C.byref(wr), C.byref(u),
+                                                    C.byref(p), C.byref(st)))
+        return {"rows_per_block": r.value, "k_tile": kt.value, "window_rows": wr.value, "union_per_nnz": u.value,
+                "padding": p.value, "staged_per_row": st.value}
+
     def nnz_range_rows(self, nnz_begin: int, nnz_end: int) -> tuple[int, int]:
         a, b = C.c_int(), C.c_int()
         _cabi.check(_cabi.lib().spmm_nnz_range_rows(self.handle, nnz_begin, nnz_end, C.byref(a), C.byref(b)))

@@ -221,6 +221,49 @@ def cfg2(args, emit, dev):
                     A.close()
                 del sets
                 torch.cuda.empty_cache()
+        if k >= 2 and k % 2 == 0 and args.unions:
+            for spec in args.unions.split(","):
+                f = [int(x) for x in spec.split("x")] + [0] * 7
+                R, kt, sl, ncw, depth, split, npw = f[:7]
+
+                def make(s, R=R, kt=kt, sl=sl, ncw=ncw, depth=depth, split=split, npw=npw):
+                    A = spmm.DeviceCSR.from_host(host, dev.index, 0)
+                    _cabi.tune("reset", 0)
+                    _cabi.tune("tiled.kt", kt)
+                    _cabi.tune("union.slots", sl)
+                    _cabi.tune("tiled.ncw", ncw)
+                    _cabi.tune("tiled.depth", depth)
+                    _cabi.tune("union.split", split)
+                    _cabi.tune("tiled.npw", npw)
+                    try:
+                        A.build_union(R, k)
+                    finally:
+                        _cabi.tune("reset", 0)
+                    return A
+                try:
+                    sets = operand_sets(make, n, n, k, dev, fp)
+                except Exception as e:
+                    emit({"config": "cfg2", "k": k, "union": spec, "error": str(e)[:200]})
+                    continue
+                info = sets[0][0].union_info()
+                # parity against the CSR row kernel before any timing
+                A0, B0, C0 = sets[0]
+                ref = torch.empty_like(C0)
+                stream = torch.cuda.current_stream().cuda_stream
+                A0.multiply(B0.data_ptr(), k, ref.data_ptr(), "rows", stream)
+                C0.fill_(float("nan"))
+                A0.multiply(B0.data_ptr(), k, C0.data_ptr(), "union", stream)
+                torch.cuda.synchronize()
+                err = ((C0 - ref).abs() / ref.abs().clamp_min(1e-300)).nan_to_num(nan=float("inf")).max().item()
+                info["max_rel_err_vs_rows"] = err
+                vs = [(f"union {spec}", "union", {})]
+                if args.variants:
+                    vs += [(f"union {spec} dbg={d}", "union", {"union.debug": d}) for d in (64, 65, 66)]
+                run_variants("cfg2", sets, k, vs, args.iters, emit, host.nnz, n, {"union": info})
+                for A, _, _ in sets:
+                    A.close()
+                del sets
+                torch.cuda.empty_cache()
         if k >= 16 and args.packed:
             for R, kl in ((1, 8), (1, 16), (2, 8), (2, 16)):
                 if (k // 2) % kl:
@@ -458,6 +501,7 @@ def main():
     ap.add_argument("--variants", action="store_true")
     ap.add_argument("--cpu", action="store_true", help="also time the reference CPU code on cfg2")
     ap.add_argument("--packed", action="store_true", help="also time the warp-packed stream layouts on cfg2")
+    ap.add_argument("--unions", default="", help="cfg2: union layouts to time, e.g. 2x32x4x6x8x48 (rows per block x k-tile x slots x consumer warps x depth x split length)")
     ap.add_argument("--tiles", default="", help="cfg2: tile layouts to time, e.g. -1x16,64x16,32x8x32x2 (rows_per_tile x box_rows [x k-tile [x box threshold [x depth]]])")
     ap.add_argument("--only", default="", help="regex: run only the variants whose label matches")
     ap.add_argument("--rowblocks", default="0,2,4", help="row-block layouts to time on cfg2")
