@@ -76,6 +76,18 @@ int spmm_csr_from_coo_device(int device, int n_rows, int n_cols, long long n_ent
                              const int *d_rows, const int *d_cols, const double *d_vals,
                              int symmetric, spmm_csr_t *out);
 
+/* Text half of readMatrixMarketFile (utils.cpp:70-153) in native code: comment lines, the size line, then the body as a
+ * stream of whitespace-separated tokens (line breaks mean nothing, as with the reference's operator>>), converted by all
+ * host threads. Returns malloc'ed 0-based records (free them with spmm_mm_free); *symmetric is set when a comment line
+ * contains "symmetric" (:88-91), a "pattern" file gets 1.0 values (:130-133). Errors: the reference's messages
+ * "Unable to open file: ", "Failed to read matrix dimensions from file: ", "Failed to read data from file: " (:77,:114,:140)
+ * through spmm_last_error(); records outside the declared size (undefined behaviour in the reference) are an error. */
+int spmm_mm_read(const char *path, int *n_rows, int *n_cols, long long *n_entries, int *symmetric,
+                 int **rows, int **cols, double **vals);
+void spmm_mm_free(int *rows, int *cols, double *vals);
+/* readMatrixMarketFile end to end: spmm_mm_read + spmm_csr_from_coo_host (utils.cpp:70-185). */
+int spmm_csr_from_matrix_market(int device, const char *path, spmm_csr_t *out);
+
 int spmm_csr_destroy(spmm_csr_t A);
 int spmm_csr_info(spmm_csr_t A, int *n_rows, int *n_cols, long long *nnz, int *device);
 int spmm_csr_device_ptrs(spmm_csr_t A, const int **d_rowptr, const int **d_colidx, const double **d_vals);

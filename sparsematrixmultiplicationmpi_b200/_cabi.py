@@ -46,6 +46,9 @@ PROTOTYPES = {
     "spmm_csr_create_device": (_i, [_i, _i, _i, _ll, _p, _p, _p, _i, C.POINTER(_p)]),
     "spmm_csr_from_coo_host": (_i, [_i, _i, _i, _ll, _p, _p, _p, _i, C.POINTER(_p)]),
     "spmm_csr_from_coo_device": (_i, [_i, _i, _i, _ll, _p, _p, _p, _i, C.POINTER(_p)]),
+    "spmm_mm_read": (_i, [C.c_char_p, _pi, _pi, _pll, _pi, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
+    "spmm_mm_free": (None, [_p, _p, _p]),
+    "spmm_csr_from_matrix_market": (_i, [_i, C.c_char_p, C.POINTER(_p)]),
     "spmm_csr_destroy": (_i, [_p]),
     "spmm_csr_info": (_i, [_p, _pi, _pi, _pll, _pi]),
     "spmm_csr_device_ptrs": (_i, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),

@@ -18,52 +18,40 @@ from .matrix import DeviceCSR, SparseMatrix, as_fat_vector
 def parse_matrix_market(filename: str):
     """Text front end of readMatrixMarketFile (utils.cpp:70-153) -> (n_rows, n_cols, rows, cols, vals, symmetric).
 
-    Header lines start with '%'; any of them containing "symmetric" marks the matrix symmetric (so
-    "skew-symmetric" counts, with no sign flip), "pattern" gives every record the value 1.0 (:84-105).
-    The first other line is "rows cols nnz" (:108-109); then nnz whitespace-separated records
-    "r c [v]", 1-based (:124-153). Errors are the reference's messages (:77, :114, :140).
+    Native tokenizer (csrc/mm_read.cu, spmm_mm_read): header lines start with '%'; any of them containing
+    "symmetric" marks the matrix symmetric (so "skew-symmetric" counts, with no sign flip), "pattern" gives every
+    record the value 1.0 (:84-105). The first other line is "rows cols nnz" (:108-109); then nnz records
+    "r c [v]", 1-based, as a whitespace-separated token stream (:124-153). Errors are the reference's messages
+    (:77, :114, :140), raised as RuntimeError.
     """
+    L = _cabi.lib()
+    nr, nc, sym, ne = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+    pr, pc, pv = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    _cabi.check(L.spmm_mm_read(filename.encode(), C.byref(nr), C.byref(nc), C.byref(ne), C.byref(sym), C.byref(pr),
+                               C.byref(pc), C.byref(pv)))
+    n = ne.value
     try:
-        f = open(filename, "rb")
-    except OSError:
-        raise RuntimeError("Unable to open file: " + filename)
-    with f:
-        symmetric = pattern = False
-        size_line = None
-        for raw in f:
-            if raw.startswith(b"%"):
-                symmetric |= b"symmetric" in raw
-                pattern |= b"pattern" in raw
-            else:
-                size_line = raw
-                break
-        try:
-            n_rows, n_cols, nnz = (int(t) for t in size_line.split()[:3])
-        except Exception:
-            raise RuntimeError("Failed to read matrix dimensions from file: " + filename)
-        tokens = f.read().split()
-    per = 2 if pattern else 3
-    if len(tokens) < per * nnz:
-        raise RuntimeError("Failed to read data from file: " + filename)
-    tokens = tokens[:per * nnz]
-    try:
-        rows = np.array(tokens[0::per], dtype=np.int64) - 1
-        cols = np.array(tokens[1::per], dtype=np.int64) - 1
-        vals = np.ones(nnz, dtype=np.float64) if pattern else np.array(tokens[2::per], dtype=np.float64)
-    except ValueError:
-        raise RuntimeError("Failed to read data from file: " + filename)
-    return n_rows, n_cols, rows.astype(np.int32), cols.astype(np.int32), vals, symmetric
+        if n and pr.value:
+            rows = np.ctypeslib.as_array(C.cast(pr, C.POINTER(C.c_int)), shape=(n,)).copy()
+            cols = np.ctypeslib.as_array(C.cast(pc, C.POINTER(C.c_int)), shape=(n,)).copy()
+            vals = np.ctypeslib.as_array(C.cast(pv, C.POINTER(C.c_double)), shape=(n,)).copy()
+        else:
+            rows, cols, vals = np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0, np.float64)
+    finally:
+        L.spmm_mm_free(pr, pc, pv)
+    return nr.value, nc.value, rows, cols, vals, bool(sym.value)
 
 
 def readMatrixMarketFile(filename: str, device: int = 0, return_device: bool = False):
     """MatrixMarket coordinate file -> SparseMatrix, bit-identical to the reference loader's CSR.
 
-    The records are parsed on the host; mirroring, the per-row (column, value) order and the row
+    The records are tokenized on the host by all its threads (spmm_csr_from_matrix_market); mirroring, the per-row (column, value) order and the row
     pointer are built in HBM by spmm_csr_from_coo_host. With return_device=True the resident
     DeviceCSR is returned alongside, so the multiply can reuse it without another upload.
     """
-    n_rows, n_cols, rows, cols, vals, symmetric = parse_matrix_market(filename)
-    dev = DeviceCSR.from_coo_host(n_rows, n_cols, rows, cols, vals, symmetric, device)
+    h = C.c_void_p()
+    _cabi.check(_cabi.lib().spmm_csr_from_matrix_market(device, filename.encode(), C.byref(h)))
+    dev = DeviceCSR(h.value)
     host = dev.download()
     if return_device:
         return host, dev

@@ -566,6 +566,75 @@ def test_tiled_mixed_sign_duplicates_and_strided(oracle, golden_multiply):
 
 
 # ---------------------------------------------------------------- multiply with the gather fused in (spmm_multiply_scatter_device)
+# ---------------------------------------------------------------- union kernel (spmm_union.cu): blocks of rows over union columns
+def union_multiply(m, B, k, R, tune, k_layout=None):
+    _cabi.tune("reset", 0)
+    for key, val in tune.items():
+        _cabi.tune(key, val)
+    try:
+        with spmm.DeviceCSR.from_host(m, 0, 0) as A:
+            info = A.build_union(R, k_layout or k)
+            assert info["rows_per_block"] == R and info["union_per_nnz"] <= 1.0 + 1e-12
+            dB = dev(B)
+            dC = torch.full((m.numRows, k), np.nan, dtype=torch.float64, device="cuda")
+            A.multiply(dB.data_ptr(), k, dC.data_ptr(), "union", torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            return dC.cpu().numpy()
+    finally:
+        _cabi.tune("reset", 0)
+
+
+@pytest.mark.parametrize("shape", ["fem_like", "short", "rect_wide", "rect_tall", "single_row", "all_empty"])
+@pytest.mark.parametrize("k", [2, 32, 40, 64, 96])
+@pytest.mark.parametrize("R,tune", [(2, {}), (2, {"tiled.ncw": 8, "tiled.depth": 10}), (2, {"union.slots": 8, "tiled.ncw": 4, "tiled.depth": 4}),
+                                    (4, {"tiled.ncw": 4, "tiled.depth": 4}), (2, {"tiled.kt": 16, "tiled.ncw": 8, "tiled.depth": 12})])
+def test_union_kernel_vs_oracle(oracle, shape, k, R, tune):
+    seed, n, nc, mean, long_row, empty_every = SHAPES[shape]
+    rp, ci, va = random_csr(seed, n, nc, mean, long_row=long_row, empty_every=empty_every, positive=True)
+    B = np.random.default_rng(seed + k).integers(1, 101, (nc, k)).astype(np.float64)
+    ref = oracle.spmm(rp, ci, va, B, k)
+    if va.size == 0:
+        pytest.skip("no layout for an empty matrix (the CSR kernels write the zeros)")
+    got = union_multiply(spmm.SparseMatrix(va, ci, rp, n, nc), B, k, R, tune)
+    assert_close_rel(got, ref, tol=REL_TOL)
+
+
+def test_union_kernel_long_rows_mixed_sign_and_refusals(oracle, golden_multiply):
+    # a 3,000-entry hub row is cut into segments folded in a fixed order; mixed signs and duplicate columns (golden "hub")
+    g = golden_multiply
+    rp, ci, va, B = g["hub_rowptr"], g["hub_colidx"], g["hub_vals"], g["hub_B"]
+    n, k = len(rp) - 1, B.shape[1]
+    m = spmm.SparseMatrix(va, ci, rp, n, n)
+    if k % 2 == 0:
+        assert_close_rel(union_multiply(m, B, k, 2, {}), g["hub_C_seq"], rp, ci, va, B)
+    B2 = np.random.default_rng(3).integers(1, 101, (n, 32)).astype(np.float64)
+    assert_close_rel(union_multiply(m, B2, 32, 2, {}), oracle.spmm(rp, ci, va, B2, 32), rp, ci, va, B2)
+    # rows that are not sorted by column: the layout is refused, the CSR kernels stay in charge
+    rp3, ci3, va3 = random_csr(11, 500, 500, 8, positive=True)
+    ci3 = ci3.copy()
+    lo, hi = rp3[5], rp3[6]
+    if hi - lo >= 2:
+        ci3[lo], ci3[hi - 1] = ci3[hi - 1], ci3[lo]
+        with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va3, ci3, rp3, 500, 500), 0, 0) as A:
+            if ci3[lo] != ci3[hi - 1]:
+                with pytest.raises(_cabi.SpmmError, match="not sorted"):
+                    A.build_union(2, 64)
+            B3 = dev(np.ones((500, 3)))
+            C3 = torch.empty((500, 4), dtype=torch.float64, device="cuda")
+            with pytest.raises(_cabi.SpmmError, match="union kernel requested"):
+                A.multiply(B3.data_ptr(), 4, C3.data_ptr(), "union", 0)
+
+
+def test_union_kernel_cop20k_shape_vs_oracle(oracle):
+    n, nc, r, c, v, sym = gen.cop20k_A_shaped()
+    with spmm.DeviceCSR.from_coo_host(n, nc, r, c, v, sym, device=0) as A0:
+        host = A0.download()
+    for k in (32, 64):
+        B = np.random.default_rng(k).integers(1, 101, (n, k)).astype(np.float64)
+        ref = oracle.spmm(host.rowPtr, host.colIndices, host.values, B, k)
+        assert_close_rel(union_multiply(host, B, k, 2, {}), ref, tol=REL_TOL)
+
+
 @pytest.mark.parametrize("kernel,k", [("rows", 5), ("rows", 64), ("merge", 32), ("tiled", 64), ("tiled", 24), ("auto", 16)])
 def test_scatter_multiply_same_device(oracle, kernel, k):
     """Every destination receives the same C (on one GPU the 'peers' are three buffers of the same device)."""

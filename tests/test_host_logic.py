@@ -64,6 +64,41 @@ def test_matrix_market_errors(tmp_path):
         spmm.parse_matrix_market(str(p2))
 
 
+def test_matrix_market_native_reader_token_stream(oracle, tmp_path):
+    """The body is a token stream (utils.cpp:128-136): records may span lines, '+' signs, CRLF, tabs; a file large
+    enough for several reader threads must give the oracle's records bit for bit."""
+    p = tmp_path / "odd.mtx"
+    p.write_bytes(b"%%MatrixMarket matrix coordinate real general\r\n% a comment\r\n3 4 4\r\n1 1\n2.5 2\t+3 -1e-3\r\n"
+                  b"3 4 0x1p-1 1\n\n 2 +7.25E+1\n trailing tokens are ignored 9 9 9\n")
+    nr, nc, rows, cols, vals, sym = spmm.parse_matrix_market(str(p))
+    assert (nr, nc, sym) == (3, 4, False)
+    assert rows.tolist() == [0, 1, 2, 0] and cols.tolist() == [0, 2, 3, 1]
+    assert vals.tolist() == [2.5, -1e-3, 0.5, 72.5]
+    rng = np.random.default_rng(5)
+    n, ne = 4000, 300_000
+    r, c = rng.integers(1, n + 1, ne), rng.integers(1, n + 1, ne)
+    v = rng.standard_normal(ne) * 10.0 ** rng.integers(-30, 30, ne)
+    big = tmp_path / "big.mtx"
+    with open(big, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real symmetric\n%c\n")
+        f.write(f"{n} {n} {ne}\n")
+        f.write("".join(f"{a} {b} {float(x)!r}" + ("\n" if i % 3 else " ") for i, (a, b, x) in enumerate(zip(r, c, v))))
+    nr, nc, rows, cols, vals, sym = spmm.parse_matrix_market(str(big))
+    onr, onc, orows, ocols, ovals, osym, _ = oracle.read_mtx_coo(str(big))
+    assert (nr, nc, sym) == (onr, onc, osym) == (n, n, True)
+    assert np.array_equal(rows, orows) and np.array_equal(cols, ocols)
+    assert np.array_equal(vals.view(np.uint64), ovals.view(np.uint64))
+    assert np.array_equal(vals, v)  # repr() round-trips every double
+    bad = tmp_path / "bad.mtx"
+    bad.write_text("%%MatrixMarket matrix coordinate real general\n2 2 2\n1 1 1.0\n2 x 3.0\n")
+    with pytest.raises(RuntimeError, match="Failed to read data"):
+        spmm.parse_matrix_market(str(bad))
+    oob = tmp_path / "oob.mtx"
+    oob.write_text("%%MatrixMarket matrix coordinate real general\n2 2 1\n3 1 1.0\n")
+    with pytest.raises(RuntimeError, match="outside the declared"):
+        spmm.parse_matrix_market(str(oob))
+
+
 def test_cop20k_shaped_generator_hits_the_published_shape():
     n, nc, r, c, v, sym = gen.cop20k_A_shaped()
     assert (n, nc, sym) == (121192, 121192, True)
