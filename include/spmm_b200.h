@@ -41,7 +41,8 @@ enum spmm_kernel
     SPMM_KERNEL_PACKED = 4,   /* warp-packed coalesced A stream (needs spmm_csr_build_packed) */
     SPMM_KERNEL_STAGED = 5,   /* CSR rows with the id/value stream staged through shared memory by cp.async (k multiple of 16, rows <= 2048 long) */
     SPMM_KERNEL_TILED = 6,    /* row tiles whose B rows are staged in shared memory by TMA (needs spmm_csr_build_tiles; even k) */
-    SPMM_KERNEL_UNION = 7     /* blocks of 2 or 4 rows over the union of their columns, B rows staged by TMA gather4 (needs spmm_csr_build_union; even k) */
+    SPMM_KERNEL_UNION = 7,    /* blocks of 2 or 4 rows over the union of their columns, B rows staged by TMA gather4 (needs spmm_csr_build_union; even k) */
+    SPMM_KERNEL_STREAM = 8    /* k = 1, 2, 4, 8: CSR arrays streamed in nnz order, rows reduced from shared memory; bit-identical to the reference's mul-then-add (spmm_stream.cu) */
 };
 
 const char *spmm_last_error(void);

@@ -13,9 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SPMM_B200_LIB") or os.path.join(HERE, "libspmm_b200.so")  # override: diagnostic builds only
 
 SPMM_OK, SPMM_ERR_INVALID, SPMM_ERR_CUDA, SPMM_ERR_NOMEM, SPMM_ERR_UNSUPPORTED = range(5)
-KERNEL_AUTO, KERNEL_ROWS, KERNEL_MERGE, KERNEL_ROWBLOCK, KERNEL_PACKED, KERNEL_STAGED, KERNEL_TILED, KERNEL_UNION = 0, 1, 2, 3, 4, 5, 6, 7
+KERNEL_AUTO, KERNEL_ROWS, KERNEL_MERGE, KERNEL_ROWBLOCK, KERNEL_PACKED, KERNEL_STAGED, KERNEL_TILED, KERNEL_UNION, KERNEL_STREAM = 0, 1, 2, 3, 4, 5, 6, 7, 8
 KERNELS = {"auto": KERNEL_AUTO, "rows": KERNEL_ROWS, "merge": KERNEL_MERGE, "rowblock": KERNEL_ROWBLOCK,
-           "packed": KERNEL_PACKED, "staged": KERNEL_STAGED, "tiled": KERNEL_TILED, "union": KERNEL_UNION}
+           "packed": KERNEL_PACKED, "staged": KERNEL_STAGED, "tiled": KERNEL_TILED, "union": KERNEL_UNION, "stream": KERNEL_STREAM}
 
 
 class SpmmError(RuntimeError):

@@ -248,6 +248,9 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "tiled.npw") t.tiled_npw = value;
     else if (k == "host.slabs") t.host_slabs = value;
     else if (k == "tiled.prefetch") t.tiled_prefetch = value;
+    else if (k == "stream") t.stream = value;
+    else if (k == "stream.tile") t.stream_tile = value;
+    else if (k == "stream.kmax") t.stream_auto_kmax = value;
     else if (k == "union.slots") t.union_slots = value;
     else if (k == "union.split") t.union_split = value;
     else if (k == "union.auto") t.union_auto = value;
@@ -435,7 +438,13 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
     SPMM_REQUIRE(d_B != nullptr || A->nnz == 0, "d_B is NULL");
     SPMM_CUDA(cudaSetDevice(A->device));
     cudaStream_t s = (cudaStream_t)stream;
-    SPMM_REQUIRE(kernel >= SPMM_KERNEL_AUTO && kernel <= SPMM_KERNEL_UNION, "unknown kernel id");
+    SPMM_REQUIRE(kernel >= SPMM_KERNEL_AUTO && kernel <= SPMM_KERNEL_STREAM, "unknown kernel id");
+    if (kernel == SPMM_KERNEL_STREAM)
+    {
+        SPMM_REQUIRE(stream_shape_ok(A, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count),
+                     "stream kernel: k must be 1, 2, 4 or 8 (B 16-byte aligned with an even leading dimension from k = 2), rows of at most 3072 / k non-zeros");
+        return launch_stream(A, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
+    }
     SPMM_REQUIRE(kernel != SPMM_KERNEL_TILED || A->tl_T != 0, "tiled kernel requested but spmm_csr_build_tiles was not called (or found no fitting tile shape)");
     if (kernel == SPMM_KERNEL_UNION)
     {
@@ -448,6 +457,10 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
     SPMM_REQUIRE(kernel != SPMM_KERNEL_ROWBLOCK || A->rb_R != 0, "row-block kernel requested but spmm_csr_build_rowblocks was not called");
     if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)
         return launch_merge(A, 0, A->n_rows, 0, A->nnz, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
+    // narrow fat vectors in nnz order: opt-in (spmm_tune_set("stream.kmax", 8)); measured no faster than the row kernels (profiles/r1_stream.md)
+    if (kernel == SPMM_KERNEL_AUTO && tuning().stream != 0 && k_count <= tuning().stream_auto_kmax &&
+        stream_shape_ok(A, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count))
+        return launch_stream(A, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
     // AUTO builds the tile layout the first time a multiply can use it (k >= 8, even, mid-sized matrix with
     // regular rows): one-off, a few milliseconds, 16 bytes per non-zero next to the CSR. spmm_tune_set("tiled", 0)
     // or an explicit spmm_csr_build_tiles(A, 0, 0) keeps the CSR kernels.

@@ -72,6 +72,9 @@ struct Tuning
     int tiled_prefetch = -1; // launch: tiles ahead whose blob is prefetched into L2 (-1 auto)
     int union_slots = 0;    // union layout: slots per item (4: 8-lane teams, 8: 4-lane teams)
     int union_split = 0;    // union layout: blocks with more union entries are cut into segments of about this length
+    int stream = -1;        // -1 auto, 0 AUTO never uses the stream kernel (k = 1, 2, 4, 8)
+    int stream_auto_kmax = 0; // AUTO takes the stream kernel up to this k (0: never — measured no faster than the row kernels, profiles/r1_stream.md)
+    int stream_tile = 0;    // stream kernel: non-zeros per tile (0 = 4096 / k)
     int union_debug = 0;    // diagnostics, wrong results by design (see spmm_union.cu)
     int union_auto = -1;    // -1 auto, 0 AUTO never builds / uses the union layout
 };
@@ -172,6 +175,9 @@ bool union_shape_ok(const spmm_csr_s *A, const double *d_B, long long ldb, const
 int launch_union(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int kc,
                  cudaStream_t stream, const struct ExtraDst *extra = nullptr);
 void free_union(spmm_csr_s *A);
+bool stream_shape_ok(const spmm_csr_s *A, const double *d_B, long long ldb, const double *d_C, long long ldc, int kc);
+int launch_stream(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int kc,
+                  cudaStream_t stream);
 bool staged_shape_ok(const spmm_csr_s *A, int w, int kl, int nv, int tiles, int kc);
 int launch_staged(const spmm_csr_s *A, int nv, int tiles, const double *d_B, long long ldb, double *d_C, long long ldc,
                   cudaStream_t stream);

@@ -566,6 +566,42 @@ def test_tiled_mixed_sign_duplicates_and_strided(oracle, golden_multiply):
 
 
 # ---------------------------------------------------------------- multiply with the gather fused in (spmm_multiply_scatter_device)
+# ---------------------------------------------------------------- stream kernel (spmm_stream.cu): k = 1, 2, 4, 8, bit-identical
+@pytest.mark.parametrize("shape", ["short", "fem_like", "rect_wide", "rect_tall", "single_row"])
+@pytest.mark.parametrize("k", [1, 2, 4, 8])
+@pytest.mark.parametrize("tune", [{}, {"stream.tile": 256}, {"stream.tile": 1024}])
+def test_stream_kernel_bit_identical_to_the_oracle(oracle, shape, k, tune):
+    seed, n, nc, mean, long_row, empty_every = SHAPES[shape]
+    rp, ci, va = random_csr(seed, n, nc, mean, long_row=long_row, empty_every=empty_every, positive=False)
+    B = np.random.default_rng(seed + k).standard_normal((nc, k))
+    ref = oracle.spmm(rp, ci, va, B, k)
+    got = gpu_multiply(spmm.SparseMatrix(va, ci, rp, n, nc), B, k, "stream", tune)
+    # product rounded, then added in ascending non-zero order: the reference's own arithmetic (-ffp-contract=off)
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+    auto = gpu_multiply(spmm.SparseMatrix(va, ci, rp, n, nc), B, k, "auto", {"stream.kmax": 8})  # AUTO opted in
+    assert np.array_equal(auto.view(np.uint64), ref.view(np.uint64))
+
+
+def test_stream_kernel_refusals_and_strided(oracle):
+    rp, ci, va = random_csr(3, 1200, 1200, 6, long_row=40000, empty_every=5, positive=True)
+    m = spmm.SparseMatrix(va, ci, rp, 1200, 1200)
+    B = np.ones((1200, 8))
+    with pytest.raises(_cabi.SpmmError, match="stream kernel"):
+        gpu_multiply(m, B, 8, "stream")  # a 40,000-entry row does not fit a tile
+    rp, ci, va = random_csr(4, 900, 900, 9, positive=True)
+    with pytest.raises(_cabi.SpmmError, match="stream kernel"):
+        gpu_multiply(spmm.SparseMatrix(va, ci, rp, 900, 900), np.ones((900, 3)), 3, "stream")
+    # a 4-column slab of a 12-column fat vector (the k-slab strategy)
+    B = np.random.default_rng(1).standard_normal((900, 12))
+    ref = oracle.spmm(rp, ci, va, np.ascontiguousarray(B[:, 4:8]), 4)
+    with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, 900, 900), 0, 0) as A:
+        dB, dC = dev(B), torch.full((900, 12), np.nan, dtype=torch.float64, device="cuda")
+        A.multiply_strided(dB.data_ptr(), 12, dC.data_ptr(), 12, 4, 4, "stream", torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = dC.cpu().numpy()
+    assert np.array_equal(got[:, 4:8], ref) and np.isnan(got[:, :4]).all() and np.isnan(got[:, 8:]).all()
+
+
 # ---------------------------------------------------------------- union kernel (spmm_union.cu): blocks of rows over union columns
 def union_multiply(m, B, k, R, tune, k_layout=None):
     _cabi.tune("reset", 0)
