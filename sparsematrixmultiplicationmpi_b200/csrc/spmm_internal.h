@@ -131,7 +131,7 @@ struct spmm_csr_s
     int *d_sptr = nullptr, *d_pcol = nullptr;
     double *d_pval = nullptr;
     // B-staged row tiles (spmm_tiled.cu), optional
-    int tl_T = 0, tl_BR = 0, tl_tiles = 0, tl_NS = 0, tl_POOL = 0, tl_max_recs = 0, tl_chunk = 0, tl_kt = 0, tl_depth = 0, tl_drains = 0, tl_ksplit = 0;
+    int tl_T = 0, tl_BR = 0, tl_tiles = 0, tl_NS = 0, tl_POOL = 0, tl_max_recs = 0, tl_max_blob = 0, tl_chunk = 0, tl_kt = 0, tl_depth = 0, tl_drains = 0, tl_ksplit = 0;
     long long tl_box_rows_loaded = 0, tl_single_rows = 0; // B rows staged per pass over the matrix
     bool tl_tried = false;                                // AUTO already attempted the lazy build
     bool tl_auto = false;                                 // the layout was built by AUTO (it may rebuild it for another k)

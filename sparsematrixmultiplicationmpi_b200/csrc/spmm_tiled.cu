@@ -86,6 +86,7 @@ enum
     ST_MAXPOOL = 2, // most singles in `depth` consecutive tiles
     ST_MAXLOAD = 3,
     ST_DRAINS = 4, // tiles that only fit once everything before them has finished
+    ST_MAXBLOB = 5, // largest blob in bytes
     ST_WORDS = 6
 };
 // 64-bit totals behind the status words
@@ -101,7 +102,8 @@ __host__ __device__ inline int units_cap(int T) { return (T + UW - 1) / UW + TB_
 // value stream (8 e) and the padded id stream (2 (e + 3T) at most) of every earlier tile.
 __host__ __device__ inline unsigned long long blob_offset(int t, long long e0, int hdr_bytes, int T)
 {
-    return (unsigned long long)t * (unsigned long long)(hdr_bytes + 8 * T + 48) + ((10ull * (unsigned long long)e0 + 15ull) & ~15ull);
+    // (+ 112 T: the rows of a unit start on distinct banks, at most 7 values and 7 id groups of padding per row)
+    return (unsigned long long)t * (unsigned long long)(hdr_bytes + 120 * T + 48) + ((10ull * (unsigned long long)e0 + 15ull) & ~15ull);
 }
 
 // Builder: one CTA per chunk, tiles replayed in order. DRY: only count.
@@ -128,7 +130,8 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
     __shared__ unsigned s_units[(TB_MAXT / UW + 1 + TB_SPLITCAP) * UW]; // word 0 of the unit entries
     __shared__ int s_uidx[(TB_MAXT / UW + 1 + TB_SPLITCAP) * UW];      // word 1: first slot of the row (segment) in the id stream
     __shared__ int s_ioff[TB_MAXT + 1];                                 // id-stream offset of each row (rows padded to 4 ids)
-    __shared__ int s_nload, s_nsplit, s_pool_ptr, s_drain;
+    __shared__ int s_voff[TB_MAXT + 1];                                 // value-stream offset of each row
+    __shared__ int s_nload, s_nsplit, s_pool_ptr, s_drain, s_nval, s_nid;
     __shared__ int s_recent[TB_DMAX]; // singles of the last `depth` tiles
 
     const int BR = 1 << p.lgBR;
@@ -275,14 +278,7 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
             if (s_rp[r + 1] - s_rp[r] >= TB_SPLIT)
                 atomicAdd(&s_nsplit, 1);
         __syncthreads();
-        // id stream: every row starts at a multiple of 4 ids, so a team reads 4 ids with one 8-byte load
-        for (int r = threadIdx.x; r <= nr; r += TB_THREADS)
-        {
-            int o = 0;
-            for (int q = 0; q < r; ++q)
-                o += (s_rp[q + 1] - s_rp[q] + 3) & ~3;
-            s_ioff[r] = o;
-        }
+        // (stream offsets of the rows are laid out unit by unit further down: s_voff / s_ioff)
         const int n_split = min(s_nsplit, TB_SPLITCAP);
         const int n_normal_units = (nr - n_split + UW - 1) / UW;
         const int n_units = n_normal_units + n_split;
@@ -310,8 +306,8 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
                 {
                     const int b = min(j * seg, len), e = min(b + seg, len);
                     s_units[(n_normal_units + srank) * UW + j] =
-                        (unsigned)(s_rp[r] + b) | ((unsigned)(e - b) << 13) | ((unsigned)r << 23) | 0x80000000u;
-                    s_uidx[(n_normal_units + srank) * UW + j] = s_ioff[r] + b;
+                        (unsigned)b | ((unsigned)(e - b) << 13) | ((unsigned)r << 23) | 0x80000000u; // begin: relative, placed below
+                    s_uidx[(n_normal_units + srank) * UW + j] = b;
                 }
             }
             else
@@ -330,9 +326,68 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
                 }
                 if (len > 0x3FF)
                     atomicOr(status + ST_FAIL, 8); // more than TB_SPLITCAP very long rows in one tile
-                s_units[rank] = (unsigned)s_rp[r] | ((unsigned)(len & 0x3FF) << 13) | ((unsigned)r << 23);
-                s_uidx[rank] = s_ioff[r];
+                s_units[rank] = ((unsigned)(len & 0x3FF) << 13) | ((unsigned)r << 23); // begin: placed below
+                s_uidx[rank] = 0;
             }
+        }
+        __syncthreads();
+        // ---- stream layout, unit by unit: the eight rows of a unit are walked in lockstep by the eight teams of a warp, one
+        // 8-byte value load (and one 8-byte load of four ids) per team and step. Eight unrelated addresses collide on the
+        // shared-memory banks (13 % of this kernel's load wavefronts, profiles/r1_tiled.md); rows whose streams start on
+        // eight different 8-byte bank pairs never do (tools/microbench/lds_patterns.cu), so each row is pushed to the next
+        // offset whose residue mod 16 no earlier row of its unit holds: at most 7 slots of padding per row and stream.
+        if (threadIdx.x == 0)
+        {
+            int pos = 0, ipos = 0; // doubles / groups of four ids
+            for (int u = 0; u < n_units; ++u)
+            {
+                if (u >= n_normal_units)
+                {
+                    // split row: its eight segments lie one after the other
+                    const unsigned e0w = s_units[u * UW];
+                    const int r = (int)((e0w >> 23) & 0xFF), len = s_rp[r + 1] - s_rp[r];
+                    for (int j = 0; j < UW; ++j)
+                    {
+                        const unsigned w = s_units[u * UW + j];
+                        const int b = (int)(w & 0x1FFF);
+                        s_units[u * UW + j] = (w & ~0x1FFFu) | (unsigned)(pos + b);
+                        s_uidx[u * UW + j] = ipos * 4 + b;
+                    }
+                    s_voff[r] = pos;
+                    s_ioff[r] = ipos * 4;
+                    pos += len;
+                    ipos += (len + 3) >> 2;
+                    continue;
+                }
+                unsigned used_v = 0, used_i = 0;
+                for (int j = 0; j < UW; ++j)
+                {
+                    const unsigned w = s_units[u * UW + j];
+                    const int r = (int)((w >> 23) & 0xFF);
+                    if (r == (int)UE_PAD_ROW)
+                        continue;
+                    const int len = s_rp[r + 1] - s_rp[r];
+                    if (len > 0)
+                    {
+                        while ((used_v >> (pos & 15)) & 1u)
+                            ++pos;
+                        used_v |= 1u << (pos & 15);
+                        while ((used_i >> (ipos & 15)) & 1u)
+                            ++ipos;
+                        used_i |= 1u << (ipos & 15);
+                    }
+                    s_units[u * UW + j] = (w & ~0x1FFFu) | (unsigned)pos;
+                    s_uidx[u * UW + j] = ipos * 4;
+                    s_voff[r] = pos;
+                    s_ioff[r] = ipos * 4;
+                    pos += len;
+                    ipos += (len + 3) >> 2;
+                }
+            }
+            s_nval = pos;
+            s_nid = ipos * 4;
+            if (pos > 0x1FFF)
+                atomicOr(status + ST_FAIL, 16); // the begin field of a unit entry holds 13 bits
         }
         __syncthreads();
 
@@ -398,6 +453,8 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
             s_pool_ptr = (pool_start + ns_total) % p.POOL;
             my_singles += (unsigned long long)ns_real;
             atomicMax(status + ST_MAXREC, n);
+            atomicMax(status + ST_MAXBLOB,
+                      p.hdr_bytes + (int)(((unsigned)s_nval * 8u + 15u) & ~15u) + (int)(((unsigned)s_nid * 2u + 15u) & ~15u));
             atomicMax(status + ST_MAXPOOL, recent);
             atomicMax(status + ST_MAXLOAD, s_nload);
         }
@@ -405,8 +462,8 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
             continue;
 
         // blob = header | unit table | values (8 bytes per non-zero) | slab-row ids (2 bytes, rows padded to 4 ids)
-        const int n_ids = s_ioff[nr];
-        const unsigned val_bytes = ((unsigned)n * 8u + 15u) & ~15u, id_bytes = ((unsigned)n_ids * 2u + 15u) & ~15u;
+        const int n_ids = s_nid;
+        const unsigned val_bytes = ((unsigned)s_nval * 8u + 15u) & ~15u, id_bytes = ((unsigned)n_ids * 2u + 15u) & ~15u;
         const unsigned off16 = (unsigned)(blob_offset(t, e0, p.hdr_bytes, p.T) >> 4);
         unsigned char *mine = blob + ((unsigned long long)off16 << 4);
         if (threadIdx.x == 0)
@@ -452,7 +509,7 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
                 else
                     hi = mid;
             }
-            val_out[j] = vals[e0 + j];
+            val_out[s_voff[lo] + (j - s_rp[lo])] = vals[e0 + j];
             id_out[s_ioff[lo] + (j - s_rp[lo])] = (unsigned short)sr;
         }
     }
@@ -802,7 +859,51 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
             for (int i = 0; i < NL; ++i)
                 acc[i] = make_double2(0.0, 0.0);
             const unsigned vbase = vals_s + begin * 8, ibase = ids_s + e.y * 2;
-            for (int i = 0; i < maxlen; i += U)
+            int i = 0;
+            {
+                // Fast path: the steps every team of the unit still has (rows of a unit are of similar length) run without
+                // predicates, zero fills and per-load address arithmetic — the predicated loop below issues ~95 instructions
+                // per 4 steps for 29 loads and FMAs, and the kernel's issue slots were 59 % busy (profiles/r1_tiled.md).
+                // The slab address of accumulator 0 has bit 6 = tq (the slab is 1024-byte aligned, a slab row is a multiple of
+                // 128 bytes, l*16 < 64): accumulator x^1 is the same address with bit 6 flipped, x+2 lies 128 bytes further.
+                const int fast_end = __reduce_min_sync(0xFFFFFFFFu, len) & ~(U - 1);
+                const unsigned b0 = s_slab + colo[0] * 8;
+                for (; i < fast_end; i += U)
+                {
+                    double v[U];
+                    unsigned id[U];
+#pragma unroll
+                    for (int g = 0; g < U; g += 4)
+                    {
+                        const uint2 four = lds64u(ibase + (i + g) * 2);
+                        id[g] = four.x & 0xFFFFu;
+                        id[g + 1] = four.x >> 16;
+                        id[g + 2] = four.y & 0xFFFFu;
+                        id[g + 3] = four.y >> 16;
+                    }
+#pragma unroll
+                    for (int q = 0; q < U; ++q)
+                        v[q] = lds64d(vbase + (i + q) * 8);
+                    double2 b[U][NL];
+#pragma unroll
+                    for (int q = 0; q < U; ++q)
+                    {
+                        const unsigned a0 = b0 + id[q] * (KT * 8), a1 = a0 ^ 64u;
+#pragma unroll
+                        for (int x = 0; x < NL; ++x)
+                            b[q][x] = lds128d(((x & 1) ? a1 : a0) + (x >> 1) * 128);
+                    }
+#pragma unroll
+                    for (int q = 0; q < U; ++q)
+#pragma unroll
+                        for (int x = 0; x < NL; ++x)
+                        {
+                            acc[x].x = fma(v[q], b[q][x].x, acc[x].x);
+                            acc[x].y = fma(v[q], b[q][x].y, acc[x].y);
+                        }
+                }
+            }
+            for (; i < maxlen; i += U)
             {
                 static_assert(U % 4 == 0, "ids are read four at a time");
                 double v[U];
@@ -967,10 +1068,11 @@ struct TiledSmem
     size_t blob_stride, slab_off, slab_bytes, total;
 };
 
-TiledSmem tiled_smem(int kt, int depth, int T, int BR, int NS, int POOL, int max_recs)
+TiledSmem tiled_smem(int kt, int depth, int T, int BR, int NS, int POOL, int max_blob)
 {
     TiledSmem m;
-    m.blob_stride = (hdr_bytes_of(T) + 10ull * max_recs + 6ull * T + 32 + 127) & ~127ull; // values + ids (rows padded to 4)
+    (void)T;
+    m.blob_stride = ((size_t)max_blob + 32 + 127) & ~127ull; // header + unit table + values + ids of the largest tile
     m.slab_off = (BLOB_OFF + (size_t)depth * m.blob_stride + 1023) & ~1023ull;
     m.slab_bytes = ((size_t)NS * BR + (size_t)POOL) * kt * 8;
     m.total = m.slab_off + m.slab_bytes + 1024; // + slack: the kernel aligns its base to 1024
@@ -982,7 +1084,7 @@ int launch_tiled_t(const spmm_csr_s *A, const double *d_B, long long ldb, double
                    cudaStream_t stream, const ExtraDst &extra)
 {
     auto kern = spmm_tiled_kernel<KT, NCW, U, NPW>;
-    const TiledSmem m = tiled_smem(KT, A->tl_depth, A->tl_T, A->tl_BR, A->tl_NS, A->tl_POOL, A->tl_max_recs);
+    const TiledSmem m = tiled_smem(KT, A->tl_depth, A->tl_T, A->tl_BR, A->tl_NS, A->tl_POOL, A->tl_max_blob);
     if (m.total > (size_t)SMEM_CAP)
     {
         set_error("tiled kernel: the tile layout was built for a narrower k-tile; it does not fit in shared memory");
@@ -1144,7 +1246,7 @@ void free_tiles(spmm_csr_s *A)
     A->d_tdesc = nullptr;
     A->d_tloads = nullptr;
     A->d_tsingles = nullptr;
-    A->tl_T = A->tl_BR = A->tl_tiles = A->tl_NS = A->tl_POOL = A->tl_max_recs = A->tl_chunk = A->tl_kt = A->tl_depth = A->tl_ksplit = 0;
+    A->tl_T = A->tl_BR = A->tl_tiles = A->tl_NS = A->tl_POOL = A->tl_max_recs = A->tl_max_blob = A->tl_chunk = A->tl_kt = A->tl_depth = A->tl_ksplit = 0;
     A->tl_box_rows_loaded = A->tl_single_rows = 0;
 }
 
@@ -1237,7 +1339,7 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
         int pool = tn.tiled_pool > 0 ? tn.tiled_pool : (int)(1.5 * depth * avg) + 32;
         pool = std::min(std::max(pool, 32), std::max(32, res.status[ST_MAXPOOL] + 8));
         pool = (pool + 7) & ~7;
-        const TiledSmem fixed = tiled_smem(kt, depth, T, BR, 0, pool, res.status[ST_MAXREC]);
+        const TiledSmem fixed = tiled_smem(kt, depth, T, BR, 0, pool, res.status[ST_MAXBLOB]);
         if (fixed.total + 8ull * BR * kt * 8 > (size_t)SMEM_CAP)
             continue;
         p.NS = (int)std::min<size_t>(TB_NSMAX, ((size_t)SMEM_CAP - fixed.total) / ((size_t)BR * kt * 8));
@@ -1301,6 +1403,7 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
     A->tl_NS = p.NS;
     A->tl_POOL = p.POOL;
     A->tl_max_recs = res.status[ST_MAXREC];
+    A->tl_max_blob = res.status[ST_MAXBLOB];
     A->tl_chunk = p.tiles_per_chunk;
     A->tl_kt = kt;
     A->tl_depth = depth;
