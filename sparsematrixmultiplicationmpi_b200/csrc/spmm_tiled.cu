@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
     __shared__ int s_ioff[TB_MAXT + 1];                                 // id-stream offset of each row (rows padded to 4 ids)
     __shared__ int s_voff[TB_MAXT + 1];                                 // value-stream offset of each row
     __shared__ int s_nload, s_nsplit, s_pool_ptr, s_drain, s_nval, s_nid;
+    __shared__ int s_usz_v[TB_MAXT / UW + 1 + TB_SPLITCAP], s_usz_i[TB_MAXT / UW + 1 + TB_SPLITCAP]; // unit sizes, then unit starts
     __shared__ int s_recent[TB_DMAX]; // singles of the last `depth` tiles
 
     const int BR = 1 << p.lgBR;
@@ -336,29 +337,24 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
         // shared-memory banks (13 % of this kernel's load wavefronts, profiles/r1_tiled.md); rows whose streams start on
         // eight different 8-byte bank pairs never do (tools/microbench/lds_patterns.cu), so each row is pushed to the next
         // offset whose residue mod 16 no earlier row of its unit holds: at most 7 slots of padding per row and stream.
-        if (threadIdx.x == 0)
+        // (The pushes of a unit depend on the lengths of its rows only, not on where the unit starts — a different start
+        // rotates all residues alike — so every unit is laid out by its own thread from offset 0 and the unit sizes are
+        // scanned afterwards.)
+        if (threadIdx.x < n_units)
         {
-            int pos = 0, ipos = 0; // doubles / groups of four ids
-            for (int u = 0; u < n_units; ++u)
+            const int u = threadIdx.x;
+            int pos = 0, ipos = 0; // doubles / groups of four ids, relative to the start of the unit
+            if (u >= n_normal_units)
             {
-                if (u >= n_normal_units)
-                {
-                    // split row: its eight segments lie one after the other
-                    const unsigned e0w = s_units[u * UW];
-                    const int r = (int)((e0w >> 23) & 0xFF), len = s_rp[r + 1] - s_rp[r];
-                    for (int j = 0; j < UW; ++j)
-                    {
-                        const unsigned w = s_units[u * UW + j];
-                        const int b = (int)(w & 0x1FFF);
-                        s_units[u * UW + j] = (w & ~0x1FFFu) | (unsigned)(pos + b);
-                        s_uidx[u * UW + j] = ipos * 4 + b;
-                    }
-                    s_voff[r] = pos;
-                    s_ioff[r] = ipos * 4;
-                    pos += len;
-                    ipos += (len + 3) >> 2;
-                    continue;
-                }
+                // split row: its eight segments lie one after the other
+                const int r = (int)((s_units[u * UW] >> 23) & 0xFF), len = s_rp[r + 1] - s_rp[r];
+                pos = len;
+                ipos = (len + 3) >> 2;
+                s_voff[r] = 0;
+                s_ioff[r] = 0;
+            }
+            else
+            {
                 unsigned used_v = 0, used_i = 0;
                 for (int j = 0; j < UW; ++j)
                 {
@@ -384,10 +380,44 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
                     ipos += (len + 3) >> 2;
                 }
             }
+            s_usz_v[u] = pos;
+            s_usz_i[u] = ipos;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            int pos = 0, ipos = 0;
+            for (int u = 0; u < n_units; ++u)
+            {
+                const int sv = s_usz_v[u], si = s_usz_i[u];
+                s_usz_v[u] = pos;
+                s_usz_i[u] = ipos;
+                pos += sv;
+                ipos += si;
+            }
             s_nval = pos;
             s_nid = ipos * 4;
             if (pos > 0x1FFF)
                 atomicOr(status + ST_FAIL, 16); // the begin field of a unit entry holds 13 bits
+        }
+        __syncthreads();
+        if (threadIdx.x < n_units)
+        {
+            const int u = threadIdx.x, bv = s_usz_v[u], bi = s_usz_i[u] * 4;
+            for (int j = 0; j < UW; ++j)
+            {
+                const unsigned w = s_units[u * UW + j];
+                const int r = (int)((w >> 23) & 0xFF);
+                if (r == (int)UE_PAD_ROW)
+                    continue;
+                s_units[u * UW + j] = (w & ~0x1FFFu) | (unsigned)((int)(w & 0x1FFF) + bv);
+                s_uidx[u * UW + j] += bi;
+                if (u < n_normal_units || j == 0)
+                {
+                    s_voff[r] += bv;
+                    s_ioff[r] += bi;
+                }
+            }
         }
         __syncthreads();
 
