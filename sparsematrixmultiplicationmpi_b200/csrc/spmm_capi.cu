@@ -248,6 +248,8 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "tiled.npw") t.tiled_npw = value;
     else if (k == "host.slabs") t.host_slabs = value;
     else if (k == "tiled.prefetch") t.tiled_prefetch = value;
+    else if (k == "tiled.group") t.tiled_group = value;
+    else if (k == "tiled.stride") t.tiled_stride = value;
     else if (k == "stream") t.stream = value;
     else if (k == "stream.tile") t.stream_tile = value;
     else if (k == "stream.kmax") t.stream_auto_kmax = value;

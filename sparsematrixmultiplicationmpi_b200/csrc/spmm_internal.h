@@ -69,6 +69,8 @@ struct Tuning
     int tiled_ksplit = 0;   // build: CTAs that share one chunk, each taking a group of k-tiles (0/1 none)
     int tiled_npw = 0;      // launch: producer warps (4, 8)
     int host_slabs = 0;     // host-buffer multiply: k-slabs in the PCIe pipeline (0 auto, 1 none)
+    int tiled_group = 0;    // build: tiles one far-band apart walked in turn, this many bands per group (0 auto = 2, 1 off)
+    int tiled_stride = 0;   // build: far-band distance in rows (0 = detect from the matrix)
     int tiled_prefetch = -1; // launch: tiles ahead whose blob is prefetched into L2 (-1 auto)
     int union_slots = 0;    // union layout: slots per item (4: 8-lane teams, 8: 4-lane teams)
     int union_split = 0;    // union layout: blocks with more union entries are cut into segments of about this length
@@ -138,6 +140,8 @@ struct spmm_csr_s
     unsigned char *d_tblob = nullptr;
     void *d_tdesc = nullptr, *d_tloads = nullptr;
     int *d_tsingles = nullptr;
+    int *d_torder = nullptr;          // walking order of the tiles (nullptr: as they lie)
+    int tl_stride = 0, tl_group = 0;  // detected far-band distance in rows, planes interleaved per super-group
     // row blocks over union columns with a gather4-staged window (spmm_union.cu), optional
     spmm::UnionDev *un = nullptr;
     bool un_tried = false; // AUTO already attempted the lazy build

@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
                                                                  unsigned char *__restrict__ blob,
                                                                  TileDesc *__restrict__ tdesc, int2 *__restrict__ loads,
                                                                  int *__restrict__ singles, int *__restrict__ status,
-                                                                 unsigned long long *__restrict__ totals)
+                                                                 unsigned long long *__restrict__ totals,
+                                                                 const int *__restrict__ order)
 {
     using Sort = cub::BlockRadixSort<int, TB_THREADS, TB_ITEMS>;
     using Scan = cub::BlockScan<int, TB_THREADS>;
@@ -150,9 +151,12 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
     unsigned long long my_loads = 0, my_singles = 0; // thread 0 only
     int last_fence = 0; // last tile (of the chunk) that waits for everything before it; tile 0 does by construction
 
-    for (int t = t_begin; t < t_end; ++t)
+    // `pos` is a tile's place in the walking order (what the kernel iterates and what tdesc / loads / singles are indexed
+    // by); `t` is the tile itself (its rows, its blob). order == nullptr: tiles are walked as they lie.
+    for (int pos = t_begin; pos < t_end; ++pos)
     {
-        const int lt = t - t_begin;
+        const int t = order ? order[pos] : pos;
+        const int lt = pos - t_begin;
         const int r0 = t * p.T, r1 = min(p.n_rows, r0 + p.T);
         const int nr = r1 - r0;
         const int e0 = rowptr[r0], e1 = rowptr[r1];
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
                 s_slot_stamp[best] = lt;
                 s_uslot[u] = best;
                 if (!DRY)
-                    loads[(size_t)t * p.NS + nl] = make_int2(s_ubox[u] << p.lgBR, best);
+                    loads[(size_t)pos * p.NS + nl] = make_int2(s_ubox[u] << p.lgBR, best);
                 ++nl;
             }
             s_nload = nl;
@@ -503,8 +507,8 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
             d.bytes = (unsigned)p.hdr_bytes + val_bytes + id_bytes;
             d.counts = (unsigned)s_nload | ((unsigned)ns_total << 16) | ((unsigned)fence << 29);
             d.pool_start = pool_start;
-            tdesc[t] = d;
-            *reinterpret_cast<int4 *>(mine) = make_int4(n, n_units, nr, (int)((unsigned)p.hdr_bytes + val_bytes));
+            tdesc[pos] = d;
+            *reinterpret_cast<int4 *>(mine) = make_int4(n, n_units, t, (int)((unsigned)p.hdr_bytes + val_bytes)); // .z: the tile (its C rows)
         }
         uint2 *units_out = reinterpret_cast<uint2 *>(mine + 16);
         for (int i = threadIdx.x; i < (p.hdr_bytes - 16) / 8; i += TB_THREADS)
@@ -514,7 +518,7 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
         for (int i = threadIdx.x; i < (int)(id_bytes / 2); i += TB_THREADS)
             id_out[i] = 0; // padding ids are never used for arithmetic; keep them inside the slab
         if (threadIdx.x < ns_total - ns_real)
-            singles[(size_t)t * p.POOL + ns_real + threadIdx.x] = 0; // padding rows: any valid B row
+            singles[(size_t)pos * p.POOL + ns_real + threadIdx.x] = 0; // padding rows: any valid B row
         __syncthreads(); // id padding written before the real ids
 #pragma unroll
         for (int i = 0; i < TB_ITEMS; ++i)
@@ -525,7 +529,7 @@ __global__ void __launch_bounds__(TB_THREADS) tile_build_kernel(const int *__res
             int sr = srow[i];
             if (sr < 0)
             {
-                singles[(size_t)t * p.POOL + spos] = col[i];
+                singles[(size_t)pos * p.POOL + spos] = col[i];
                 sr = p.NS * BR + (pool_start + spos) % p.POOL;
                 ++spos;
             }
@@ -875,7 +879,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
         const int n_units = hdr.y;
         const unsigned units = blob + 16;
         const unsigned vals_s = blob + a.hdr_bytes, ids_s = blob + (unsigned)hdr.w;
-        double *__restrict__ Ck = a.C + (long long)cur.t * a.T * a.ldc + k0;
+        double *__restrict__ Ck = a.C + (long long)hdr.z * a.T * a.ldc + k0; // hdr.z: the tile at this place of the walking order
 
         // units round-robin over the warps, rotated by the item so the remainder moves around
         for (int u = (warp + w) % NCW; !T_NO_COMPUTE && u < n_units; u += NCW)
@@ -1240,12 +1244,12 @@ int build_tiles_once(spmm_csr_s *A, const BuildParams &p, bool dry, BuildResult 
     {
         if (dry)
             tile_build_kernel<true><<<n_chunks, TB_THREADS>>>(A->d_rowptr, A->d_colidx, A->d_vals, p, nullptr, nullptr,
-                                                              nullptr, nullptr, d_status, d_total);
+                                                              nullptr, nullptr, d_status, d_total, A->d_torder);
         else
             tile_build_kernel<false><<<n_chunks, TB_THREADS>>>(A->d_rowptr, A->d_colidx, A->d_vals, p, A->d_tblob,
                                                                reinterpret_cast<TileDesc *>(A->d_tdesc),
                                                                reinterpret_cast<int2 *>(A->d_tloads), A->d_tsingles,
-                                                               d_status, d_total);
+                                                               d_status, d_total, A->d_torder);
         e = cudaGetLastError();
     }
     unsigned char h[sizeof(int) * ST_WORDS + sizeof(unsigned long long) * TOT_WORDS];
@@ -1257,11 +1261,79 @@ int build_tiles_once(spmm_csr_s *A, const BuildParams &p, bool dry, BuildResult 
     memcpy(res->totals, h + sizeof(int) * ST_WORDS, sizeof(unsigned long long) * TOT_WORDS);
     if (getenv("SPMM_TILED_DEBUG"))
         fprintf(stderr,
-                "[tiled build] %s T=%d BR=%d NS=%d POOL=%d depth=%d thr=%d chunk=%d: fail=%d max_recs=%d max_pool=%d max_loads=%d "
+                "[tiled build] %s T=%d BR=%d NS=%d POOL=%d depth=%d thr=%d chunk=%d band=%d group=%d: fail=%d max_recs=%d max_pool=%d max_loads=%d "
                 "drains=%d loads=%llu singles=%llu\n",
-                dry ? "dry" : "final", p.T, 1 << p.lgBR, p.NS, p.POOL, p.depth, p.thr, p.tiles_per_chunk, res->status[ST_FAIL],
+                dry ? "dry" : "final", p.T, 1 << p.lgBR, p.NS, p.POOL, p.depth, p.thr, p.tiles_per_chunk, A->tl_stride, A->tl_group, res->status[ST_FAIL],
                 res->status[ST_MAXREC], res->status[ST_MAXPOOL], res->status[ST_MAXLOAD], res->status[ST_DRAINS], res->totals[TOT_LOADS],
                 res->totals[TOT_SINGLES]);
+    return SPMM_OK;
+}
+} // namespace
+
+namespace
+{
+// Distance (in rows) of the matrix's dominant far band: FEM-like matrices on a 3-D grid couple row r with rows r +- P
+// (the next grid plane). 0 when no band far from the diagonal holds a sizeable share of the non-zeros.
+int detect_far_band(const spmm_csr_s *A, int *stride_rows)
+{
+    *stride_rows = 0;
+    if (A->n_rows < 4096 || A->nnz == 0)
+        return SPMM_OK;
+    std::vector<int> rp((size_t)A->n_rows + 1), ci((size_t)A->nnz);
+    SPMM_CUDA(cudaMemcpy(rp.data(), A->d_rowptr, sizeof(int) * rp.size(), cudaMemcpyDeviceToHost));
+    SPMM_CUDA(cudaMemcpy(ci.data(), A->d_colidx, sizeof(int) * ci.size(), cudaMemcpyDeviceToHost));
+    constexpr int BIN = 64, NEAR = 256;
+    std::vector<long long> cnt((size_t)A->n_cols / BIN + 2, 0), sum((size_t)A->n_cols / BIN + 2, 0);
+    for (int r = 0; r < A->n_rows; ++r)
+        for (int j = rp[r]; j < rp[r + 1]; ++j)
+        {
+            const int d = ci[j] - r;
+            if (d >= NEAR)
+            {
+                ++cnt[d / BIN];
+                sum[d / BIN] += d;
+            }
+        }
+    size_t m = 0;
+    for (size_t i = 1; i < cnt.size(); ++i)
+        if (cnt[i] > cnt[m])
+            m = i;
+    long long c = 0, sm = 0;
+    for (size_t i = m >= 2 ? m - 2 : 0; i <= m + 2 && i < cnt.size(); ++i)
+    {
+        c += cnt[i];
+        sm += sum[i];
+    }
+    if (c * 12 >= A->nnz && c > 0) // the band holds at least 1/12 of all non-zeros (a third of the upper triangle of a 27-point stencil)
+        *stride_rows = (int)(sm / c);
+    return SPMM_OK;
+}
+
+// Walking order for tiles of T rows: tiles one far band (S tiles) apart are visited in turn, G bands per group, so the B rows
+// a tile stages for the next plane are still in the window when that plane's tile comes (1 + 2/G stagings per B row
+// instead of 3). nullptr order = as they lie.
+int set_tile_order(spmm_csr_s *A, int n_tiles, int T, int stride_rows, int G)
+{
+    cudaFree(A->d_torder);
+    A->d_torder = nullptr;
+    A->tl_stride = A->tl_group = 0;
+    const int S = T > 0 ? (stride_rows + T / 2) / T : 0;
+    if (stride_rows <= 0 || G <= 1 || S < 2 || n_tiles < 2 * S)
+        return SPMM_OK;
+    std::vector<int> order;
+    order.reserve((size_t)n_tiles);
+    for (int g0 = 0; g0 < n_tiles; g0 += G * S)
+        for (int i = 0; i < S; ++i)
+            for (int q = 0; q < G; ++q)
+            {
+                const int t = g0 + q * S + i;
+                if (t < n_tiles)
+                    order.push_back(t);
+            }
+    SPMM_CUDA(cudaMalloc(&A->d_torder, sizeof(int) * (size_t)n_tiles));
+    SPMM_CUDA(cudaMemcpy(A->d_torder, order.data(), sizeof(int) * (size_t)n_tiles, cudaMemcpyHostToDevice));
+    A->tl_stride = stride_rows;
+    A->tl_group = G;
     return SPMM_OK;
 }
 } // namespace
@@ -1272,6 +1344,9 @@ void free_tiles(spmm_csr_s *A)
     cudaFree(A->d_tdesc);
     cudaFree(A->d_tloads);
     cudaFree(A->d_tsingles);
+    cudaFree(A->d_torder);
+    A->d_torder = nullptr;
+    A->tl_stride = A->tl_group = 0;
     A->d_tblob = nullptr;
     A->d_tdesc = nullptr;
     A->d_tloads = nullptr;
@@ -1338,6 +1413,14 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
     p.thr = tn.tiled_thr > 0 ? tn.tiled_thr : std::max(2, 3 * BR / 8);
     p.depth = depth;
     BuildResult res;
+    int far_band = tn.tiled_stride;
+    const int group = tn.tiled_group > 0 ? tn.tiled_group : 2; // measured on cfg2: 2 stages a third fewer B rows at no cost; 3+ overflow the window (drains)
+    if (far_band == 0 && group > 1)
+    {
+        const int rc = detect_far_band(A, &far_band);
+        if (rc)
+            return rc;
+    }
     const int auto_cand[] = {96, 80, 72, 64, 48, 32, 16};
     int chosen = 0;
     BuildParams best = {};
@@ -1355,10 +1438,13 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
         const int n_chunks_want = std::max(1, sms * per_sm / ksplit); // ksplit CTAs share a chunk (one k-tile group each)
         p.tiles_per_chunk =
             tn.tiled_chunk > 0 ? tn.tiled_chunk : std::max(1, (p.n_tiles + n_chunks_want - 1) / n_chunks_want);
+        int rc = set_tile_order(A, p.n_tiles, T, far_band, group);
+        if (rc)
+            return rc;
         // dry run with the largest window: record maximum and singles of this tile height
         p.NS = TB_NSMAX;
         p.POOL = 1 << 20;
-        int rc = build_tiles_once(A, p, true, &res);
+        rc = build_tiles_once(A, p, true, &res);
         if (rc)
             return rc;
         if (res.status[ST_FAIL])
@@ -1411,6 +1497,11 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
             return SPMM_ERR_UNSUPPORTED;
         }
         return SPMM_OK; // no tile shape fits: the CSR kernels stay in charge
+    }
+    {
+        const int orc = set_tile_order(A, p.n_tiles, p.T, far_band, group); // the order of the chosen tile height
+        if (orc)
+            return orc;
     }
     const unsigned long long blob_bytes = blob_offset(p.n_tiles, A->nnz, p.hdr_bytes, p.T) + 64;
     SPMM_REQUIRE((blob_bytes >> 4) < (1ull << 32), "matrix too large for the tile layout");

@@ -514,6 +514,30 @@ def test_tiled_shapes_and_teams(oracle, T, BR, tune):
     assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
 
 
+@pytest.mark.parametrize("group", [1, 2, 3, 4, 6])
+@pytest.mark.parametrize("k", [16, 64])
+def test_tiled_walking_order_of_far_band_matrices(oracle, group, k):
+    """Tiles one far band apart are walked in turn (spmm_tiled.cu: set_tile_order): any group size must give the same C."""
+    n, nc, r, c, v, sym = gen.cop20k_A_shaped(n=30_000, nnz=600_000, nx=20, ny=25, seed=3)
+    with spmm.DeviceCSR.from_coo_host(n, nc, r, c, v, sym, device=0) as A0:
+        host = A0.download()
+    B = np.random.default_rng(k).integers(1, 101, (n, k)).astype(np.float64)
+    ref = oracle.spmm(host.rowPtr, host.colIndices, host.values, B, k)
+    _cabi.tune("reset", 0)
+    _cabi.tune("tiled.group", group)
+    try:
+        with spmm.DeviceCSR.from_host(host, 0, 0) as A:
+            A.build_tiles(32, 16, k)
+            dB = dev(B)
+            dC = torch.full((n, k), np.nan, dtype=torch.float64, device="cuda")
+            A.multiply(dB.data_ptr(), k, dC.data_ptr(), "tiled", torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            got = dC.cpu().numpy()
+    finally:
+        _cabi.tune("reset", 0)
+    assert_close_rel(got, ref, tol=REL_TOL)
+
+
 def test_tiled_auto_dispatch_and_refusals(oracle):
     # scattered columns: no tile shape fits -> build succeeds with no layout, AUTO keeps the CSR kernels
     rp, ci, va = random_csr(41, 4000, 400000, 30, positive=True)

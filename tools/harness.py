@@ -188,8 +188,9 @@ def cfg2(args, emit, dev):
                 ns_cap = f[5] if len(f) > 5 else 0
                 pool = f[6] if len(f) > 6 else 0
                 ksplit = f[7] if len(f) > 7 else 0
+                group = f[8] if len(f) > 8 else 0
 
-                def make(s, T=T, BR=BR, kt=kt, thr=thr, depth=depth, ns_cap=ns_cap, pool=pool, ksplit=ksplit):
+                def make(s, T=T, BR=BR, kt=kt, thr=thr, depth=depth, ns_cap=ns_cap, pool=pool, ksplit=ksplit, group=group):
                     A = spmm.DeviceCSR.from_host(host, dev.index, 0)
                     _cabi.tune("reset", 0)
                     _cabi.tune("tiled.kt", kt)
@@ -198,6 +199,7 @@ def cfg2(args, emit, dev):
                     _cabi.tune("tiled.ns", ns_cap)
                     _cabi.tune("tiled.pool", pool)
                     _cabi.tune("tiled.ksplit", ksplit)
+                    _cabi.tune("tiled.group", group)
                     try:
                         A.build_tiles(T, BR)
                     finally:
