@@ -247,6 +247,7 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "tiled.ksplit") t.tiled_ksplit = value;
     else if (k == "tiled.npw") t.tiled_npw = value;
     else if (k == "host.slabs") t.host_slabs = value;
+    else if (k == "host.pipe") t.host_pipe = value;
     else if (k == "tiled.prefetch") t.tiled_prefetch = value;
     else if (k == "tiled.group") t.tiled_group = value;
     else if (k == "tiled.stride") t.tiled_stride = value;
@@ -716,7 +717,7 @@ static int host_call_slabs(spmm_csr_t A, const double *B, int k, double *C, int 
     {
         SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_up, cudaStreamNonBlocking));
         SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_down, cudaStreamNonBlocking));
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 32; ++i)
         {
             SPMM_CUDA(cudaEventCreateWithFlags(&A->ev_up[i], cudaEventDisableTiming));
             SPMM_CUDA(cudaEventCreateWithFlags(&A->ev_done[i], cudaEventDisableTiming));
@@ -759,6 +760,140 @@ static int host_call_slabs(spmm_csr_t A, const double *B, int k, double *C, int 
     return SPMM_OK;
 }
 
+// ---- row-block pipeline of the host-buffer multiply ------------------------------------------------------------------
+// For matrices whose rows look only a little beyond their own index (banded / FEM-like), B is uploaded in row order and
+// block j of C is multiplied as soon as the B rows it reads have arrived, then travels down while later blocks are still
+// being uploaded and multiplied: both PCIe directions run on contiguous pieces (the k-slab pipeline above moves strided
+// slabs and still waits for whole slabs). hp_need[j] = 1 + the largest column the rows of blocks 0..j hold.
+// Measured on the B200 box (cfg2 k=64, 62 MB each way): 1.94 ms against 1.82 ms for two k-slabs — with both directions busy
+// all the time each runs at ~32 GB/s (56 GB/s alone), so the overlap buys nothing there; opt-in (spmm_tune_set("host.pipe", 1 | -1)).
+constexpr int HP_BLOCKS = 16;
+
+__global__ void block_maxcol_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx, const int *__restrict__ cut,
+                                    int *__restrict__ out)
+{
+    const int e0 = rowptr[cut[blockIdx.x]], e1 = rowptr[cut[blockIdx.x + 1]];
+    int m = -1;
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x)
+        m = max(m, colidx[e]);
+    m = __reduce_max_sync(0xFFFFFFFFu, m);
+    if ((threadIdx.x & 31) == 0)
+        atomicMax(out + blockIdx.x, m);
+}
+
+static int host_pipe_prepare(spmm_csr_t A)
+{
+    if (A->hp_blocks)
+        return SPMM_OK;
+    const int nb = std::max(1, std::min(HP_BLOCKS, A->n_rows));
+    std::vector<int> cut((size_t)nb + 1), need((size_t)nb, 0);
+    for (int j = 0; j <= nb; ++j)
+        cut[j] = (int)((long long)A->n_rows * j / nb);
+    int *d = nullptr;
+    SPMM_CUDA(cudaMalloc(&d, sizeof(int) * (2 * (size_t)nb + 1)));
+    cudaError_t e = cudaMemcpy(d, cut.data(), sizeof(int) * ((size_t)nb + 1), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaMemset(d + nb + 1, 0xFF, sizeof(int) * (size_t)nb); // -1
+    if (e == cudaSuccess)
+    {
+        block_maxcol_kernel<<<nb, 1024>>>(A->d_rowptr, A->d_colidx, d, d + nb + 1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpy(need.data(), d + nb + 1, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    SPMM_CUDA(e);
+    int run = 0;
+    for (int j = 0; j < nb; ++j)
+    {
+        run = std::max(run, need[j] + 1);
+        need[j] = run;
+    }
+    A->hp_cut = cut;
+    A->hp_need = need;
+    A->hp_blocks = nb;
+    return SPMM_OK;
+}
+
+// time of the pipeline in units of "bytes over one PCIe direction": upload in row order, block j after its rows, download in order
+static double host_pipe_estimate(const spmm_csr_s *A)
+{
+    double t_done = 0.0, t_down = 0.0;
+    for (int j = 0; j < A->hp_blocks; ++j)
+    {
+        t_done = std::max(t_done, (double)A->hp_need[j]);
+        t_down = std::max(t_down, t_done) + (double)(A->hp_cut[j + 1] - A->hp_cut[j]);
+    }
+    return t_down; // in rows (x k x 8 bytes)
+}
+
+static int host_call_rowpipe(spmm_csr_t A, const double *B, int k, double *C, int kernel)
+{
+    SPMM_CUDA(cudaSetDevice(A->device));
+    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)A->n_rows * (size_t)k;
+    if (!A->stream)
+        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
+    if (!A->stream_up)
+    {
+        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_up, cudaStreamNonBlocking));
+        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_down, cudaStreamNonBlocking));
+        for (int i = 0; i < 32; ++i)
+        {
+            SPMM_CUDA(cudaEventCreateWithFlags(&A->ev_up[i], cudaEventDisableTiming));
+            SPMM_CUDA(cudaEventCreateWithFlags(&A->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    if (A->d_B_elems < nb)
+    {
+        cudaFree(A->d_B);
+        A->d_B = nullptr;
+        A->d_B_elems = 0;
+        SPMM_CUDA(cudaMalloc(&A->d_B, sizeof(double) * nb));
+        A->d_B_elems = nb;
+    }
+    if (A->d_C_elems < nc)
+    {
+        cudaFree(A->d_C);
+        A->d_C = nullptr;
+        A->d_C_elems = 0;
+        SPMM_CUDA(cudaMalloc(&A->d_C, sizeof(double) * nc));
+        A->d_C_elems = nc;
+    }
+    // B travels up in HP_BLOCKS contiguous pieces of rows
+    const int nup = std::max(1, std::min(HP_BLOCKS, A->n_cols));
+    std::vector<int> up_cut((size_t)nup + 1);
+    for (int i = 0; i <= nup; ++i)
+        up_cut[i] = (int)((long long)A->n_cols * i / nup);
+    int issued = 0; // upload pieces issued so far
+    for (int j = 0; j < A->hp_blocks; ++j)
+    {
+        const int r0 = A->hp_cut[j], r1 = A->hp_cut[j + 1];
+        while (issued < nup && up_cut[issued] < A->hp_need[j])
+        {
+            const size_t o = (size_t)up_cut[issued] * k, n = (size_t)(up_cut[issued + 1] - up_cut[issued]) * k;
+            SPMM_CUDA(cudaMemcpyAsync(A->d_B + o, B + o, sizeof(double) * n, cudaMemcpyHostToDevice, A->stream_up));
+            SPMM_CUDA(cudaEventRecord(A->ev_up[issued], A->stream_up));
+            ++issued;
+        }
+        if (issued > 0)
+            SPMM_CUDA(cudaStreamWaitEvent(A->stream, A->ev_up[issued - 1], 0));
+        if (r1 > r0)
+        {
+            const int rc = spmm_multiply_rows_device(A, r0, r1, A->d_B, k, A->d_C + (size_t)r0 * k, kernel, A->stream);
+            if (rc)
+                return rc;
+            SPMM_CUDA(cudaEventRecord(A->ev_done[j], A->stream));
+            SPMM_CUDA(cudaStreamWaitEvent(A->stream_down, A->ev_done[j], 0));
+            SPMM_CUDA(cudaMemcpyAsync(C + (size_t)r0 * k, A->d_C + (size_t)r0 * k, sizeof(double) * (size_t)(r1 - r0) * k,
+                                      cudaMemcpyDeviceToHost, A->stream_down));
+        }
+    }
+    // (rows of B no block reads are not uploaded at all)
+    SPMM_CUDA(cudaStreamSynchronize(A->stream_down));
+    SPMM_CUDA(cudaStreamSynchronize(A->stream));
+    return SPMM_OK;
+}
+
 extern "C" int spmm_multiply_host(spmm_csr_t A, const double *B, int k, double *C, int kernel)
 {
     SPMM_REQUIRE(A != nullptr, "handle is NULL");
@@ -767,6 +902,18 @@ extern "C" int spmm_multiply_host(spmm_csr_t A, const double *B, int k, double *
     if (nc == 0)
         return SPMM_OK;
     SPMM_REQUIRE(C != nullptr && (B != nullptr || nb == 0), "B/C is NULL");
+    const bool large = (nb + nc) * sizeof(double) >= (16u << 20);
+    // banded / FEM-like matrices: row-block pipeline when it beats the k-slab pipeline (1.5 x the larger direction)
+    if (nb > 0 && A->nnz > 0 && tuning().host_pipe != 0 && (large || tuning().host_pipe == 1) &&
+        (kernel == SPMM_KERNEL_AUTO || kernel == SPMM_KERNEL_ROWS || kernel == SPMM_KERNEL_MERGE))
+    {
+        const int prc = host_pipe_prepare(A);
+        if (prc)
+            return prc;
+        const double slab_units = 1.5 * (double)std::max(A->n_rows, A->n_cols);
+        if (tuning().host_pipe == 1 || host_pipe_estimate(A) <= 0.85 * slab_units)
+            return host_call_rowpipe(A, B, k, C, kernel);
+    }
     // large operands: pipeline two k-slabs so that the two PCIe directions overlap
     int slabs = tuning().host_slabs;
     if (slabs <= 0)

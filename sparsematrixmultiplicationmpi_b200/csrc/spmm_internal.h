@@ -5,6 +5,7 @@
 #include <functional>
 #include <map>
 #include <string>
+#include <vector>
 
 #include "spmm_b200.h"
 
@@ -69,6 +70,8 @@ struct Tuning
     int tiled_ksplit = 0;   // build: CTAs that share one chunk, each taking a group of k-tiles (0/1 none)
     int tiled_npw = 0;      // launch: producer warps (4, 8)
     int host_slabs = 0;     // host-buffer multiply: k-slabs in the PCIe pipeline (0 auto, 1 none)
+    int host_pipe = 0;      // host-buffer multiply: row-block pipeline for banded matrices (0 off, 1 always, -1 when its estimate beats the k-slabs);
+                            // off by default: measured 1.94 ms against 1.82 ms for two k-slabs on cfg2 k=64 — both directions together cap at ~65 GB/s on this host
     int tiled_group = 0;    // build: tiles one far-band apart walked in turn, this many bands per group (0 auto = 2, 1 off)
     int tiled_stride = 0;   // build: far-band distance in rows (0 = detect from the matrix)
     int tiled_prefetch = -1; // launch: tiles ahead whose blob is prefetched into L2 (-1 auto)
@@ -121,7 +124,10 @@ struct spmm_csr_s
     size_t d_B_elems = 0, d_C_elems = 0;
     cudaStream_t stream = nullptr; // owned, for host-buffer calls
     cudaStream_t stream_up = nullptr, stream_down = nullptr; // k-slab pipeline of the host-buffer multiply
-    cudaEvent_t ev_up[8] = {}, ev_done[8] = {};
+    cudaEvent_t ev_up[32] = {}, ev_done[32] = {};
+    // row-block pipeline of the host-buffer multiply: block j of C needs the B rows [0, hp_need[j])
+    int hp_blocks = 0;
+    std::vector<int> hp_cut, hp_need;
     // row-block union format (spmm_rowblock.cu), optional
     int rb_R = 0, rb_blocks = 0;
     long long rb_entries = 0;

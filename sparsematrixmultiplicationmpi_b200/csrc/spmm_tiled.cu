@@ -1277,7 +1277,7 @@ namespace
 int detect_far_band(const spmm_csr_s *A, int *stride_rows)
 {
     *stride_rows = 0;
-    if (A->n_rows < 4096 || A->nnz == 0)
+    if (A->n_rows < 4096 || A->nnz == 0 || A->nnz > (32ll << 20)) // (the scan below runs on the host: keep it to mid-sized matrices)
         return SPMM_OK;
     std::vector<int> rp((size_t)A->n_rows + 1), ci((size_t)A->nnz);
     SPMM_CUDA(cudaMemcpy(rp.data(), A->d_rowptr, sizeof(int) * rp.size(), cudaMemcpyDeviceToHost));

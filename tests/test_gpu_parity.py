@@ -740,12 +740,40 @@ def test_host_multiply_k_slab_pipeline(oracle, slabs):
     ref = oracle.spmm(rp, ci, va, B, k)
     _cabi.tune("reset", 0)
     _cabi.tune("host.slabs", slabs)
+    _cabi.tune("host.pipe", 0)  # this test is about the k-slab pipeline
     try:
         with spmm.DeviceCSR.from_host(m, 0) as A:
             got = A.multiply_host(B, k, "auto")
             assert_close_rel(got, ref, tol=REL_TOL)
             again = A.multiply_host(B, k, "rows")
             assert_close_rel(again, ref, tol=REL_TOL)
+    finally:
+        _cabi.tune("reset", 0)
+
+
+@pytest.mark.parametrize("shape", ["banded", "random", "rect_wide", "rect_tall", "mostly_empty"])
+@pytest.mark.parametrize("pipe", [-1, 1])
+def test_host_multiply_row_block_pipeline(oracle, shape, pipe):
+    """spmm_multiply_host with the row-block pipeline (host.pipe): block j of C is multiplied once the B rows it reads have
+    arrived. Forced (1) on shapes where block 0 already needs all of B, automatic (-1) where the estimate decides."""
+    k = 64
+    if shape == "banded":
+        n, nc = 40_000, 40_000
+        rp, ci, va = banded_csr(61, n, 9, 30, (-700, 0, 700))
+    else:
+        n, nc, mean, ee = {"random": (30_000, 30_000, 8, 0), "rect_wide": (9_000, 50_000, 10, 0),
+                           "rect_tall": (50_000, 700, 3, 4), "mostly_empty": (30_000, 30_000, 1, 2)}[shape]
+        rp, ci, va = random_csr(17, n, nc, mean, empty_every=ee, positive=True)
+    m = spmm.SparseMatrix(va, ci, rp, n, nc)
+    B = np.random.default_rng(9).integers(1, 101, (nc, k)).astype(np.float64)
+    ref = oracle.spmm(rp, ci, va, B, k)
+    _cabi.tune("reset", 0)
+    _cabi.tune("host.pipe", pipe)
+    try:
+        with spmm.DeviceCSR.from_host(m, 0) as A:
+            for kernel in ("auto", "rows"):
+                got = A.multiply_host(B, k, kernel)
+                assert_close_rel(got, ref, tol=REL_TOL)
     finally:
         _cabi.tune("reset", 0)
 
