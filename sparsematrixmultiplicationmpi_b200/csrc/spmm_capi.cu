@@ -467,9 +467,10 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
     // AUTO builds the tile layout the first time a multiply can use it (k >= 8, even, mid-sized matrix with
     // regular rows): one-off, a few milliseconds, 16 bytes per non-zero next to the CSR. spmm_tune_set("tiled", 0)
     // or an explicit spmm_csr_build_tiles(A, 0, 0) keeps the CSR kernels.
-    if (kernel == SPMM_KERNEL_AUTO && A->tl_auto && A->tl_T != 0 && A->tl_ksplit > std::max(1, (k_count + 15) / 16))
+    if (kernel == SPMM_KERNEL_AUTO && A->tl_auto && A->tl_T != 0 &&
+        (A->tl_ksplit > std::max(1, (k_count + 15) / 16) || (A->tl_kt == 8) != (k_count <= 8)))
     {
-        free_tiles(A); // built for a wider k: its long chunks would leave SMs idle here, build again for this k
+        free_tiles(A); // built for a wider k (long chunks would leave SMs idle) or for the other k-tile width: build again for this k
         A->tl_tried = false;
     }
     if (kernel == SPMM_KERNEL_AUTO && !A->tl_tried && A->tl_T == 0 && tuning().tiled != 0 && k_count >= 8 &&
@@ -477,11 +478,14 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
     {
         A->tl_tried = true;
         // many k-tiles: longer chunks shared by several CTAs (one k-tile group each), fewer window warm-ups
-        const int saved = tuning().tiled_ksplit;
+        const int saved = tuning().tiled_ksplit, saved_kt = tuning().tiled_kt;
         if (saved == 0)
             tuning().tiled_ksplit = k_count >= 64 ? 4 : (k_count >= 32 ? 2 : 1);
+        if (saved_kt == 0 && k_count <= 8)
+            tuning().tiled_kt = 8; // 64-byte window rows: half the bytes staged and read for k <= 8
         const int brc = spmm_csr_build_tiles(A, -1, 0);
         tuning().tiled_ksplit = saved;
+        tuning().tiled_kt = saved_kt;
         A->tl_auto = true;
         if (brc != SPMM_OK)
             free_tiles(A); // not fatal: the CSR kernels stay in charge

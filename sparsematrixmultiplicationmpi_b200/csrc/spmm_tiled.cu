@@ -664,7 +664,10 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
                                                                          const __grid_constant__ CUtensorMap row_map)
 {
     constexpr int NL = KT / (2 * TL); // LDS.128 per lane and record
-    static_assert(NL >= 2 && NL * 2 * TL == KT, "a quarter-warp (2 teams) must cover distinct banks");
+    static_assert(NL >= 1 && NL * 2 * TL == KT, "a team of TL lanes covers the k-tile with NL 16-byte accesses per lane");
+    // (NL = 1, the 8-column k-tile for k <= 8: the two teams of a quarter-warp read 64-byte slab rows that share their banks
+    // when the rows have the same parity — 1.5 wavefronts per quarter-warp on average instead of the 2 a half-empty 16-column
+    // k-tile costs, and half the bytes staged)
     extern __shared__ __align__(1024) unsigned char smem[];
     const unsigned s0 = (smem_u32(smem) + 1023u) & ~1023u;
     const unsigned full = s0, empty = s0 + 64; // 8 bytes each, indexed by work item mod depth
@@ -864,7 +867,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
     int colo[NL];          // column (in doubles) of accumulator i inside the k-tile
 #pragma unroll
     for (int i = 0; i < NL; ++i)
-        colo[i] = ((i ^ tq) * TL + l) * 2;
+        colo[i] = ((NL > 1 ? (i ^ tq) : i) * TL + l) * 2;
 
     long long q_wait = 0, q_main = 0, q_t0 = TCLK();
     int st = 0, use = 0;
@@ -988,7 +991,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
                 double2 al[NL];
 #pragma unroll
                 for (int x = 0; x < NL; ++x)
-                    al[x] = tq ? acc[x ^ 1] : acc[x];
+                    al[x] = (NL > 1 && tq) ? acc[NL > 1 ? (x ^ 1) : x] : acc[x];
 #pragma unroll
                 for (int x = 0; x < NL; ++x)
 #pragma unroll
@@ -1370,11 +1373,22 @@ int launch_tiled(const spmm_csr_s *A, const double *d_B, long long ldb, double *
     const int ncw = t.tiled_ncw > 0 ? t.tiled_ncw : 16;
     const int u = t.tiled_unroll > 0 ? t.tiled_unroll : 4;
     const int npw = t.tiled_npw == 8 ? 8 : 4;
+    if (kt == 8)
+    {
+        if (ncw == 16 && u == 4 && npw == 4)
+            return launch_tiled_t<8, 16, 4, 4>(A, d_B, ldb, d_C, ldc, kc, stream, x);
+        if (ncw == 12 && u == 4 && npw == 4)
+            return launch_tiled_t<8, 12, 4, 4>(A, d_B, ldb, d_C, ldc, kc, stream, x);
+        if (ncw == 8 && u == 4 && npw == 4)
+            return launch_tiled_t<8, 8, 4, 4>(A, d_B, ldb, d_C, ldc, kc, stream, x);
+        set_error("tiled kernel: the 8-column k-tile goes with 8, 12 or 16 consumer warps, unroll 4, 4 producer warps");
+        return SPMM_ERR_INVALID;
+    }
     if (kt == 16)
         return launch_tiled_ncw<16>(A, ncw, u, npw, d_B, ldb, d_C, ldc, kc, stream, x);
     if (kt == 32)
         return launch_tiled_ncw<32>(A, ncw, u, npw, d_B, ldb, d_C, ldc, kc, stream, x);
-    set_error("tiled kernel: k-tile must be 16 or 32");
+    set_error("tiled kernel: k-tile must be 8, 16 or 32");
     return SPMM_ERR_INVALID;
 }
 

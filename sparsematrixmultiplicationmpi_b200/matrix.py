@@ -164,11 +164,15 @@ class DeviceCSR:
         made longer and shared by 2 or 4 CTAs, each taking a group of k-tiles (what AUTO does on its own)."""
         if k > 0:
             _cabi.tune("tiled.ksplit", 4 if k >= 64 else (2 if k >= 32 else 1))
+            if k <= 8:
+                _cabi.tune("tiled.kt", 8)  # 64-byte window rows
         try:
             _cabi.check(_cabi.lib().spmm_csr_build_tiles(self.handle, rows_per_tile, box_rows))
         finally:
             if k > 0:
                 _cabi.tune("tiled.ksplit", 0)
+                if k <= 8:
+                    _cabi.tune("tiled.kt", 0)
         return self.tile_info()
 
     def tile_info(self) -> dict:

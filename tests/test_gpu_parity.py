@@ -514,6 +514,33 @@ def test_tiled_shapes_and_teams(oracle, T, BR, tune):
     assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
 
 
+@pytest.mark.parametrize("shape", list(TILED_SHAPES))
+@pytest.mark.parametrize("k", [2, 6, 8])
+@pytest.mark.parametrize("ncw", [16, 8])
+def test_tiled_kernel_8_column_k_tile(oracle, shape, k, ncw):
+    """k <= 8: the window rows are 64 bytes (k-tile of 8 columns, one 16-byte access per lane)."""
+    n, mean, hb, planes, long_row, ee = TILED_SHAPES[shape]
+    rp, ci, va = banded_csr(33, n, mean, hb, planes, long_row, ee)
+    B = np.random.default_rng(k).integers(1, 101, (n, k)).astype(np.float64)
+    ref = oracle.spmm(rp, ci, va, B, k)
+    _cabi.tune("reset", 0)
+    _cabi.tune("tiled.kt", 8)
+    _cabi.tune("tiled.ncw", ncw)
+    try:
+        with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, n, n), 0, 0) as A:
+            info = A.build_tiles(-1, 0)
+            if not info["rows_per_tile"]:
+                pytest.skip("no tile shape fits this matrix")
+            dB = dev(B)
+            dC = torch.full((n, k), np.nan, dtype=torch.float64, device="cuda")
+            A.multiply(dB.data_ptr(), k, dC.data_ptr(), "tiled", torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            got = dC.cpu().numpy()
+    finally:
+        _cabi.tune("reset", 0)
+    assert_close_rel(got, ref, tol=REL_TOL)
+
+
 @pytest.mark.parametrize("group", [1, 2, 3, 4, 6])
 @pytest.mark.parametrize("k", [16, 64])
 def test_tiled_walking_order_of_far_band_matrices(oracle, group, k):
