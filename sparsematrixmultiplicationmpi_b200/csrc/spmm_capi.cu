@@ -473,7 +473,7 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
         free_tiles(A); // built for a wider k (long chunks would leave SMs idle) or for the other k-tile width: build again for this k
         A->tl_tried = false;
     }
-    if (kernel == SPMM_KERNEL_AUTO && !A->tl_tried && A->tl_T == 0 && tuning().tiled != 0 && k_count >= 8 &&
+    if (kernel == SPMM_KERNEL_AUTO && !A->tl_tried && A->tl_T == 0 && tuning().tiled != 0 && k_count >= 4 &&
         k_count % 2 == 0 && A->nnz >= 200000 && A->nnz <= (64ll << 20))
     {
         A->tl_tried = true;

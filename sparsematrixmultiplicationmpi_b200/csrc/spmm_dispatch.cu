@@ -90,7 +90,7 @@ int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_l
             const bool fits = tiled_shape_ok(A, d_B, ldb, d_C, ldc, kc);
             const double staged = (double)A->tl_box_rows_loaded + (double)A->tl_single_rows;
             const double reuse = staged > 0 ? (double)A->nnz / staged : 0.0;
-            if (fits && (derived == 6 || t.tiled == 1 || (kc >= 8 && reuse >= 2.0 && A->tl_drains * 20 <= A->tl_tiles)))
+            if (fits && (derived == 6 || t.tiled == 1 || (kc >= (A->tl_kt == 8 ? 4 : 8) && reuse >= 2.0 && A->tl_drains * 20 <= A->tl_tiles)))
                 return launch_tiled(A, d_B, ldb, d_C, ldc, kc, stream, extra);
             if (derived == 6)
             {

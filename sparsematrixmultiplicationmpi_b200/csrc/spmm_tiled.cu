@@ -1418,7 +1418,9 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
     const int kt = tn.tiled_kt > 0 ? tn.tiled_kt : 16; // k-tile the window is sized for
     const int sms = device_props(A->device).sm_count;
     // measured on the cop20k_A shape (profiles/r1_tiled.md): tall tiles and a wide window beat a deeper pipeline
-    const int depth = (tn.tiled_depth >= 2 && tn.tiled_depth <= TB_DMAX) ? tn.tiled_depth : 2;
+    const int kt_for_depth = tn.tiled_kt > 0 ? tn.tiled_kt : 16;
+    // (64-byte window rows leave room for a third work item in flight: measured 20.6 against 22.7 us at k=8, T=96)
+    const int depth = (tn.tiled_depth >= 2 && tn.tiled_depth <= TB_DMAX) ? tn.tiled_depth : (kt_for_depth == 8 ? 3 : 2);
     const int ksplit = std::max(1, std::min(8, tn.tiled_ksplit)); // CTAs per chunk (set from k by AUTO / the Python wrapper)
 
     BuildParams p = {};
@@ -1440,7 +1442,7 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
     BuildParams best = {};
     double best_score = 0.0;
     // short chunks (one CTA per chunk walks every k-tile) favour 64-row tiles, long shared chunks taller ones (measured)
-    const int first_cand = ksplit > 1 ? 0 : 3;
+    const int first_cand = (ksplit > 1 || kt == 8) ? 0 : 3;
     for (int ci = first_cand; ci < (rows_per_tile > 0 ? first_cand + 1 : 7); ++ci)
     {
         const int T = rows_per_tile > 0 ? rows_per_tile : auto_cand[ci];
