@@ -254,6 +254,7 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "stream") t.stream = value;
     else if (k == "stream.tile") t.stream_tile = value;
     else if (k == "stream.kmax") t.stream_auto_kmax = value;
+    else if (k == "stream.persist") t.stream_persist = value;
     else if (k == "union.slots") t.union_slots = value;
     else if (k == "union.split") t.union_split = value;
     else if (k == "union.auto") t.union_auto = value;

@@ -79,6 +79,8 @@ struct Tuning
     int union_split = 0;    // union layout: blocks with more union entries are cut into segments of about this length
     int stream = -1;        // -1 auto, 0 AUTO never uses the stream kernel (k = 1, 2, 4, 8)
     int stream_auto_kmax = 0; // AUTO takes the stream kernel up to this k (0: never — measured no faster than the row kernels, profiles/r1_stream.md)
+    int stream_persist = 0; // stream kernel: CTAs per SM of the persistent, software-pipelined variant (0 = one CTA per tile, the default:
+                            // the pipelined variant measured the same 18-19 us at k=1, profiles/r1_stream.md)
     int stream_tile = 0;    // stream kernel: non-zeros per tile (0 = 4096 / k)
     int union_debug = 0;    // diagnostics, wrong results by design (see spmm_union.cu)
     int union_auto = -1;    // -1 auto, 0 AUTO never builds / uses the union layout

@@ -620,7 +620,7 @@ def test_tiled_mixed_sign_duplicates_and_strided(oracle, golden_multiply):
 # ---------------------------------------------------------------- stream kernel (spmm_stream.cu): k = 1, 2, 4, 8, bit-identical
 @pytest.mark.parametrize("shape", ["short", "fem_like", "rect_wide", "rect_tall", "single_row"])
 @pytest.mark.parametrize("k", [1, 2, 4, 8])
-@pytest.mark.parametrize("tune", [{}, {"stream.tile": 256}, {"stream.tile": 1024}])
+@pytest.mark.parametrize("tune", [{}, {"stream.tile": 256}, {"stream.tile": 1024}, {"stream.persist": 4}, {"stream.persist": 2, "stream.tile": 512}])
 def test_stream_kernel_bit_identical_to_the_oracle(oracle, shape, k, tune):
     seed, n, nc, mean, long_row, empty_every = SHAPES[shape]
     rp, ci, va = random_csr(seed, n, nc, mean, long_row=long_row, empty_every=empty_every, positive=False)

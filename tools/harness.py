@@ -103,6 +103,8 @@ def variant_list(k, full):
     if k in (1, 2, 4, 8):
         v.append(("stream", "stream", {}))
         v += [(f"stream tile={t}", "stream", {"stream.tile": t}) for t in (256, 512, 1024, 2048, 4096, 8192) if t * k * 8 <= 96 * 1024]
+        v += [(f"stream tile={t} persist={p}", "stream", {"stream.tile": t, "stream.persist": p})
+              for t in (512, 1024, 2048) for p in (0, 2, 4, 6, 8) if t * k * 8 <= 96 * 1024]
     if not full:
         return v
     for u in (1, 2, 4, 8):
