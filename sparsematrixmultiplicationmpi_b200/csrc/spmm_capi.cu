@@ -254,6 +254,7 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "stream") t.stream = value;
     else if (k == "stream.tile") t.stream_tile = value;
     else if (k == "stream.kmax") t.stream_auto_kmax = value;
+    else if (k == "stream.min_nnz") t.stream_auto_min_nnz = value;
     else if (k == "stream.persist") t.stream_persist = value;
     else if (k == "union.slots") t.union_slots = value;
     else if (k == "union.split") t.union_split = value;
@@ -461,8 +462,10 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
     SPMM_REQUIRE(kernel != SPMM_KERNEL_ROWBLOCK || A->rb_R != 0, "row-block kernel requested but spmm_csr_build_rowblocks was not called");
     if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)
         return launch_merge(A, 0, A->n_rows, 0, A->nnz, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
-    // narrow fat vectors in nnz order: opt-in (spmm_tune_set("stream.kmax", 8)); measured no faster than the row kernels (profiles/r1_stream.md)
+    // k = 1 on matrices of 4 M non-zeros and more: streamed in nnz order (3.1 against 2.4 TB/s at 10.5 M non-zeros, and bit-identical to
+    // the reference); wider k / smaller matrices by spmm_tune_set("stream.kmax" / "stream.min_nnz") (profiles/r1_stream.md)
     if (kernel == SPMM_KERNEL_AUTO && tuning().stream != 0 && k_count <= tuning().stream_auto_kmax &&
+        A->nnz >= tuning().stream_auto_min_nnz &&
         stream_shape_ok(A, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count))
         return launch_stream(A, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
     // AUTO builds the tile layout the first time a multiply can use it (k >= 8, even, mid-sized matrix with

@@ -78,7 +78,8 @@ struct Tuning
     int union_slots = 0;    // union layout: slots per item (4: 8-lane teams, 8: 4-lane teams)
     int union_split = 0;    // union layout: blocks with more union entries are cut into segments of about this length
     int stream = -1;        // -1 auto, 0 AUTO never uses the stream kernel (k = 1, 2, 4, 8)
-    int stream_auto_kmax = 0; // AUTO takes the stream kernel up to this k (0: never — measured no faster than the row kernels, profiles/r1_stream.md)
+    int stream_auto_kmax = 1; // AUTO takes the stream kernel up to this k ...
+    int stream_auto_min_nnz = 4 << 20; // ... from this many non-zeros (measured: equal to the row kernel at 2.6 M non-zeros, 43 against 56 us at 10.5 M; profiles/r1_stream.md)
     int stream_persist = 0; // stream kernel: CTAs per SM of the persistent, software-pipelined variant (0 = one CTA per tile, the default:
                             // the pipelined variant measured the same 18-19 us at k=1, profiles/r1_stream.md)
     int stream_tile = 0;    // stream kernel: non-zeros per tile (0 = 4096 / k)

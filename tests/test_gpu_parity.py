@@ -629,7 +629,7 @@ def test_stream_kernel_bit_identical_to_the_oracle(oracle, shape, k, tune):
     got = gpu_multiply(spmm.SparseMatrix(va, ci, rp, n, nc), B, k, "stream", tune)
     # product rounded, then added in ascending non-zero order: the reference's own arithmetic (-ffp-contract=off)
     assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
-    auto = gpu_multiply(spmm.SparseMatrix(va, ci, rp, n, nc), B, k, "auto", {"stream.kmax": 8})  # AUTO opted in
+    auto = gpu_multiply(spmm.SparseMatrix(va, ci, rp, n, nc), B, k, "auto", {"stream.kmax": 8, "stream.min_nnz": 0})  # AUTO opted in
     assert np.array_equal(auto.view(np.uint64), ref.view(np.uint64))
 
 
