@@ -112,7 +112,7 @@ int spmm_csr_rowblock_info(spmm_csr_t A, int *rows_per_block, long long *union_e
  * whose k is a multiple of 2*lanes_per_row. */
 int spmm_csr_build_packed(spmm_csr_t A, int rows_per_unit, int lanes_per_row);
 int spmm_csr_packed_info(spmm_csr_t A, int *rows_per_unit, int *lanes_per_row, long long *slots, double *fill_ratio);
-/* Optional fourth layout, the one AUTO prefers for k >= 16 when neighbouring rows share columns:
+/* Optional fourth layout, the one AUTO prefers for even k >= 4 when neighbouring rows share columns:
  * tiles of rows_per_tile consecutive rows walked in order by one CTA that keeps a window of B-row
  * boxes (box_rows consecutive rows of B each, brought in by one TMA box copy) in shared memory;
  * non-zeros re-encoded as 16-byte records addressing that window, stragglers staged row by row
