@@ -12,7 +12,10 @@
 // Work split (layout: spmm_union_build.h): an item = SL slots (one per team of 32/SL lanes) = the work of ONE consumer warp;
 // consumer warp c takes items c, c+NCW, ... of the CTA's chunk; NPW producer warps walk all items, D items in flight.
 // Every consumer passes every item's "landed" barrier in order (it may read window rows an earlier item loaded); barriers
-// are indexed modulo 2*D so that no barrier can run two phases ahead of a warp that still has to observe it.
+// are indexed modulo 32 >= 2*D so that no barrier can run two phases ahead of a warp that still has to observe it.
+// STATUS: experimental. Correct (tests/test_gpu_parity.py, tests/union_layout_emul.cpp) but 1.7x slower than the tiled kernel on
+// the cop20k_A shape (profiles/r1_union.md: TMA issue cost per 1 KB gather, ~500 cycles of barrier hand-off per 2.5 KB item,
+// too few items in flight for the consumers to hide their own latency). Never picked by AUTO.
 // Per (row, column) the accumulation order is ascending column as in the reference; a block longer than the split length
 // is cut into segments whose partial sums are folded in a fixed order (within the 1e-12 tolerance, like the merge kernel).
 // Absent entries of the union are 0.0 values: B is assumed finite (0 * inf would leak into a row that does not hold
@@ -129,7 +132,7 @@ struct UnionArgs
     const int *gslot;
     double *C;
     long long ldc;
-    int n_rows, kc, nkt, D, S, maxg;
+    int n_rows, kc, nkt, D, maxg;
     long long *prof; // dbg & 64: per CTA 8 counters
     int dbg; // diagnostics (wrong results): 1 consumers skip the arithmetic, 2 no B rows are staged, 4 no blobs either
     unsigned slab_off; // offset of the window from the aligned smem base
@@ -510,7 +513,6 @@ int launch_union_t(const UnionDev *u, const double *d_B, long long ldb, double *
     a.kc = kc;
     a.nkt = (kc + KT - 1) / KT;
     a.D = u->D;
-    a.S = 2 * u->D;
     a.maxg = u->maxg;
     a.dbg = tuning().union_debug;
     a.slab_off = (unsigned)u->slab_off;
