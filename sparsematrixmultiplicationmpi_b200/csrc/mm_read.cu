@@ -29,14 +29,22 @@ inline bool is_space(unsigned char c) { return c == ' ' || c == '\n' || c == '\t
 inline bool parse_int(const char *b, const char *e, int *out)
 {
     if (b < e && *b == '+')
+    {
         ++b;
+        if (b < e && (*b == '+' || *b == '-'))
+            return false; // "+-3": from_chars would take the minus; operator>> fails
+    }
     const auto r = std::from_chars(b, e, *out);
     return r.ec == std::errc() && r.ptr == e;
 }
 inline bool parse_double(const char *b, const char *e, double *out)
 {
     if (b < e && *b == '+')
+    {
         ++b;
+        if (b < e && (*b == '+' || *b == '-'))
+            return false;
+    }
     const auto r = std::from_chars(b, e, *out);
     if (r.ec == std::errc() && r.ptr == e)
         return true;

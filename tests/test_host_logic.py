@@ -89,14 +89,53 @@ def test_matrix_market_native_reader_token_stream(oracle, tmp_path):
     assert np.array_equal(rows, orows) and np.array_equal(cols, ocols)
     assert np.array_equal(vals.view(np.uint64), ovals.view(np.uint64))
     assert np.array_equal(vals, v)  # repr() round-trips every double
-    bad = tmp_path / "bad.mtx"
-    bad.write_text("%%MatrixMarket matrix coordinate real general\n2 2 2\n1 1 1.0\n2 x 3.0\n")
-    with pytest.raises(RuntimeError, match="Failed to read data"):
-        spmm.parse_matrix_market(str(bad))
+    for junk in ("2 x 3.0", "2 2 +-3.0", "+-2 2 3.0", "2 2 3.0.1", "2 2 1e"):
+        bad = tmp_path / "bad.mtx"
+        bad.write_text("%%MatrixMarket matrix coordinate real general\n2 2 2\n1 1 1.0\n" + junk + "\n")
+        with pytest.raises(RuntimeError, match="Failed to read data"):
+            spmm.parse_matrix_market(str(bad))
+        with pytest.raises(RuntimeError, match="Failed to read data"):
+            oracle.read_mtx_coo(str(bad))
     oob = tmp_path / "oob.mtx"
     oob.write_text("%%MatrixMarket matrix coordinate real general\n2 2 1\n3 1 1.0\n")
     with pytest.raises(RuntimeError, match="outside the declared"):
         spmm.parse_matrix_market(str(oob))
+
+
+def test_matrix_market_native_reader_random_token_layouts(oracle, tmp_path):
+    """Property test: whatever the whitespace between tokens and the spelling of the numbers, the native reader and the
+    oracle's restatement of utils.cpp:70-153 produce the same records, bit for bit."""
+    hypothesis = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    seps = st.sampled_from([" ", "  ", "\t", "\n", " \n", "\r\n", "\n\n", " \t "])
+    spell = st.sampled_from(["{!r}", "{:.17g}", "{:.17e}", "+{:.17g}", "{:.20f}"])
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 40), st.integers(1, 40), st.integers(0, 60), st.booleans(), st.booleans(), st.data())
+    def check(nr, nc, ne, symmetric, pattern, data):
+        if symmetric:
+            nc = nr
+        rows = data.draw(st.lists(st.integers(1, nr), min_size=ne, max_size=ne))
+        cols = data.draw(st.lists(st.integers(1, nc), min_size=ne, max_size=ne))
+        vals = data.draw(st.lists(st.floats(-1e30, 1e30, allow_nan=False, width=64), min_size=ne, max_size=ne))
+        kind = "pattern" if pattern else "real"
+        text = f"%%MatrixMarket matrix coordinate {kind} {'symmetric' if symmetric else 'general'}\n% comment\n{nr} {nc} {ne}\n"
+        for r, c, v in zip(rows, cols, vals):
+            text += f"{r}{data.draw(seps)}{c}"
+            if not pattern:
+                fmt = data.draw(spell)
+                text += data.draw(seps) + (fmt if v >= 0 or not fmt.startswith("+") else "{!r}").format(float(v))
+            text += data.draw(seps)
+        path = tmp_path / "prop.mtx"
+        path.write_text(text, newline="")
+        got = spmm.parse_matrix_market(str(path))
+        onr, onc, orows, ocols, ovals, osym, _ = oracle.read_mtx_coo(str(path))
+        assert (got[0], got[1], got[5]) == (onr, onc, osym)
+        assert np.array_equal(got[2], orows) and np.array_equal(got[3], ocols)
+        assert np.array_equal(got[4].view(np.uint64), ovals.view(np.uint64))
+
+    check()
 
 
 def test_cop20k_shaped_generator_hits_the_published_shape():
