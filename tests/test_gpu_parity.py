@@ -301,6 +301,25 @@ def test_cop20k_shape_all_k_vs_oracle_and_properties(oracle):
         assert abs(float((x * Ay).sum() - (y * Ax).sum())) <= 1e-9 * float((x * Ay).sum())
 
 
+def test_auto_rebuilds_its_layouts_across_k(oracle):
+    """One handle, AUTO, a sequence of k that crosses every layout boundary (8-column k-tile for k <= 8, 16-column above,
+    chunks shared by 2 / 4 CTAs from k = 32 / 64, row kernels for odd k and k = 2): each result against the oracle."""
+    n, nc, r, c, v, sym = gen.cop20k_A_shaped(n=30_000, nnz=600_000, nx=20, ny=25, seed=7)
+    with spmm.DeviceCSR.from_coo_host(n, nc, r, c, v, sym) as A:
+        host = A.download()
+        for k in (64, 4, 2, 16, 6, 8, 128, 1, 32, 5, 64):
+            B = np.random.default_rng(100 + k).integers(1, 101, (n, k)).astype(np.float64)
+            ref = oracle.spmm(host.rowPtr, host.colIndices, host.values, B, k)
+            dB = dev(B)
+            dC = torch.full((n, k), np.nan, dtype=torch.float64, device="cuda")
+            A.multiply(dB.data_ptr(), k, dC.data_ptr(), "auto")
+            torch.cuda.synchronize()
+            assert_close_rel(dC.cpu().numpy(), ref, tol=REL_TOL)
+            info = A.tile_info()
+            if k in (4, 6, 8, 16, 32, 64, 128):
+                assert info["rows_per_tile"] > 0, (k, info)  # FEM-like rows: AUTO must have built a tile layout
+
+
 def test_large_banded_properties():
     """2^22 x 2^22 banded, 32 per row (cfg4's shape at 1/8 size): checksum and linearity properties."""
     n, k = 1 << 22, 16
