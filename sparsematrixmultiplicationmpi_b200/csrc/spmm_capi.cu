@@ -678,13 +678,9 @@ extern "C" int spmm_reduce_blocks_device(int device, int n_src, const double *co
     return SPMM_OK;
 }
 
-// Host-buffer plumbing shared by the *_host entry points: B up, launch, C_local down.
-template <typename Launch>
-static int host_call(spmm_csr_t A, const double *B, size_t nb, double *C, size_t nc, Launch launch)
+// device staging buffers of the host-buffer entry points, grown on demand
+static int ensure_host_buffers(spmm_csr_t A, size_t nb, size_t nc)
 {
-    SPMM_CUDA(cudaSetDevice(A->device));
-    if (!A->stream)
-        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
     if (A->d_B_elems < nb)
     {
         cudaFree(A->d_B);
@@ -698,8 +694,41 @@ static int host_call(spmm_csr_t A, const double *B, size_t nb, double *C, size_t
         cudaFree(A->d_C);
         A->d_C = nullptr;
         A->d_C_elems = 0;
-        SPMM_CUDA(cudaMalloc(&A->d_C, sizeof(double) * nc));
+        SPMM_CUDA(cudaMalloc(&A->d_C, sizeof(double) * std::max<size_t>(nc, 1)));
         A->d_C_elems = nc;
+    }
+    return SPMM_OK;
+}
+
+// compute stream + upload / download streams and events of the pipelined host-buffer multiplies
+static int ensure_pipe_streams(spmm_csr_t A)
+{
+    if (!A->stream)
+        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
+    if (!A->stream_up)
+    {
+        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_up, cudaStreamNonBlocking));
+        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_down, cudaStreamNonBlocking));
+        for (int i = 0; i < 32; ++i)
+        {
+            SPMM_CUDA(cudaEventCreateWithFlags(&A->ev_up[i], cudaEventDisableTiming));
+            SPMM_CUDA(cudaEventCreateWithFlags(&A->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    return SPMM_OK;
+}
+
+// Host-buffer plumbing shared by the *_host entry points: B up, launch, C_local down.
+template <typename Launch>
+static int host_call(spmm_csr_t A, const double *B, size_t nb, double *C, size_t nc, Launch launch)
+{
+    SPMM_CUDA(cudaSetDevice(A->device));
+    if (!A->stream)
+        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
+    {
+        const int rc = ensure_host_buffers(A, nb, nc);
+        if (rc)
+            return rc;
     }
     // Pageable host buffers (std::vector / numpy storage) are copied directly; cudaMemcpyAsync
     // from pageable memory stages through the driver's pinned bounce buffers.
@@ -719,33 +748,12 @@ static int host_call_slabs(spmm_csr_t A, const double *B, int k, double *C, int 
 {
     SPMM_CUDA(cudaSetDevice(A->device));
     const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)A->n_rows * (size_t)k;
-    if (!A->stream)
-        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
-    if (!A->stream_up)
     {
-        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_up, cudaStreamNonBlocking));
-        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_down, cudaStreamNonBlocking));
-        for (int i = 0; i < 32; ++i)
-        {
-            SPMM_CUDA(cudaEventCreateWithFlags(&A->ev_up[i], cudaEventDisableTiming));
-            SPMM_CUDA(cudaEventCreateWithFlags(&A->ev_done[i], cudaEventDisableTiming));
-        }
-    }
-    if (A->d_B_elems < nb)
-    {
-        cudaFree(A->d_B);
-        A->d_B = nullptr;
-        A->d_B_elems = 0;
-        SPMM_CUDA(cudaMalloc(&A->d_B, sizeof(double) * nb));
-        A->d_B_elems = nb;
-    }
-    if (A->d_C_elems < nc)
-    {
-        cudaFree(A->d_C);
-        A->d_C = nullptr;
-        A->d_C_elems = 0;
-        SPMM_CUDA(cudaMalloc(&A->d_C, sizeof(double) * nc));
-        A->d_C_elems = nc;
+        int rc = ensure_pipe_streams(A);
+        if (!rc)
+            rc = ensure_host_buffers(A, nb, nc);
+        if (rc)
+            return rc;
     }
     const int ks = k / slabs; // columns per slab (k % slabs == 0 checked by the caller)
     const size_t pitch = sizeof(double) * (size_t)k, width = sizeof(double) * (size_t)ks;
@@ -839,33 +847,12 @@ static int host_call_rowpipe(spmm_csr_t A, const double *B, int k, double *C, in
 {
     SPMM_CUDA(cudaSetDevice(A->device));
     const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)A->n_rows * (size_t)k;
-    if (!A->stream)
-        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
-    if (!A->stream_up)
     {
-        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_up, cudaStreamNonBlocking));
-        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_down, cudaStreamNonBlocking));
-        for (int i = 0; i < 32; ++i)
-        {
-            SPMM_CUDA(cudaEventCreateWithFlags(&A->ev_up[i], cudaEventDisableTiming));
-            SPMM_CUDA(cudaEventCreateWithFlags(&A->ev_done[i], cudaEventDisableTiming));
-        }
-    }
-    if (A->d_B_elems < nb)
-    {
-        cudaFree(A->d_B);
-        A->d_B = nullptr;
-        A->d_B_elems = 0;
-        SPMM_CUDA(cudaMalloc(&A->d_B, sizeof(double) * nb));
-        A->d_B_elems = nb;
-    }
-    if (A->d_C_elems < nc)
-    {
-        cudaFree(A->d_C);
-        A->d_C = nullptr;
-        A->d_C_elems = 0;
-        SPMM_CUDA(cudaMalloc(&A->d_C, sizeof(double) * nc));
-        A->d_C_elems = nc;
+        int rc = ensure_pipe_streams(A);
+        if (!rc)
+            rc = ensure_host_buffers(A, nb, nc);
+        if (rc)
+            return rc;
     }
     // B travels up in HP_BLOCKS contiguous pieces of rows
     const int nup = std::max(1, std::min(HP_BLOCKS, A->n_cols));
