@@ -431,6 +431,34 @@ int spmm_csr_schedule(spmm_csr_t A, long long bins[8], int *max_row_len, double 
 
 // ---- multiply ---------------------------------------------------------------------
 
+// AUTO builds the tile layout the first time a multiply can use it (even k >= 4, mid-sized matrix with regular rows):
+// one-off, ~10 ms, about 10 bytes per non-zero next to the CSR; it is rebuilt when k moves to the other k-tile width (8 columns
+// for k <= 8) or to fewer k-tiles than CTAs share a chunk. spmm_tune_set("tiled", 0) or an explicit
+// spmm_csr_build_tiles(A, 0, 0) keeps the CSR kernels. Failure to build is not an error: the CSR kernels stay in charge.
+static void auto_tile_layout(spmm_csr_t A, int k)
+{
+    if (A->tl_auto && A->tl_T != 0 && (A->tl_ksplit > std::max(1, (k + 15) / 16) || (A->tl_kt == 8) != (k <= 8)))
+    {
+        free_tiles(A);
+        A->tl_tried = false;
+    }
+    if (A->tl_tried || A->tl_T != 0 || tuning().tiled == 0 || k < 4 || k % 2 != 0 || A->nnz < 200000 || A->nnz > (64ll << 20))
+        return;
+    A->tl_tried = true;
+    const int saved = tuning().tiled_ksplit, saved_kt = tuning().tiled_kt;
+    if (saved == 0)
+        tuning().tiled_ksplit = k >= 64 ? 4 : (k >= 32 ? 2 : 1); // longer chunks shared by several CTAs, one k-tile group each
+    if (saved_kt == 0 && k <= 8)
+        tuning().tiled_kt = 8; // 64-byte window rows: half the bytes staged and read for k <= 8
+    const int brc = spmm_csr_build_tiles(A, -1, 0);
+    tuning().tiled_ksplit = saved;
+    tuning().tiled_kt = saved_kt;
+    A->tl_auto = true;
+    if (brc != SPMM_OK)
+        free_tiles(A);
+}
+
+
 int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, double *d_C, int ldc, int k_begin,
                                  int k_count, int kernel, void *stream)
 {
@@ -468,32 +496,8 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
         A->nnz >= tuning().stream_auto_min_nnz &&
         stream_shape_ok(A, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count))
         return launch_stream(A, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
-    // AUTO builds the tile layout the first time a multiply can use it (k >= 8, even, mid-sized matrix with
-    // regular rows): one-off, a few milliseconds, 16 bytes per non-zero next to the CSR. spmm_tune_set("tiled", 0)
-    // or an explicit spmm_csr_build_tiles(A, 0, 0) keeps the CSR kernels.
-    if (kernel == SPMM_KERNEL_AUTO && A->tl_auto && A->tl_T != 0 &&
-        (A->tl_ksplit > std::max(1, (k_count + 15) / 16) || (A->tl_kt == 8) != (k_count <= 8)))
-    {
-        free_tiles(A); // built for a wider k (long chunks would leave SMs idle) or for the other k-tile width: build again for this k
-        A->tl_tried = false;
-    }
-    if (kernel == SPMM_KERNEL_AUTO && !A->tl_tried && A->tl_T == 0 && tuning().tiled != 0 && k_count >= 4 &&
-        k_count % 2 == 0 && A->nnz >= 200000 && A->nnz <= (64ll << 20))
-    {
-        A->tl_tried = true;
-        // many k-tiles: longer chunks shared by several CTAs (one k-tile group each), fewer window warm-ups
-        const int saved = tuning().tiled_ksplit, saved_kt = tuning().tiled_kt;
-        if (saved == 0)
-            tuning().tiled_ksplit = k_count >= 64 ? 4 : (k_count >= 32 ? 2 : 1);
-        if (saved_kt == 0 && k_count <= 8)
-            tuning().tiled_kt = 8; // 64-byte window rows: half the bytes staged and read for k <= 8
-        const int brc = spmm_csr_build_tiles(A, -1, 0);
-        tuning().tiled_ksplit = saved;
-        tuning().tiled_kt = saved_kt;
-        A->tl_auto = true;
-        if (brc != SPMM_OK)
-            free_tiles(A); // not fatal: the CSR kernels stay in charge
-    }
+    if (kernel == SPMM_KERNEL_AUTO)
+        auto_tile_layout(A, k_count);
     return launch_rows(A, 0, A->n_rows, 0, A->nnz, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count,
                        kernel == SPMM_KERNEL_ROWS ? 0 : (kernel == SPMM_KERNEL_AUTO ? 1 : kernel), s);
 }
@@ -526,18 +530,8 @@ int spmm_multiply_scatter_device(spmm_csr_t A, const double *d_B, int k, int n_d
     double *d_C = d_C_list[0];
     if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)
         return launch_merge(A, 0, A->n_rows, 0, A->nnz, 0, d_B, k, d_C, k, k, s, &x);
-    if (kernel == SPMM_KERNEL_AUTO && !A->tl_tried && A->tl_T == 0 && tuning().tiled != 0 && k >= 8 && k % 2 == 0 &&
-        A->nnz >= 200000 && A->nnz <= (64ll << 20))
-    {
-        A->tl_tried = true;
-        const int saved = tuning().tiled_ksplit;
-        if (saved == 0)
-            tuning().tiled_ksplit = k >= 64 ? 4 : (k >= 32 ? 2 : 1);
-        const int brc = spmm_csr_build_tiles(A, -1, 0);
-        tuning().tiled_ksplit = saved;
-        if (brc != SPMM_OK)
-            free_tiles(A);
-    }
+    if (kernel == SPMM_KERNEL_AUTO)
+        auto_tile_layout(A, k);
     return launch_rows(A, 0, A->n_rows, 0, A->nnz, 0, d_B, k, d_C, k, k,
                        kernel == SPMM_KERNEL_ROWS ? 0 : (kernel == SPMM_KERNEL_AUTO ? 1 : kernel), s, &x);
 }
