@@ -65,6 +65,10 @@ int cached_bounds(const spmm_csr_s *A, int kind, int grid, cudaStream_t stream, 
         SPMM_CUDA(cudaMalloc(&d, sizeof(int) * ((size_t)grid + 1)));
         fill(d);
         cudaError_t e = cudaGetLastError();
+        // one-off per (matrix, grid): finished before the caller launches anything — kernels launched with programmatic
+        // dependent launch read their cuts before they wait for the kernels ahead of them in the stream
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess)
         {
             cudaFree(d);
@@ -72,7 +76,6 @@ int cached_bounds(const spmm_csr_s *A, int kind, int grid, cudaStream_t stream, 
         }
         it = A->bounds.emplace(key, d).first;
     }
-    (void)stream;
     *out = it->second;
     return SPMM_OK;
 }
@@ -250,6 +253,7 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "host.pipe") t.host_pipe = value;
     else if (k == "tiled.prefetch") t.tiled_prefetch = value;
     else if (k == "tiled.group") t.tiled_group = value;
+    else if (k == "tiled.pdl") t.tiled_pdl = value;
     else if (k == "tiled.stride") t.tiled_stride = value;
     else if (k == "stream") t.stream = value;
     else if (k == "stream.tile") t.stream_tile = value;

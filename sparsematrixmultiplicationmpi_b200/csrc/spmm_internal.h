@@ -72,6 +72,7 @@ struct Tuning
     int host_slabs = 0;     // host-buffer multiply: k-slabs in the PCIe pipeline (0 auto, 1 none)
     int host_pipe = 0;      // host-buffer multiply: row-block pipeline for banded matrices (0 off, 1 always, -1 when its estimate beats the k-slabs);
                             // off by default: measured 1.94 ms against 1.82 ms for two k-slabs on cfg2 k=64 — both directions together cap at ~65 GB/s on this host
+    int tiled_pdl = 1;      // launch: programmatic dependent launch of the tiled kernel (0 off)
     int tiled_group = 0;    // build: tiles one far-band apart walked in turn, this many bands per group (0 auto = 2, 1 off)
     int tiled_stride = 0;   // build: far-band distance in rows (0 = detect from the matrix)
     int tiled_prefetch = -1; // launch: tiles ahead whose blob is prefetched into L2 (-1 auto)

@@ -355,6 +355,9 @@ __global__ void __launch_bounds__(THREADS, SWEEP ? 1 : min_blocks(NV, W, U, 1, T
 
     const RowClip rp{a.rowptr, a.nnz_lo, a.nnz_hi};
     __shared__ int s_chunk[2];
+    // programmatic dependent launch (no-ops without the launch attribute): the next kernel of the stream may start its
+    // prologue as this grid drains; B is read and C written only after the grids before this one have completed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // Large matrices: row tiles dealt round-robin, so that at any moment all CTAs of the grid work
     // inside one window of grid*tile_rows consecutive rows and the B rows they share stay in L2
     // (one far-apart chunk per CTA would keep hundreds of disjoint B windows alive at once).
@@ -388,6 +391,7 @@ __global__ void __launch_bounds__(THREADS, SWEEP ? 1 : min_blocks(NV, W, U, 1, T
             bulk_prefetch_l2((const char *)a.B + b0, min(share, (size_t)a.b_bytes - b0), threadIdx.x, THREADS);
     }
 
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31;
     const int lt = lane % T; // lane inside the team
     const int g = lt / KL;   // which of the NP concurrent non-zeros

@@ -84,7 +84,24 @@ int launch_rows_full(const spmm_csr_s *A, const SpmmArgs &args, int tiles, int d
         if (rc)
             return rc;
     }
-    kern<<<dim3((unsigned)grid, (unsigned)tiles), THREADS, 0, stream>>>(a2);
+    // programmatic dependent launch: the kernel's prologue (CTA cuts, row extents, L2 prefetches) may run under the tail of the
+    // kernel before it in the stream; it executes griddepcontrol.wait before it reads B or writes C (spmm_kernels.cuh)
+    if (tn.tiled_pdl != 0)
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid, (unsigned)tiles);
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SPMM_CUDA(cudaLaunchKernelEx(&cfg, kern, a2));
+    }
+    else
+        kern<<<dim3((unsigned)grid, (unsigned)tiles), THREADS, 0, stream>>>(a2);
     SPMM_CUDA(cudaGetLastError());
     return SPMM_OK;
 }

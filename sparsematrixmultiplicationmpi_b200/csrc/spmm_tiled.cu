@@ -676,6 +676,10 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
     const int D = a.depth;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Programmatic dependent launch: the next multiply of the stream may place its CTAs as ours retire and run its prologue
+    // (barriers, tile descriptors, the first value/id blob — all derived from A) under our tail; everything that touches
+    // B or C waits for the grids before it (griddepcontrol.wait below). Launched without the attribute both are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0)
     {
         for (int i = 0; i < D; ++i)
@@ -799,6 +803,8 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
                                  : "memory");
                 }
             }
+            if (w == 0)
+                asm volatile("griddepcontrol.wait;" ::: "memory"); // B may be the result of the kernel before this one
             if (!T_NO_STAGE && pw + NPW * lane < n_loads)
                 tma_box(s_slab + (unsigned)m.ld.y * box_bytes, &box_map, k0, m.ld.x, bar);
             for (int i = pw + NPW * (lane + 32); !T_NO_STAGE && i < n_loads; i += NPW * 32) // more than NPW*32 boxes: rare
@@ -871,6 +877,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
 
     long long q_wait = 0, q_main = 0, q_t0 = TCLK();
     int st = 0, use = 0;
+    asm volatile("griddepcontrol.wait;" ::: "memory"); // C may still be read (as its B) by the kernel before this one
     for (int w = 0; cur.c < a.n_chunks; ++w, work_next(cur))
     {
         const long long c0 = TCLK();
@@ -1177,7 +1184,22 @@ int launch_tiled_t(const spmm_csr_s *A, const double *d_B, long long ldb, double
         SPMM_CUDA(cudaMalloc(&d_prof, sizeof(long long) * 12 * 1024));
     a.prof = d_prof;
 #endif
-    kern<<<grid, (NCW + NPW) * 32, m.total, stream>>>(a, box_map, row_map);
+    if (tuning().tiled_pdl != 0)
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)((NCW + NPW) * 32));
+        cfg.dynamicSmemBytes = m.total;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SPMM_CUDA(cudaLaunchKernelEx(&cfg, kern, a, box_map, row_map));
+    }
+    else
+        kern<<<grid, (NCW + NPW) * 32, m.total, stream>>>(a, box_map, row_map);
     SPMM_CUDA(cudaGetLastError());
 #if TPROF
     if (++prof_calls == 20)

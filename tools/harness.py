@@ -99,7 +99,7 @@ def run_variants(name, sets, k, variants, iters, emit, nnz, n_rows, extra=None):
 
 
 def variant_list(k, full):
-    v = [("auto", "auto", {}), ("rows(auto shape)", "rows", {}), ("merge", "merge", {})]
+    v = [("auto", "auto", {}), ("auto pdl=0", "auto", {"tiled.pdl": 0}), ("rows(auto shape)", "rows", {}), ("merge", "merge", {})]
     if k in (1, 2, 4, 8):
         v.append(("stream", "stream", {}))
         v += [(f"stream tile={t}", "stream", {"stream.tile": t}) for t in (256, 512, 1024, 2048, 4096, 8192) if t * k * 8 <= 96 * 1024]
