@@ -223,17 +223,12 @@ def main():
     host = first.download()
     sets = []
     for s in range(OPERAND_SETS):
-        A = first if s == 0 else spmm.DeviceCSR.from_host(host, local_rank, 0)
-        if args.kernel == "rowblock":
-            A.build_rowblocks(2)
-        elif args.kernel == "packed":
-            A.build_packed(1, 8)
-        elif args.kernel in ("auto", "tiled"):
+        A = first if s == 0 else spmm.DeviceCSR.from_host(host, local_rank)
+        if args.kernel in ("auto", "tiled"):
             A.build_tiles(-1, 0, k)  # what AUTO does by itself on its first k>=16 multiply; done here so it is outside any timing
         Bd = torch.randint(1, 101, (n, k), device=dev).double()
         Cd = torch.empty((n, k), dtype=torch.float64, device=dev)
         sets.append((A, Bd, Cd))
-    rb = sets[0][0].rowblock_info()
     tiles = sets[0][0].tile_info()
     launches_per_step = 2 if (args.kernel == "merge") else 1
 
@@ -278,9 +273,8 @@ def main():
                 "traffic": recorded_traffic(k), "peak_kind": peak_kind, "algorithmic_bytes_per_launch": abytes,
                 "frac_of_8TBs_nominal": achieved / 8000.0,
                 "kernel": "spmm_tiled_kernel" if tiles["rows_per_tile"] and k >= 8 and k % 2 == 0 and args.kernel in ("auto", "tiled")
-                else "spmm_rowblock_kernel" if rb["rows_per_block"] and args.kernel in ("auto", "rowblock")
                 else ("spmm_merge_kernel" if args.kernel == "merge" else "spmm_rows_kernel"),
-                "tiles": tiles, "rowblock": rb}
+                "tiles": tiles}
 
     # ---- e2e: the reference-shaped host entry point, pinned host buffers, copies inside the timed region ----
     Bh = torch.randint(1, 101, (n, k)).double().pin_memory()

@@ -37,11 +37,8 @@ enum spmm_kernel
     SPMM_KERNEL_AUTO = 0,
     SPMM_KERNEL_ROWS = 1,  /* (sub-)warp-per-row teams over contiguous row chunks */
     SPMM_KERNEL_MERGE = 2, /* nnz-balanced merge-path with deterministic carry fix-up */
-    SPMM_KERNEL_ROWBLOCK = 3, /* R consecutive rows per team over the union of their columns (needs spmm_csr_build_rowblocks) */
-    SPMM_KERNEL_PACKED = 4,   /* warp-packed coalesced A stream (needs spmm_csr_build_packed) */
-    SPMM_KERNEL_STAGED = 5,   /* CSR rows with the id/value stream staged through shared memory by cp.async (k multiple of 16, rows <= 2048 long) */
+    /* ids 3, 4, 5 and 7 belonged to experimental layouts that never won a regime (profiles/r1_union.md); retired */
     SPMM_KERNEL_TILED = 6,    /* row tiles whose B rows are staged in shared memory by TMA (needs spmm_csr_build_tiles; even k) */
-    SPMM_KERNEL_UNION = 7,    /* blocks of 2 or 4 rows over the union of their columns, B rows staged by TMA gather4 (needs spmm_csr_build_union; even k) */
     SPMM_KERNEL_STREAM = 8    /* k = 1, 2, 4, 8: CSR arrays streamed in nnz order, rows reduced from shared memory; bit-identical to the reference's mul-then-add (spmm_stream.cu) */
 };
 
@@ -97,22 +94,7 @@ int spmm_csr_download(spmm_csr_t A, int *rowptr, int *colidx, double *vals);
 /* Row-length schedule: bins[0..7] = rows with length 0, 1-2, 3-4, 5-8, 9-16, 17-32, 33-256, >256. */
 int spmm_csr_schedule(spmm_csr_t A, long long bins[8], int *max_row_len, double *mean_row_len,
                       int *auto_kernel);
-/* Optional second layout of the same matrix for large k: row blocks of R consecutive rows
- * with the union of their column lists (spmm_rowblock.cu). rows_per_block:
- * 2 or 4 = build it; 0 = drop it; -1 = build the widest one whose zero fill stays modest,
- * or none. The CSR arrays are untouched. Needs ascending column ids inside every row
- * (what readMatrixMarketFile produces, utils.cpp:156-159); otherwise SPMM_ERR_UNSUPPORTED. */
-int spmm_csr_build_rowblocks(spmm_csr_t A, int rows_per_block);
-int spmm_csr_rowblock_info(spmm_csr_t A, int *rows_per_block, long long *union_entries, double *fill_ratio);
-/* Optional third layout: the A stream re-laid per warp ("SELL-4-4": slices of 32/lanes_per_row
- * consecutive rows — or row blocks of 2 rows when rows_per_unit = 2, which needs
- * spmm_csr_build_rowblocks(A, 2) first — in groups of 4 steps, ids as int4, values as double2,
- * padded with id -1) so a warp reads it as one coalesced stream (spmm_packed.cu).
- * rows_per_unit 0 drops it. lanes_per_row: 8 or 16. Used by AUTO for whole-matrix multiplies
- * whose k is a multiple of 2*lanes_per_row. */
-int spmm_csr_build_packed(spmm_csr_t A, int rows_per_unit, int lanes_per_row);
-int spmm_csr_packed_info(spmm_csr_t A, int *rows_per_unit, int *lanes_per_row, long long *slots, double *fill_ratio);
-/* Optional fourth layout, the one AUTO prefers for even k >= 4 when neighbouring rows share columns:
+/* Optional second layout next to the CSR, the one AUTO prefers for even k >= 4 when neighbouring rows share columns:
  * tiles of rows_per_tile consecutive rows walked in order by one CTA that keeps a window of B-row
  * boxes (box_rows consecutive rows of B each, brought in by one TMA box copy) in shared memory;
  * non-zeros re-encoded as 16-byte records addressing that window, stragglers staged row by row
@@ -126,18 +108,6 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows);
  * share of the non-zeros whose B row is staged on its own. Zeros when no layout is built. */
 int spmm_csr_tile_info(spmm_csr_t A, int *rows_per_tile, int *box_rows, int *window_slots, int *max_records,
                        double *reuse, double *single_fraction);
-/* Optional fifth layout (spmm_union.cu): rows_per_block (2 or 4; -1 = 2) consecutive rows are walked
- * over the ascending union of their column lists so that one B row read from shared memory feeds several rows from
- * registers; B rows are staged one by one (TMA gather4) in a least-recently-used window, the k-tile is 32 columns.
- * `k` is the column count the layout is cut for (chunks = SMs / k-tiles). 0 drops the layout. Built on the host from a
- * copy of the CSR arrays (one-off per matrix); fails with SPMM_ERR_UNSUPPORTED on rows that are not sorted by column or
- * longer than 16,320 union entries. B must be finite (absent union entries are 0.0 values). Serves
- * SparseMatrixFatVectorMultiply.cpp:17-28. */
-int spmm_csr_build_union(spmm_csr_t A, int rows_per_block, int k);
-/* union_per_nnz = B-row reads per non-zero; padding = slot steps per union entry; staged_per_row = B rows brought into
- * shared memory per matrix row and pass. Zeros when no layout is built. */
-int spmm_csr_union_info(spmm_csr_t A, int *rows_per_block, int *k_tile, int *window_rows, double *union_per_nnz,
-                        double *padding, double *staged_per_row);
 /* Sub-matrix A[:, col_begin:col_end) with local column ids (column-block strategy,
  * north_star reading of sparseMatrixFatVectorMultiplyColumnWise). Built on the device. */
 int spmm_csr_column_block(spmm_csr_t A, int col_begin, int col_end, spmm_csr_t *out);
@@ -226,7 +196,7 @@ int spmm_gen_fat_vector_device(int device, double *d_out, long long n_elems, lon
                                unsigned long long seed, void *stream);
 
 /* Measurement knob (not needed for correct results): override the automatic team shape.
- * keys: rows.kl rows.nv rows.np rows.unroll rows.vec rows.ctas_per_sm merge.items rowblock tiled tiled.kt tiled.ncw tiled.unroll tiled.thr tiled.chunk tiled.depth tiled.pool tiled.ns tiled.ksplit tiled.npw tiled.prefetch host.slabs reset */
+ * keys: rows.kl rows.nv rows.np rows.unroll rows.vec rows.ctas_per_sm merge.items tiled tiled.kt tiled.ncw tiled.unroll tiled.thr tiled.chunk tiled.depth tiled.pool tiled.ns tiled.ksplit tiled.npw tiled.prefetch host.slabs reset */
 int spmm_tune_set(const char *key, int value);
 
 #ifdef __cplusplus

@@ -13,9 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SPMM_B200_LIB") or os.path.join(HERE, "libspmm_b200.so")  # override: diagnostic builds only
 
 SPMM_OK, SPMM_ERR_INVALID, SPMM_ERR_CUDA, SPMM_ERR_NOMEM, SPMM_ERR_UNSUPPORTED = range(5)
-KERNEL_AUTO, KERNEL_ROWS, KERNEL_MERGE, KERNEL_ROWBLOCK, KERNEL_PACKED, KERNEL_STAGED, KERNEL_TILED, KERNEL_UNION, KERNEL_STREAM = 0, 1, 2, 3, 4, 5, 6, 7, 8
-KERNELS = {"auto": KERNEL_AUTO, "rows": KERNEL_ROWS, "merge": KERNEL_MERGE, "rowblock": KERNEL_ROWBLOCK,
-           "packed": KERNEL_PACKED, "staged": KERNEL_STAGED, "tiled": KERNEL_TILED, "union": KERNEL_UNION, "stream": KERNEL_STREAM}
+KERNEL_AUTO, KERNEL_ROWS, KERNEL_MERGE, KERNEL_TILED, KERNEL_STREAM = 0, 1, 2, 6, 8
+KERNELS = {"auto": KERNEL_AUTO, "rows": KERNEL_ROWS, "merge": KERNEL_MERGE, "tiled": KERNEL_TILED, "stream": KERNEL_STREAM}
 
 
 class SpmmError(RuntimeError):
@@ -55,14 +54,8 @@ PROTOTYPES = {
     "spmm_csr_download": (_i, [_p, _p, _p, _p]),
     "spmm_csr_schedule": (_i, [_p, _pll, _pi, _pd, _pi]),
     "spmm_csr_column_block": (_i, [_p, _i, _i, C.POINTER(_p)]),
-    "spmm_csr_build_rowblocks": (_i, [_p, _i]),
-    "spmm_csr_rowblock_info": (_i, [_p, _pi, _pll, _pd]),
-    "spmm_csr_build_packed": (_i, [_p, _i, _i]),
-    "spmm_csr_packed_info": (_i, [_p, _pi, _pi, _pll, _pd]),
     "spmm_csr_build_tiles": (_i, [_p, _i, _i]),
     "spmm_csr_tile_info": (_i, [_p, _pi, _pi, _pi, _pi, _pd, _pd]),
-    "spmm_csr_build_union": (_i, [_p, _i, _i]),
-    "spmm_csr_union_info": (_i, [_p, _pi, _pi, _pi, _pd, _pd, _pd]),
     "spmm_multiply_device": (_i, [_p, _p, _i, _p, _i, _p]),
     "spmm_multiply_scatter_device": (_i, [_p, _p, _i, _i, C.POINTER(_p), _i, _p]),
     "spmm_multiply_strided_device": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _p]),

@@ -136,7 +136,11 @@ int build_schedule(spmm_csr_s *A, cudaStream_t stream)
     {
         unsigned long long *d_bins = nullptr;
         SPMM_CUDA(cudaMalloc(&d_bins, 9 * sizeof(unsigned long long)));
-        SPMM_CUDA(cudaMemsetAsync(d_bins, 0, 9 * sizeof(unsigned long long), stream));
+        if (cudaError_t me = cudaMemsetAsync(d_bins, 0, 9 * sizeof(unsigned long long), stream); me != cudaSuccess)
+        {
+            cudaFree(d_bins);
+            SPMM_CUDA(me);
+        }
         const int threads = 256;
         const int blocks = (int)std::min<long long>(((long long)A->n_rows + threads - 1) / threads,
                                                     (long long)device_props(A->device).sm_count * 8);
@@ -181,7 +185,7 @@ int make_handle(int device, int n_rows, int n_cols, long long nnz, spmm_csr_s **
 int alloc_arrays(spmm_csr_s *A)
 {
     SPMM_CUDA(cudaMalloc(&A->d_rowptr, sizeof(int) * ((size_t)A->n_rows + 1)));
-    // + 8 elements: the staged kernel copies whole 16-byte pieces and may touch up to 3 ids / 1 value past nnz
+    // + 8 elements: vector loads of the last ids / values may touch the padding past nnz
     SPMM_CUDA(cudaMalloc(&A->d_colidx, sizeof(int) * ((size_t)std::max<long long>(A->nnz, 1) + 8)));
     SPMM_CUDA(cudaMalloc(&A->d_vals, sizeof(double) * ((size_t)std::max<long long>(A->nnz, 1) + 8)));
     A->owns = true;
@@ -233,11 +237,9 @@ int spmm_tune_set(const char *key, int value)
     if (k == "rows.np") t.rows_np = value;
     else if (k == "rows.kl") t.rows_kl = value;
     else if (k == "rows.nv") t.rows_nv = value;
-    else if (k == "rowblock") t.rowblock = value;
     else if (k == "rows.sweep") t.rows_sweep = value;
     else if (k == "rows.prefetch") t.rows_prefetch = value;
     else if (k == "rows.tile") t.rows_tile = value;
-    else if (k == "rows.staged") t.rows_staged = value;
     else if (k == "tiled") t.tiled = value;
     else if (k == "tiled.kt") t.tiled_kt = value;
     else if (k == "tiled.ncw") t.tiled_ncw = value;
@@ -259,11 +261,6 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "stream.tile") t.stream_tile = value;
     else if (k == "stream.kmax") t.stream_auto_kmax = value;
     else if (k == "stream.min_nnz") t.stream_auto_min_nnz = value;
-    else if (k == "stream.persist") t.stream_persist = value;
-    else if (k == "union.slots") t.union_slots = value;
-    else if (k == "union.split") t.union_split = value;
-    else if (k == "union.auto") t.union_auto = value;
-    else if (k == "union.debug") t.union_debug = value;
     else if (k == "rows.threads") t.rows_threads = value;
     else if (k == "rows.unroll") t.rows_unroll = value;
     else if (k == "rows.vec") t.rows_vec = value;
@@ -362,10 +359,7 @@ int spmm_csr_destroy(spmm_csr_t A)
         cudaFree(A->d_colidx);
         cudaFree(A->d_vals);
     }
-    free_rowblocks(A);
-    free_packed(A);
     free_tiles(A);
-    free_union(A);
     drop_bounds(A, -1);
     cudaFree(A->d_B);
     cudaFree(A->d_C);
@@ -379,8 +373,10 @@ int spmm_csr_destroy(spmm_csr_t A)
     {
         cudaStreamDestroy(A->stream_up);
         cudaStreamDestroy(A->stream_down);
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 32; ++i)
         {
+            if (!A->ev_up[i])
+                continue;
             cudaEventDestroy(A->ev_up[i]);
             cudaEventDestroy(A->ev_done[i]);
         }
@@ -475,7 +471,9 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
     SPMM_REQUIRE(d_B != nullptr || A->nnz == 0, "d_B is NULL");
     SPMM_CUDA(cudaSetDevice(A->device));
     cudaStream_t s = (cudaStream_t)stream;
-    SPMM_REQUIRE(kernel >= SPMM_KERNEL_AUTO && kernel <= SPMM_KERNEL_STREAM, "unknown kernel id");
+    SPMM_REQUIRE(kernel == SPMM_KERNEL_AUTO || kernel == SPMM_KERNEL_ROWS || kernel == SPMM_KERNEL_MERGE ||
+                     kernel == SPMM_KERNEL_TILED || kernel == SPMM_KERNEL_STREAM,
+                 "unknown kernel id");
     if (kernel == SPMM_KERNEL_STREAM)
     {
         SPMM_REQUIRE(stream_shape_ok(A, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count),
@@ -483,15 +481,6 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
         return launch_stream(A, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
     }
     SPMM_REQUIRE(kernel != SPMM_KERNEL_TILED || A->tl_T != 0, "tiled kernel requested but spmm_csr_build_tiles was not called (or found no fitting tile shape)");
-    if (kernel == SPMM_KERNEL_UNION)
-    {
-        SPMM_REQUIRE(A->un != nullptr, "union kernel requested but spmm_csr_build_union was not called (or the layout does not fit)");
-        SPMM_REQUIRE(k_begin % 2 == 0 && union_shape_ok(A, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count),
-                     "union kernel: needs even k, even leading dimensions and 16-byte aligned B and C");
-        return launch_union(A, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
-    }
-    SPMM_REQUIRE(kernel != SPMM_KERNEL_PACKED || A->pk_R != 0, "packed kernel requested but spmm_csr_build_packed was not called");
-    SPMM_REQUIRE(kernel != SPMM_KERNEL_ROWBLOCK || A->rb_R != 0, "row-block kernel requested but spmm_csr_build_rowblocks was not called");
     if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)
         return launch_merge(A, 0, A->n_rows, 0, A->nnz, 0, d_B + k_begin, ldb, d_C + k_begin, ldc, k_count, s);
     // k = 1 on matrices of 4 M non-zeros and more: streamed in nnz order (3.1 against 2.4 TB/s at 10.5 M non-zeros, and bit-identical to

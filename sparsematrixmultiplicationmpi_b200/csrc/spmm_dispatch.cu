@@ -98,39 +98,6 @@ int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_l
                 return SPMM_ERR_UNSUPPORTED;
             }
         }
-        if (extra && extra->n)
-            derived = 0; // the other derived layouts store to one destination only
-        Shape ps = s;
-        if (A->pk_R && A->pk_kl != s.kl && (kc % (2 * A->pk_kl) == 0) && s.w == 2)
-        {
-            // the packed layout fixes the lanes per row: re-derive nv / tiles for it
-            const int kq = kc / 2;
-            ps.kl = A->pk_kl;
-            ps.nv = t.rows_nv > 0 ? t.rows_nv : std::min(4, std::max(1, kq / ps.kl));
-            while (ps.nv > 1 && kq % (ps.kl * ps.nv))
-                ps.nv >>= 1;
-            ps.tiles = kq / (ps.kl * ps.nv);
-        }
-        if (derived == 5 || (derived == 1 && t.rows_staged > 0))
-        {
-            // staged kernel: 8 lanes per row; widest nv that tiles k
-            const int kq = kc / 2;
-            int nv = t.rows_nv > 0 ? t.rows_nv : 4;
-            while (nv > 1 && (kc % 2 || kq % (8 * nv)))
-                nv >>= 1;
-            const int tl = (kc % 2 == 0 && kq % (8 * nv) == 0) ? kq / (8 * nv) : 0;
-            if (tl > 0 && staged_shape_ok(A, s.w, 8, nv, tl, kc))
-                return launch_staged(A, nv, tl, d_B, ldb, d_C, ldc, stream);
-            if (derived == 5)
-            {
-                set_error("staged kernel: shape, alignment or max row length not supported");
-                return SPMM_ERR_UNSUPPORTED;
-            }
-        }
-        if ((derived == 1 || derived == 4) && packed_shape_ok(A, ps.w, ps.kl, ps.nv, ps.tiles, kc))
-            return launch_packed(A, ps.nv, ps.tiles, d_B, ldb, d_C, ldc, stream);
-        if ((derived == 1 || derived == 3) && A->rb_R && t.rowblock != 0 && rowblock_shape_ok(s.w, s.kl, s.nv, s.tiles, kc))
-            return launch_rowblock(A, s.w, s.kl, s.nv, s.tiles, d_B, ldb, d_C, ldc, stream);
     }
     int np = 1;
     if (s.nv == 1)

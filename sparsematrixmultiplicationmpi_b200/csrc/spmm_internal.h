@@ -54,10 +54,8 @@ struct Tuning
     int merge_items = 0;    // merge-path items per team
     int rows_sweep = 0;     // 1: one CTA per SM walks the column tiles itself (L1-resident window)
     int rows_threads = 0;   // sweep kernels: 512 or 1024 threads
-    int rows_staged = 0;    // 1: AUTO may pick the smem-staged row kernel
     int rows_tile = 0;      // 0 auto, > 0 rows per round-robin tile, -1 never tile (one chunk per CTA)
     int rows_prefetch = -1; // -1 auto; bit0 A chunk, bit1 B share: TMA prefetch into L2 at kernel start
-    int rowblock = -1;      // -1 auto, 0 never use the row-block format, 1 always when built
     int tiled = -1;         // -1 auto, 0 never use the tile layout, 1 always when built
     int tiled_kt = 0;       // tiled kernel: k-tile width (16, 32)
     int tiled_ncw = 0;      // consumer warps (8, 12, 16)
@@ -76,16 +74,10 @@ struct Tuning
     int tiled_group = 0;    // build: tiles one far-band apart walked in turn, this many bands per group (0 auto = 2, 1 off)
     int tiled_stride = 0;   // build: far-band distance in rows (0 = detect from the matrix)
     int tiled_prefetch = -1; // launch: tiles ahead whose blob is prefetched into L2 (-1 auto)
-    int union_slots = 0;    // union layout: slots per item (4: 8-lane teams, 8: 4-lane teams)
-    int union_split = 0;    // union layout: blocks with more union entries are cut into segments of about this length
     int stream = -1;        // -1 auto, 0 AUTO never uses the stream kernel (k = 1, 2, 4, 8)
     int stream_auto_kmax = 1; // AUTO takes the stream kernel up to this k ...
     int stream_auto_min_nnz = 4 << 20; // ... from this many non-zeros (measured: equal to the row kernel at 2.6 M non-zeros, 43 against 56 us at 10.5 M; profiles/r1_stream.md)
-    int stream_persist = 0; // stream kernel: CTAs per SM of the persistent, software-pipelined variant (0 = one CTA per tile, the default:
-                            // the pipelined variant measured the same 18-19 us at k=1, profiles/r1_stream.md)
     int stream_tile = 0;    // stream kernel: non-zeros per tile (0 = 4096 / k)
-    int union_debug = 0;    // diagnostics, wrong results by design (see spmm_union.cu)
-    int union_auto = -1;    // -1 auto, 0 AUTO never builds / uses the union layout
 };
 Tuning &tuning();
 
@@ -96,19 +88,6 @@ struct DeviceProps
 };
 const DeviceProps &device_props(int device);
 
-} // namespace spmm
-
-namespace spmm
-{
-// union layout on the device (spmm_union.cu; built on the host by spmm_union_build.cu)
-struct UnionDev
-{
-    int R = 0, KT = 0, SL = 0, NCW = 0, D = 0, NG = 0, n_chunks = 0, n_items = 0, nkt = 0, ring_bytes = 0, slab_off = 0, drains = 0, maxg = 0, NPW = 4;
-    long long staged_rows = 0, union_entries = 0, slot_steps = 0;
-    unsigned char *d_blob = nullptr;
-    void *d_items = nullptr, *d_gcols = nullptr;
-    int *d_chunk_first = nullptr, *d_gslot = nullptr;
-};
 } // namespace spmm
 
 struct spmm_csr_s
@@ -132,16 +111,6 @@ struct spmm_csr_s
     // row-block pipeline of the host-buffer multiply: block j of C needs the B rows [0, hp_need[j])
     int hp_blocks = 0;
     std::vector<int> hp_cut, hp_need;
-    // row-block union format (spmm_rowblock.cu), optional
-    int rb_R = 0, rb_blocks = 0;
-    long long rb_entries = 0;
-    int *d_blkptr = nullptr, *d_ucol = nullptr;
-    double *d_uval = nullptr;
-    // warp-packed stream layout (spmm_packed.cu), optional
-    int pk_R = 0, pk_kl = 0, pk_slices = 0;
-    long long pk_groups = 0;
-    int *d_sptr = nullptr, *d_pcol = nullptr;
-    double *d_pval = nullptr;
     // B-staged row tiles (spmm_tiled.cu), optional
     int tl_T = 0, tl_BR = 0, tl_tiles = 0, tl_NS = 0, tl_POOL = 0, tl_max_recs = 0, tl_max_blob = 0, tl_chunk = 0, tl_kt = 0, tl_depth = 0, tl_drains = 0, tl_ksplit = 0;
     long long tl_box_rows_loaded = 0, tl_single_rows = 0; // B rows staged per pass over the matrix
@@ -152,10 +121,7 @@ struct spmm_csr_s
     int *d_tsingles = nullptr;
     int *d_torder = nullptr;          // walking order of the tiles (nullptr: as they lie)
     int tl_stride = 0, tl_group = 0;  // detected far-band distance in rows, planes interleaved per super-group
-    // row blocks over union columns with a gather4-staged window (spmm_union.cu), optional
-    spmm::UnionDev *un = nullptr;
-    bool un_tried = false; // AUTO already attempted the lazy build
-    // precomputed CTA cuts per (kind, grid size): kind 0 = rows of the CSR, 1 = row blocks, 2 = packed slices
+    // precomputed CTA cuts per (kind, grid size): kind 0 = rows of the CSR
     mutable std::map<long long, int *> bounds;
     // merge-path scratch (carry rows), grown on demand
     double *d_carry = nullptr;
@@ -169,31 +135,16 @@ namespace spmm
 // rows [row_begin,row_end), each clipped to the non-zero range [nnz_lo,nnz_hi); row c_row0 is stored at d_C[0]
 int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
                 const double *d_B, long long ldb, double *d_C, long long ldc, int kc, int derived,
-                cudaStream_t stream, const struct ExtraDst *extra = nullptr); // derived: 0 CSR row kernel only, 1 best available, 3 row-block, 4 packed, 5 staged, 6 tiled
+                cudaStream_t stream, const struct ExtraDst *extra = nullptr); // derived: 0 CSR row kernel only, 1 best available, 6 tiled
 int launch_merge(spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
                  const double *d_B, long long ldb, double *d_C, long long ldc, int kc, cudaStream_t stream,
                  const struct ExtraDst *extra = nullptr);
-bool rowblock_shape_ok(int w, int kl, int nv, int tiles, int kc);
-int launch_rowblock(const spmm_csr_s *A, int w, int kl, int nv, int tiles, const double *d_B, long long ldb,
-                    double *d_C, long long ldc, cudaStream_t stream);
-void free_rowblocks(spmm_csr_s *A);
-bool packed_shape_ok(const spmm_csr_s *A, int w, int kl, int nv, int tiles, int kc);
-int launch_packed(const spmm_csr_s *A, int nv, int tiles, const double *d_B, long long ldb, double *d_C, long long ldc,
-                  cudaStream_t stream);
-void free_packed(spmm_csr_s *A);
 bool tiled_shape_ok(const spmm_csr_s *A, const double *d_B, long long ldb, const double *d_C, long long ldc, int kc);
 int launch_tiled(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int kc,
                  cudaStream_t stream, const struct ExtraDst *extra = nullptr);
 void free_tiles(spmm_csr_s *A);
-bool union_shape_ok(const spmm_csr_s *A, const double *d_B, long long ldb, const double *d_C, long long ldc, int kc);
-int launch_union(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int kc,
-                 cudaStream_t stream, const struct ExtraDst *extra = nullptr);
-void free_union(spmm_csr_s *A);
 bool stream_shape_ok(const spmm_csr_s *A, const double *d_B, long long ldb, const double *d_C, long long ldc, int kc);
 int launch_stream(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int kc,
-                  cudaStream_t stream);
-bool staged_shape_ok(const spmm_csr_s *A, int w, int kl, int nv, int tiles, int kc);
-int launch_staged(const spmm_csr_s *A, int nv, int tiles, const double *d_B, long long ldb, double *d_C, long long ldc,
                   cudaStream_t stream);
 // CTA cuts cached on the handle; `fill` launches the kernel that computes grid+1 cuts into its argument
 int cached_bounds(const spmm_csr_s *A, int kind, int grid, cudaStream_t stream, const int **out,

@@ -90,137 +90,6 @@ __global__ void __launch_bounds__(ST_TPB)
 }
 
 
-// Persistent variant: a CTA walks tiles blockIdx.x, += gridDim.x and keeps the column/value pairs and the row pointers of
-// its NEXT tile in registers while the current one is gathered, multiplied and reduced, so the three dependent global
-// round trips of a tile (cuts -> col/val -> B) overlap with the work of the previous tile instead of adding up per CTA.
-constexpr int ST_EPT = 8; // non-zeros per thread and tile at most
-
-template <int K>
-__global__ void __launch_bounds__(ST_TPB)
-    spmm_stream_persist_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals,
-                               const double *__restrict__ B, long long ldb, double *__restrict__ C, long long ldc,
-                               const int *__restrict__ cuts, int n_tiles)
-{
-    constexpr int LPE = K >= 4 ? K / 2 : 1;
-    constexpr int W = K / LPE;
-    constexpr int STEP = ST_TPB / LPE; // entries covered by one pass of the CTA
-    extern __shared__ __align__(16) double prod[];
-    const int part = threadIdx.x % LPE, ent = threadIdx.x / LPE;
-    int t = blockIdx.x;
-    if (t >= n_tiles)
-        return;
-    // Three tiles are in flight per CTA: the current one (column/value pairs in c/v), the next one (its extent e0/n and row
-    // range known, its pairs being loaded into c2/v2 while the current one is gathered and reduced) and the one after
-    // (its extent being fetched).
-    struct Ext
-    {
-        int r0, r1, e0, n;
-    };
-    auto extent = [&](int tile) {
-        Ext x = {0, 0, 0, 0};
-        if (tile < n_tiles)
-        {
-            x.r0 = cuts[tile];
-            x.r1 = cuts[tile + 1];
-            x.e0 = rowptr[x.r0];
-            x.n = rowptr[x.r1] - x.e0;
-        }
-        return x;
-    };
-    int c[ST_EPT], c2[ST_EPT];
-    double v[ST_EPT], v2[ST_EPT];
-    int ra = 0, rz = 0, ra2 = 0, rz2 = 0; // row pointers of this thread's first (row, column) item
-    auto load_pairs = [&](const Ext &x, int (&cc)[ST_EPT], double (&vv)[ST_EPT], int &pa, int &pz) {
-#pragma unroll
-        for (int i = 0; i < ST_EPT; ++i)
-        {
-            const int q = ent + i * STEP;
-            cc[i] = 0;
-            vv[i] = 0.0;
-            if (q < x.n)
-            {
-                cc[i] = __ldg(colidx + x.e0 + q);
-                vv[i] = __ldg(vals + x.e0 + q);
-            }
-        }
-        const int r = x.r0 + (int)threadIdx.x / K;
-        if (r < x.r1)
-        {
-            pa = rowptr[r] - x.e0;
-            pz = rowptr[r + 1] - x.e0;
-        }
-    };
-    Ext cur = extent(t), nxt = extent(t + gridDim.x);
-    load_pairs(cur, c, v, ra, rz);
-    while (true)
-    {
-        // gathers of the current tile
-        double2 b[ST_EPT];
-#pragma unroll
-        for (int i = 0; i < ST_EPT; ++i)
-        {
-            b[i] = make_double2(0.0, 0.0);
-            if (ent + i * STEP < cur.n)
-            {
-                const double *bp = B + (long long)c[i] * ldb + part * W;
-                if constexpr (W == 2)
-                    b[i] = __ldg(reinterpret_cast<const double2 *>(bp));
-                else
-                    b[i].x = __ldg(bp);
-            }
-        }
-        // pairs of the next tile and extent of the one after: issued before anything waits for the gathers
-        const bool more = t + (int)gridDim.x < n_tiles;
-        if (more)
-            load_pairs(nxt, c2, v2, ra2, rz2);
-        const Ext after = extent(t + 2 * (int)gridDim.x);
-        // products of the current tile into shared memory
-#pragma unroll
-        for (int i = 0; i < ST_EPT; ++i)
-        {
-            const int q = ent + i * STEP;
-            if (q < cur.n)
-            {
-                if constexpr (W == 2)
-                    *reinterpret_cast<double2 *>(prod + (size_t)q * K + part * 2) =
-                        make_double2(__dmul_rn(v[i], b[i].x), __dmul_rn(v[i], b[i].y));
-                else
-                    prod[(size_t)q * K + part] = __dmul_rn(v[i], b[i].x);
-            }
-        }
-        __syncthreads();
-        const int items = (cur.r1 - cur.r0) * K;
-        for (int idx = threadIdx.x; idx < items; idx += ST_TPB)
-        {
-            const int r = cur.r0 + idx / K, j = idx % K;
-            int a = ra, z = rz;
-            if (idx >= ST_TPB) // more (row, column) items than threads: empty rows in the tile
-            {
-                a = rowptr[r] - cur.e0;
-                z = rowptr[r + 1] - cur.e0;
-            }
-            double sum = 0.0;
-            for (int q = a; q < z; ++q)
-                sum = __dadd_rn(sum, prod[(size_t)q * K + j]);
-            C[(long long)r * ldc + j] = sum;
-        }
-        if (!more)
-            break;
-        t += gridDim.x;
-        cur = nxt;
-        nxt = after;
-#pragma unroll
-        for (int i = 0; i < ST_EPT; ++i)
-        {
-            c[i] = c2[i];
-            v[i] = v2[i];
-        }
-        ra = ra2;
-        rz = rz2;
-        __syncthreads(); // the products of this tile have been read: the buffer may be overwritten
-    }
-}
-
 template <int K>
 int launch_stream_t(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int cap,
                     const int *cuts, int n_tiles, cudaStream_t stream)
@@ -236,17 +105,6 @@ int launch_stream_t(const spmm_csr_s *A, const double *d_B, long long ldb, doubl
             SPMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = smem;
         }
-    }
-    constexpr int LPE = K >= 4 ? K / 2 : 1;
-    if (cap <= ST_EPT * (ST_TPB / LPE) && tuning().stream_persist > 0)
-    {
-        // a tile fits the registers of a CTA: persistent, software-pipelined variant
-        const int per_sm = tuning().stream_persist;
-        const int grid = std::max(1, std::min(n_tiles, device_props(A->device).sm_count * per_sm));
-        spmm_stream_persist_kernel<K><<<grid, ST_TPB, smem, stream>>>(A->d_rowptr, A->d_colidx, A->d_vals, d_B, ldb, d_C,
-                                                                       ldc, cuts, n_tiles);
-        SPMM_CUDA(cudaGetLastError());
-        return SPMM_OK;
     }
     kern<<<n_tiles, ST_TPB, smem, stream>>>(A->d_rowptr, A->d_colidx, A->d_vals, d_B, ldb, d_C, ldc, cuts, cap);
     SPMM_CUDA(cudaGetLastError());

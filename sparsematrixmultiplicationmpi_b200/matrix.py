@@ -66,16 +66,13 @@ class DeviceCSR:
 
     # -- construction --
     @classmethod
-    def from_host(cls, m: SparseMatrix, device: int = 0, rowblocks: int = 0) -> "DeviceCSR":
+    def from_host(cls, m: SparseMatrix, device: int = 0) -> "DeviceCSR":
         if m.rowPtr.size != m.numRows + 1:
             raise ValueError("rowPtr must hold numRows+1 offsets")
         h = C.c_void_p()
         _cabi.check(_cabi.lib().spmm_csr_create_host(device, m.numRows, m.numCols, m.nnz, m.rowPtr.ctypes.data,
                                                      m.colIndices.ctypes.data, m.values.ctypes.data, C.byref(h)))
-        out = cls(h.value)
-        if rowblocks:
-            out.build_rowblocks(rowblocks)
-        return out
+        return cls(h.value)
 
     @classmethod
     def from_coo_host(cls, n_rows, n_cols, rows, cols, vals, symmetric=False, device: int = 0) -> "DeviceCSR":
@@ -133,24 +130,6 @@ class DeviceCSR:
         return {"bins": dict(zip(names, list(bins))), "max_row_len": mx.value, "mean_row_len": mean.value,
                 "auto_kernel": {1: "rows", 2: "merge"}.get(ak.value, str(ak.value))}
 
-    def build_rowblocks(self, rows_per_block: int = -1) -> dict:
-        _cabi.check(_cabi.lib().spmm_csr_build_rowblocks(self.handle, rows_per_block))
-        return self.rowblock_info()
-
-    def rowblock_info(self) -> dict:
-        r, n, f = C.c_int(), C.c_longlong(), C.c_double()
-        _cabi.check(_cabi.lib().spmm_csr_rowblock_info(self.handle, C.byref(r), C.byref(n), C.byref(f)))
-        return {"rows_per_block": r.value, "union_entries": n.value, "fill_ratio": f.value}
-
-    def build_packed(self, rows_per_unit: int = 1, lanes_per_row: int = 8) -> dict:
-        _cabi.check(_cabi.lib().spmm_csr_build_packed(self.handle, rows_per_unit, lanes_per_row))
-        return self.packed_info()
-
-    def packed_info(self) -> dict:
-        r, l, n, f = C.c_int(), C.c_int(), C.c_longlong(), C.c_double()
-        _cabi.check(_cabi.lib().spmm_csr_packed_info(self.handle, C.byref(r), C.byref(l), C.byref(n), C.byref(f)))
-        return {"rows_per_unit": r.value, "lanes_per_row": l.value, "slots": n.value, "fill_ratio": f.value}
-
     def multiply_scatter(self, d_B: int, k: int, d_C_list, kernel: str = "auto", stream: int = 0) -> None:
         """C = A*B stored to every pointer of d_C_list (local and NVLink-mapped peer buffers): the row-wise
         strategy's gather fused into the multiply (spmm_multiply_scatter_device)."""
@@ -181,20 +160,6 @@ class DeviceCSR:
                                                    C.byref(r), C.byref(sf)))
         return {"rows_per_tile": t.value, "box_rows": b.value, "window_slots": ns.value, "max_records": mr.value,
                 "reuse": r.value, "single_fraction": sf.value}
-
-    def build_union(self, rows_per_block: int = -1, k: int = 64) -> dict:
-        """Blocks of 2 or 4 rows over the union of their columns, B rows staged by TMA gather4 (spmm_union.cu);
-        k = the number of B columns the layout is cut for. 0 rows per block drops the layout."""
-        _cabi.check(_cabi.lib().spmm_csr_build_union(self.handle, rows_per_block, k))
-        return self.union_info()
-
-    def union_info(self) -> dict:
-        r, kt, wr = C.c_int(), C.c_int(), C.c_int()
-        u, p, st = C.c_double(), C.c_double(), C.c_double()
-        _cabi.check(_cabi.lib().spmm_csr_union_info(self.handle, C.byref(r), C.byref(kt), C.byref(wr), C.byref(u),
-                                                    C.byref(p), C.byref(st)))
-        return {"rows_per_block": r.value, "k_tile": kt.value, "window_rows": wr.value, "union_per_nnz": u.value,
-                "padding": p.value, "staged_per_row": st.value}
 
     def nnz_range_rows(self, nnz_begin: int, nnz_end: int) -> tuple[int, int]:
         a, b = C.c_int(), C.c_int()

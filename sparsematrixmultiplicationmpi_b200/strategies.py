@@ -63,17 +63,16 @@ def partition_nnz(nnz: int, P: int, r: int) -> tuple[int, int]:
 class CudaCompute:
     """Engine of the product path: CSR shards in HBM, multiply through libspmm_b200.so."""
 
-    def __init__(self, device: int | None = None, kernel: str = "auto", rowblocks: int = 0):
+    def __init__(self, device: int | None = None, kernel: str = "auto"):
         if not torch.cuda.is_available():
             raise RuntimeError("sparsematrixmultiplicationmpi_b200 needs a CUDA device (no CPU fallback)")
         _cabi.lib()  # fail loudly if the extension is not built
         self.index = torch.cuda.current_device() if device is None else device
         self.device = torch.device("cuda", self.index)
         self.kernel = kernel
-        self.rowblocks = rowblocks
 
     def upload(self, m: SparseMatrix) -> DeviceCSR:
-        return DeviceCSR.from_host(m, self.index, self.rowblocks)
+        return DeviceCSR.from_host(m, self.index)
 
     def multiply(self, A: DeviceCSR, B: torch.Tensor, k: int, out: torch.Tensor | None = None) -> torch.Tensor:
         """out[n_rows, k] = A * B[n_cols, k]; contiguous float64 tensors on self.device."""

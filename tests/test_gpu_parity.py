@@ -17,13 +17,13 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-def gpu_multiply(m, B, k, kernel="auto", tune=None, rowblocks=0):
+def gpu_multiply(m, B, k, kernel="auto", tune=None):
     """C = A*B through spmm_multiply_device with device-resident operands."""
     _cabi.tune("reset", 0)
     for key, val in (tune or {}).items():
         _cabi.tune(key, val)
     try:
-        with spmm.DeviceCSR.from_host(m, 0, rowblocks) as A:
+        with spmm.DeviceCSR.from_host(m, 0) as A:
             dB = dev(B)
             dC = torch.full((m.numRows, k), np.nan, dtype=torch.float64, device="cuda")
             A.multiply(dB.data_ptr(), k, dC.data_ptr(), kernel, torch.cuda.current_stream().cuda_stream)
@@ -102,37 +102,6 @@ def test_side_by_side_nonzeros(oracle, np_, k):
     assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
 
 
-@pytest.mark.parametrize("R", [2, 4])
-@pytest.mark.parametrize("k", [8, 16, 32, 64, 128, 256])
-def test_rowblock_kernel(oracle, R, k):
-    rp, ci, va = random_csr(13, 2501, 2501, 20, empty_every=17, positive=True)  # 2501: last block is ragged
-    m = spmm.SparseMatrix(va, ci, rp, 2501, 2501)
-    B = np.random.default_rng(7).integers(1, 101, (2501, k)).astype(np.float64)
-    got = gpu_multiply(m, B, k, "rowblock", rowblocks=R)
-    assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
-    with spmm.DeviceCSR.from_host(m, 0, R) as A:
-        info = A.rowblock_info()
-        assert info["rows_per_block"] == R and 1.0 <= info["fill_ratio"] <= R
-
-
-def test_rowblock_duplicates_and_mixed_sign(oracle, golden_multiply):
-    g = golden_multiply  # golden rows hold duplicated columns and mixed-sign values
-    rp, ci, va, B = g["k8_rowptr"], g["k8_colidx"], g["k8_vals"], g["k8_B"]
-    m = spmm.SparseMatrix(va, ci, rp, len(rp) - 1, len(rp) - 1)
-    for R in (2, 4):
-        assert_close_rel(gpu_multiply(m, B, 8, "rowblock", rowblocks=R), g["k8_C_seq"], rp, ci, va, B)
-
-
-def test_rowblock_refuses_unsorted_rows():
-    m = spmm.SparseMatrix([1., 2.], [3, 1], [0, 2], 1, 4)
-    with spmm.DeviceCSR.from_host(m, 0, 0) as A:
-        with pytest.raises(_cabi.SpmmError):
-            A.build_rowblocks(2)
-        assert A.build_rowblocks(-1)["rows_per_block"] == 0  # auto: quietly keeps the CSR kernels
-        B = np.arange(8, dtype=np.float64).reshape(4, 2)
-        assert np.array_equal(A.multiply_host(B, 2), [[1 * 6 + 2 * 2, 1 * 7 + 2 * 3]])
-
-
 # ---------------------------------------------------------------- sub-ranges used by the strategies
 @pytest.mark.parametrize("kernel", ["rows", "merge"])
 def test_row_blocks_and_nnz_ranges(oracle, kernel):
@@ -142,7 +111,7 @@ def test_row_blocks_and_nnz_ranges(oracle, kernel):
     B = np.random.default_rng(8).integers(1, 101, (n, k)).astype(np.float64)
     seq = oracle.spmm(rp, ci, va, B, k)
     dB = dev(B)
-    with spmm.DeviceCSR.from_host(m, 0, 0) as A:
+    with spmm.DeviceCSR.from_host(m, 0) as A:
         for P in (1, 3, 8):
             # a4: every rank's row block
             for r in range(P):
@@ -168,7 +137,7 @@ def test_column_slabs_strided(oracle):
     B = np.random.default_rng(9).integers(1, 101, (n, k)).astype(np.float64)
     seq = oracle.spmm(rp, ci, va, B, k)
     dB = dev(B)
-    with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, n, n), 0, 0) as A:
+    with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, n, n), 0) as A:
         for P in (1, 5, 16):  # 16 > k: leading ranks own no column, the last owns all extras (ColumnWise.cpp:25-28)
             out = torch.zeros((n, k), dtype=torch.float64, device="cuda")
             for r in range(P):
@@ -181,7 +150,7 @@ def test_column_block_submatrix(oracle):
     n, k = 1000, 8
     rp, ci, va = random_csr(16, n, n, 14, empty_every=5, positive=True)
     B = np.random.default_rng(10).integers(1, 101, (n, k)).astype(np.float64)
-    with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, n, n), 0, 0) as A:
+    with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, n, n), 0) as A:
         total = np.zeros((n, k))
         nnz = 0
         for r in range(3):
@@ -245,7 +214,7 @@ def test_csr_build_rejects_out_of_range():
 
 def test_upload_download_roundtrip_is_bitwise():
     rp, ci, va = random_csr(17, 500, 700, 8, long_row=900, empty_every=3)
-    with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, 500, 700), 0, 0) as A:
+    with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, 500, 700), 0) as A:
         h = A.download()
     assert h.rowPtr.tobytes() == rp.tobytes() and h.colIndices.tobytes() == ci.tobytes() and h.values.tobytes() == va.tobytes()
 
@@ -283,13 +252,11 @@ def test_cop20k_shape_all_k_vs_oracle_and_properties(oracle):
     n, nc, r, c, v, sym = gen.cop20k_A_shaped()
     with spmm.DeviceCSR.from_coo_host(n, nc, r, c, v, sym) as A:
         host = A.download()
-        rb = A.build_rowblocks(-1)
         for k in (1, 8, 32, 64):
             B = np.random.default_rng(k).integers(1, 101, (n, k)).astype(np.float64)
             ref = oracle.spmm(host.rowPtr, host.colIndices, host.values, B, k)
             dB = dev(B)
-            kernels = ["rows", "merge"] + (["rowblock"] if rb["rows_per_block"] else [])
-            for kernel in kernels + ["auto"]:
+            for kernel in ("rows", "merge", "auto"):
                 dC = torch.full((n, k), np.nan, dtype=torch.float64, device="cuda")
                 A.multiply(dB.data_ptr(), k, dC.data_ptr(), kernel)
                 assert_close_rel(dC.cpu().numpy(), ref, tol=REL_TOL)
@@ -320,52 +287,97 @@ def test_auto_rebuilds_its_layouts_across_k(oracle):
                 assert info["rows_per_tile"] > 0, (k, info)  # FEM-like rows: AUTO must have built a tile layout
 
 
-def test_large_banded_properties():
-    """2^22 x 2^22 banded, 32 per row (cfg4's shape at 1/8 size): checksum and linearity properties."""
-    n, k = 1 << 22, 16
+def test_large_banded_vs_oracle_and_properties(oracle):
+    """cfg4's family: banded, 32 per row, k=16. 2^20 rows against the ORACLE (rows / merge / auto, and a row block
+    generated alone), then 2^22 rows through size-independent properties (A*1 = row sums, linearity)."""
+    n, k = 1 << 20, 16
+    with spmm.DeviceCSR.banded(n, 32, 4096, seed=7) as A:
+        host = A.download()
+        B = np.random.default_rng(16).integers(1, 101, (n, k)).astype(np.float64)
+        ref = oracle.spmm(host.rowPtr, host.colIndices, host.values, B, k)
+        dB = dev(B)
+        for kernel in ("rows", "merge", "auto"):
+            dC = torch.full((n, k), np.nan, dtype=torch.float64, device="cuda")
+            A.multiply(dB.data_ptr(), k, dC.data_ptr(), kernel)
+            assert_close_rel(dC.cpu().numpy(), ref, tol=REL_TOL)
+        # a row block generated alone (RowWise.cpp:26-29 partition) is bit-identical to those rows of the whole matrix
+        s, e = spmm.partition_rows(n, 8, 3)
+        with spmm.DeviceCSR.banded(n, 32, 4096, seed=7, row_begin=s, row_end=e) as blk:
+            hb = blk.download()
+            assert hb.values.tobytes() == host.values[host.rowPtr[s]:host.rowPtr[e]].tobytes()
+            Cb = torch.full((e - s, k), np.nan, dtype=torch.float64, device="cuda")
+            blk.multiply(dB.data_ptr(), k, Cb.data_ptr())
+            assert_close_rel(Cb.cpu().numpy(), ref[s:e], tol=REL_TOL)
+    n = 1 << 22
     with spmm.DeviceCSR.banded(n, 32, 4096, seed=7) as A:
         ones = torch.ones((n, k), dtype=torch.float64, device="cuda")
         C1 = torch.empty((n, k), dtype=torch.float64, device="cuda")
         A.multiply(ones.data_ptr(), k, C1.data_ptr())
         vals = A.download().values.reshape(n, 32)
         rowsum = torch.from_numpy(vals).cuda().sum(dim=1, keepdim=True)
-        # A * ones == row sums in every column
-        assert torch.allclose(C1, rowsum.expand(n, k), rtol=1e-12, atol=0)
-        # linearity: A(2x + y) == 2 A x + A y
+        assert torch.allclose(C1, rowsum.expand(n, k), rtol=1e-12, atol=0)  # A * ones == row sums in every column
         x = torch.randint(1, 101, (n, k), device="cuda").double()
         y = torch.randint(1, 101, (n, k), device="cuda").double()
         Cx, Cy, Cz = (torch.empty((n, k), dtype=torch.float64, device="cuda") for _ in range(3))
         z = 2 * x + y
         for src, dst in ((x, Cx), (y, Cy), (z, Cz)):
             A.multiply(src.data_ptr(), k, dst.data_ptr())
-        assert torch.allclose(Cz, 2 * Cx + Cy, rtol=1e-12, atol=0)
-        # a row block generated alone is bit-identical to the same rows of the whole matrix
-        s, e = spmm.partition_rows(n, 8, 3)
-        with spmm.DeviceCSR.banded(n, 32, 4096, seed=7, row_begin=s, row_end=e) as blk:
-            hb = blk.download()
-            assert hb.values.tobytes() == vals[s:e].tobytes()
-            Cb = torch.empty((e - s, k), dtype=torch.float64, device="cuda")
-            blk.multiply(x.data_ptr(), k, Cb.data_ptr())
-            assert torch.equal(Cb, Cx[s:e])
+        assert torch.allclose(Cz, 2 * Cx + Cy, rtol=1e-12, atol=0)  # linearity: A(2x + y) == 2 A x + A y
 
 
-def test_rmat_merge_equals_rows_kernel():
-    """R-MAT scale 18 (cfg3's family): power-law rows; merge-path and row kernels agree, schedule picks merge."""
-    with spmm.DeviceCSR.rmat(18, 16 << 18, seed=3) as A:
+@pytest.mark.parametrize("scale", [18, 20])
+def test_rmat_vs_oracle(oracle, scale):
+    """cfg3's family: R-MAT (0.57, 0.19, 0.19), 16 edges per vertex, duplicates kept, k=32 — merge-path, row kernel and
+    AUTO against the ORACLE; the schedule must pick merge; rows come out of the device build in (column, value) order."""
+    with spmm.DeviceCSR.rmat(scale, 16 << scale, seed=3) as A:
         n, k = A.n_rows, 32
         sched = A.schedule()
-        assert sched["max_row_len"] > 1000 and sched["bins"]["0"] > 0
-        B = torch.randint(1, 101, (n, k), device="cuda").double()
-        Cr, Cm = torch.empty((n, k), dtype=torch.float64, device="cuda"), torch.empty((n, k), dtype=torch.float64, device="cuda")
-        A.multiply(B.data_ptr(), k, Cr.data_ptr(), "rows")
-        A.multiply(B.data_ptr(), k, Cm.data_ptr(), "merge")
-        assert torch.allclose(Cr, Cm, rtol=1e-12, atol=0)
+        assert sched["max_row_len"] > 1000 and sched["bins"]["0"] > 0 and sched["auto_kernel"] == "merge"
         host = A.download()
-        assert np.all(np.diff(host.rowPtr) >= 0) and host.rowPtr[-1] == 16 << 18
-        # rows sorted by (column, value) as the loader leaves them
-        rows = np.repeat(np.arange(n), np.diff(host.rowPtr))
-        order = np.lexsort((host.values, host.colIndices, rows))
-        assert np.array_equal(order, np.arange(host.nnz))
+        assert np.all(np.diff(host.rowPtr) >= 0) and host.rowPtr[-1] == 16 << scale
+        B = np.random.default_rng(scale).integers(1, 101, (n, k)).astype(np.float64)
+        ref = oracle.spmm(host.rowPtr, host.colIndices, host.values, B, k)
+        dB = dev(B)
+        for kernel in ("merge", "rows", "auto"):
+            dC = torch.full((n, k), np.nan, dtype=torch.float64, device="cuda")
+            A.multiply(dB.data_ptr(), k, dC.data_ptr(), kernel)
+            assert_close_rel(dC.cpu().numpy(), ref, tol=REL_TOL)
+        if scale == 18:
+            rows = np.repeat(np.arange(n), np.diff(host.rowPtr))
+            order = np.lexsort((host.values, host.colIndices, rows))
+            assert np.array_equal(order, np.arange(host.nnz))
+        # cfg3 at 8 ranks: equal non-zero ranges, cut rows summed in rank order == the oracle's nnz strategy
+        total = np.zeros((n, k))
+        for r in range(8):
+            b, e = spmm.partition_nnz(host.nnz, 8, r)
+            first, last = A.nnz_range_rows(b, e)
+            out = torch.full((last - first + 1, k), np.nan, dtype=torch.float64, device="cuda")
+            A.multiply_nnz_range(b, e, first, last, dB.data_ptr(), k, out.data_ptr(), "auto")
+            total[first:last + 1] += out.cpu().numpy()
+        assert_close_rel(total, ref, tol=REL_TOL)
+
+
+def test_uniform_columns_vs_oracle_and_column_blocks(oracle):
+    """cfg5's family: 2^19 rows, 32 uniformly scattered columns per row, k=64 — whole matrix and the 8 column blocks
+    of the column-wise strategy (partials summed in rank order) against the ORACLE."""
+    n, k = 1 << 19, 64
+    with spmm.DeviceCSR.banded(n, 32, n // 2, seed=11) as A:  # window = the whole row: columns anywhere
+        host = A.download()
+        B = np.random.default_rng(5).integers(1, 101, (n, k)).astype(np.float64)
+        ref = oracle.spmm(host.rowPtr, host.colIndices, host.values, B, k)
+        dB = dev(B)
+        for kernel in ("rows", "merge", "auto"):
+            dC = torch.full((n, k), np.nan, dtype=torch.float64, device="cuda")
+            A.multiply(dB.data_ptr(), k, dC.data_ptr(), kernel)
+            assert_close_rel(dC.cpu().numpy(), ref, tol=REL_TOL)
+        total = torch.zeros((n, k), dtype=torch.float64, device="cuda")
+        part = torch.empty((n, k), dtype=torch.float64, device="cuda")
+        for r in range(8):
+            c0, c1 = spmm.partition_rows(n, 8, r)
+            with A.column_block(c0, c1) as S:
+                S.multiply(dB[c0:c1].data_ptr(), k, part.data_ptr())
+                total += part
+        assert_close_rel(total.cpu().numpy(), ref, tol=REL_TOL)
 
 
 def test_strategy_classes_on_one_gpu(oracle):
@@ -394,33 +406,6 @@ def test_sweep_kernel_variants(oracle, nv, np_, u, th, k):
     assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
 
 
-@pytest.mark.parametrize("R,kl", [(1, 8), (1, 16), (2, 8), (2, 16)])
-@pytest.mark.parametrize("k,tune", [(16, {}), (32, {}), (64, {}), (64, {"rows.sweep": 1, "rows.threads": 512}),
-                                    (64, {"rows.nv": 1}), (128, {"rows.sweep": 1, "rows.threads": 256, "rows.nv": 2}),
-                                    (256, {})])
-def test_packed_stream_kernel(oracle, R, kl, k, tune):
-    """Warp-packed A stream (spmm_packed.cu): ragged last slice, empty rows, a long row, padded groups."""
-    if (k // 2) % kl:
-        pytest.skip("k must be a multiple of 2*lanes_per_row")
-    rp, ci, va = random_csr(23, 2503, 2503, 18, long_row=333, empty_every=11, positive=True)
-    m = spmm.SparseMatrix(va, ci, rp, 2503, 2503)
-    B = np.random.default_rng(k).integers(1, 101, (2503, k)).astype(np.float64)
-    _cabi.tune("reset", 0)
-    for key, val in tune.items():
-        _cabi.tune(key, val)
-    try:
-        with spmm.DeviceCSR.from_host(m, 0, 2 if R == 2 else 0) as A:
-            info = A.build_packed(R, kl)
-            assert info["rows_per_unit"] == R and info["lanes_per_row"] == kl and info["fill_ratio"] >= 1.0
-            dB = dev(B)
-            for kernel in ("packed", "auto"):
-                dC = torch.full((2503, k), np.nan, dtype=torch.float64, device="cuda")
-                A.multiply(dB.data_ptr(), k, dC.data_ptr(), kernel)
-                assert_close_rel(dC.cpu().numpy(), oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
-    finally:
-        _cabi.tune("reset", 0)
-
-
 @pytest.mark.parametrize("tile", [32, 100, 4096])
 @pytest.mark.parametrize("k", [1, 16, 64])
 def test_round_robin_row_tiles(oracle, tile, k):
@@ -429,33 +414,6 @@ def test_round_robin_row_tiles(oracle, tile, k):
     B = np.random.default_rng(k).integers(1, 101, (5003, k)).astype(np.float64)
     got = gpu_multiply(spmm.SparseMatrix(va, ci, rp, 5003, 5003), B, k, "rows", {"rows.tile": tile})
     assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
-
-
-@pytest.mark.parametrize("k,tune", [(16, {}), (32, {"rows.unroll": 4}), (64, {}), (64, {"rows.nv": 1, "rows.threads": 256}),
-                                    (64, {"rows.nv": 2, "rows.threads": 1024, "rows.unroll": 1}), (128, {"rows.ctas_per_sm": 2}),
-                                    (192, {})])
-@pytest.mark.parametrize("shape", ["fem", "long_rows", "mostly_empty", "tiny"])
-def test_staged_kernel(oracle, k, tune, shape):
-    """A stream staged through a shared-memory ring (spmm_staged.cu): rows crossing tile borders, rows near the
-    2048-element limit, super-tiles of only empty rows, matrices smaller than one CTA chunk."""
-    cfg = {"fem": (31, 40000, 40000, 21, None, 97), "long_rows": (32, 3000, 3000, 300, 2048, 5),
-           "mostly_empty": (33, 9000, 9000, 0.02, 50, 0), "tiny": (34, 7, 7, 3, None, 0)}[shape]
-    seed, n, nc, mean, long_row, empty_every = cfg
-    rp, ci, va = random_csr(seed, n, nc, mean, long_row=long_row, empty_every=empty_every, positive=True)
-    if k > 64 and shape == "long_rows":
-        pytest.skip("covered at k <= 64")
-    B = np.random.default_rng(k).integers(1, 101, (nc, k)).astype(np.float64)
-    got = gpu_multiply(spmm.SparseMatrix(va, ci, rp, n, nc), B, k, "staged", tune)
-    assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
-
-
-def test_staged_kernel_refuses_long_rows():
-    rp, ci, va = random_csr(35, 50, 5000, 5, long_row=3000, positive=True)
-    with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, 50, 5000), 0, 0) as A:
-        B = torch.ones((5000, 16), dtype=torch.float64, device="cuda")
-        Cd = torch.empty((50, 16), dtype=torch.float64, device="cuda")
-        with pytest.raises(_cabi.SpmmError):
-            A.multiply(B.data_ptr(), 16, Cd.data_ptr(), "staged")
 
 
 # ---------------------------------------------------------------- row tiles with TMA-staged B rows (spmm_tiled.cu)
@@ -546,7 +504,7 @@ def test_tiled_kernel_8_column_k_tile(oracle, shape, k, ncw):
     _cabi.tune("tiled.kt", 8)
     _cabi.tune("tiled.ncw", ncw)
     try:
-        with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, n, n), 0, 0) as A:
+        with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, n, n), 0) as A:
             info = A.build_tiles(-1, 0)
             if not info["rows_per_tile"]:
                 pytest.skip("no tile shape fits this matrix")
@@ -572,7 +530,7 @@ def test_tiled_walking_order_of_far_band_matrices(oracle, group, k):
     _cabi.tune("reset", 0)
     _cabi.tune("tiled.group", group)
     try:
-        with spmm.DeviceCSR.from_host(host, 0, 0) as A:
+        with spmm.DeviceCSR.from_host(host, 0) as A:
             A.build_tiles(32, 16, k)
             dB = dev(B)
             dC = torch.full((n, k), np.nan, dtype=torch.float64, device="cuda")
@@ -639,7 +597,7 @@ def test_tiled_mixed_sign_duplicates_and_strided(oracle, golden_multiply):
 # ---------------------------------------------------------------- stream kernel (spmm_stream.cu): k = 1, 2, 4, 8, bit-identical
 @pytest.mark.parametrize("shape", ["short", "fem_like", "rect_wide", "rect_tall", "single_row"])
 @pytest.mark.parametrize("k", [1, 2, 4, 8])
-@pytest.mark.parametrize("tune", [{}, {"stream.tile": 256}, {"stream.tile": 1024}, {"stream.persist": 4}, {"stream.persist": 2, "stream.tile": 512}])
+@pytest.mark.parametrize("tune", [{}, {"stream.tile": 256}, {"stream.tile": 1024}])
 def test_stream_kernel_bit_identical_to_the_oracle(oracle, shape, k, tune):
     seed, n, nc, mean, long_row, empty_every = SHAPES[shape]
     rp, ci, va = random_csr(seed, n, nc, mean, long_row=long_row, empty_every=empty_every, positive=False)
@@ -664,81 +622,12 @@ def test_stream_kernel_refusals_and_strided(oracle):
     # a 4-column slab of a 12-column fat vector (the k-slab strategy)
     B = np.random.default_rng(1).standard_normal((900, 12))
     ref = oracle.spmm(rp, ci, va, np.ascontiguousarray(B[:, 4:8]), 4)
-    with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, 900, 900), 0, 0) as A:
+    with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va, ci, rp, 900, 900), 0) as A:
         dB, dC = dev(B), torch.full((900, 12), np.nan, dtype=torch.float64, device="cuda")
         A.multiply_strided(dB.data_ptr(), 12, dC.data_ptr(), 12, 4, 4, "stream", torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         got = dC.cpu().numpy()
     assert np.array_equal(got[:, 4:8], ref) and np.isnan(got[:, :4]).all() and np.isnan(got[:, 8:]).all()
-
-
-# ---------------------------------------------------------------- union kernel (spmm_union.cu): blocks of rows over union columns
-def union_multiply(m, B, k, R, tune, k_layout=None):
-    _cabi.tune("reset", 0)
-    for key, val in tune.items():
-        _cabi.tune(key, val)
-    try:
-        with spmm.DeviceCSR.from_host(m, 0, 0) as A:
-            info = A.build_union(R, k_layout or k)
-            assert info["rows_per_block"] == R and info["union_per_nnz"] <= 1.0 + 1e-12
-            dB = dev(B)
-            dC = torch.full((m.numRows, k), np.nan, dtype=torch.float64, device="cuda")
-            A.multiply(dB.data_ptr(), k, dC.data_ptr(), "union", torch.cuda.current_stream().cuda_stream)
-            torch.cuda.synchronize()
-            return dC.cpu().numpy()
-    finally:
-        _cabi.tune("reset", 0)
-
-
-@pytest.mark.parametrize("shape", ["fem_like", "short", "rect_wide", "rect_tall", "single_row", "all_empty"])
-@pytest.mark.parametrize("k", [2, 32, 40, 64, 96])
-@pytest.mark.parametrize("R,tune", [(2, {}), (2, {"tiled.ncw": 8, "tiled.depth": 10}), (2, {"union.slots": 8, "tiled.ncw": 4, "tiled.depth": 4}),
-                                    (4, {"tiled.ncw": 4, "tiled.depth": 4}), (2, {"tiled.kt": 16, "tiled.ncw": 8, "tiled.depth": 12})])
-def test_union_kernel_vs_oracle(oracle, shape, k, R, tune):
-    seed, n, nc, mean, long_row, empty_every = SHAPES[shape]
-    rp, ci, va = random_csr(seed, n, nc, mean, long_row=long_row, empty_every=empty_every, positive=True)
-    B = np.random.default_rng(seed + k).integers(1, 101, (nc, k)).astype(np.float64)
-    ref = oracle.spmm(rp, ci, va, B, k)
-    if va.size == 0:
-        pytest.skip("no layout for an empty matrix (the CSR kernels write the zeros)")
-    got = union_multiply(spmm.SparseMatrix(va, ci, rp, n, nc), B, k, R, tune)
-    assert_close_rel(got, ref, tol=REL_TOL)
-
-
-def test_union_kernel_long_rows_mixed_sign_and_refusals(oracle, golden_multiply):
-    # a 3,000-entry hub row is cut into segments folded in a fixed order; mixed signs and duplicate columns (golden "hub")
-    g = golden_multiply
-    rp, ci, va, B = g["hub_rowptr"], g["hub_colidx"], g["hub_vals"], g["hub_B"]
-    n, k = len(rp) - 1, B.shape[1]
-    m = spmm.SparseMatrix(va, ci, rp, n, n)
-    if k % 2 == 0:
-        assert_close_rel(union_multiply(m, B, k, 2, {}), g["hub_C_seq"], rp, ci, va, B)
-    B2 = np.random.default_rng(3).integers(1, 101, (n, 32)).astype(np.float64)
-    assert_close_rel(union_multiply(m, B2, 32, 2, {}), oracle.spmm(rp, ci, va, B2, 32), rp, ci, va, B2)
-    # rows that are not sorted by column: the layout is refused, the CSR kernels stay in charge
-    rp3, ci3, va3 = random_csr(11, 500, 500, 8, positive=True)
-    ci3 = ci3.copy()
-    lo, hi = rp3[5], rp3[6]
-    if hi - lo >= 2:
-        ci3[lo], ci3[hi - 1] = ci3[hi - 1], ci3[lo]
-        with spmm.DeviceCSR.from_host(spmm.SparseMatrix(va3, ci3, rp3, 500, 500), 0, 0) as A:
-            if ci3[lo] != ci3[hi - 1]:
-                with pytest.raises(_cabi.SpmmError, match="not sorted"):
-                    A.build_union(2, 64)
-            B3 = dev(np.ones((500, 3)))
-            C3 = torch.empty((500, 4), dtype=torch.float64, device="cuda")
-            with pytest.raises(_cabi.SpmmError, match="union kernel requested"):
-                A.multiply(B3.data_ptr(), 4, C3.data_ptr(), "union", 0)
-
-
-def test_union_kernel_cop20k_shape_vs_oracle(oracle):
-    n, nc, r, c, v, sym = gen.cop20k_A_shaped()
-    with spmm.DeviceCSR.from_coo_host(n, nc, r, c, v, sym, device=0) as A0:
-        host = A0.download()
-    for k in (32, 64):
-        B = np.random.default_rng(k).integers(1, 101, (n, k)).astype(np.float64)
-        ref = oracle.spmm(host.rowPtr, host.colIndices, host.values, B, k)
-        assert_close_rel(union_multiply(host, B, k, 2, {}), ref, tol=REL_TOL)
 
 
 @pytest.mark.parametrize("kernel,k", [("rows", 5), ("rows", 64), ("merge", 32), ("tiled", 64), ("tiled", 24), ("auto", 16)])

@@ -1,4 +1,5 @@
 """Host-side logic that needs no GPU: partitions, utils mirrors, MatrixMarket front end, generators, shards."""
+import math
 import os
 
 import numpy as np
@@ -125,17 +126,35 @@ def test_matrix_market_native_reader_random_token_layouts(oracle, tmp_path):
             text += f"{r}{data.draw(seps)}{c}"
             if not pattern:
                 fmt = data.draw(spell)
-                text += data.draw(seps) + (fmt if v >= 0 or not fmt.startswith("+") else "{!r}").format(float(v))
+                # "+" only in front of a number whose own spelling carries no sign (-0.0 >= 0 is true, and "+-0" is a
+                # token reference, oracle and native reader all reject)
+                positive = math.copysign(1.0, v) > 0
+                text += data.draw(seps) + (fmt if positive or not fmt.startswith("+") else "{!r}").format(float(v))
             text += data.draw(seps)
         path = tmp_path / "prop.mtx"
         path.write_text(text, newline="")
+        both_fail_or_agree(path)
+
+    def both_fail_or_agree(path):
+        """Product and oracle accept the same files: either both raise, or their records are bit-equal."""
+        try:
+            expected = oracle.read_mtx_coo(str(path))
+        except RuntimeError:
+            with pytest.raises(RuntimeError):
+                spmm.parse_matrix_market(str(path))
+            return
         got = spmm.parse_matrix_market(str(path))
-        onr, onc, orows, ocols, ovals, osym, _ = oracle.read_mtx_coo(str(path))
+        onr, onc, orows, ocols, ovals, osym, _ = expected
         assert (got[0], got[1], got[5]) == (onr, onc, osym)
         assert np.array_equal(got[2], orows) and np.array_equal(got[3], ocols)
         assert np.array_equal(got[4].view(np.uint64), ovals.view(np.uint64))
 
     check()
+    # malformed value tokens: both sides must refuse them together
+    for bad in ("+-0", "+-1.5", "1.5x", "--2"):
+        path = tmp_path / "bad.mtx"
+        path.write_text(f"%%MatrixMarket matrix coordinate real general\n2 2 1\n1 1 {bad}\n")
+        both_fail_or_agree(path)
 
 
 def test_cop20k_shaped_generator_hits_the_published_shape():

@@ -103,8 +103,6 @@ def variant_list(k, full):
     if k in (1, 2, 4, 8):
         v.append(("stream", "stream", {}))
         v += [(f"stream tile={t}", "stream", {"stream.tile": t}) for t in (256, 512, 1024, 2048, 4096, 8192) if t * k * 8 <= 96 * 1024]
-        v += [(f"stream tile={t} persist={p}", "stream", {"stream.tile": t, "stream.persist": p})
-              for t in (512, 1024, 2048) for p in (0, 2, 4, 6, 8) if t * k * 8 <= 96 * 1024]
     if not full:
         return v
     for u in (1, 2, 4, 8):
@@ -131,15 +129,6 @@ def variant_list(k, full):
                             v.append((f"sweep nv={nv} np={np_} u={u} th={th} ctas={ctas}", "rows",
                                       {"rows.sweep": 1, "rows.kl": 8, "rows.nv": nv, "rows.np": np_, "rows.unroll": u,
                                        "rows.threads": th, "rows.ctas_per_sm": ctas}))
-    if k >= 16 and (k // 2) % 8 == 0:
-        for nv in (1, 2, 4):
-            if (k // 2) % (8 * nv):
-                continue
-            for u in (1, 2, 4):
-                for th in (256, 512, 1024):
-                    for ctas in ((1, 2) if th <= 512 else (1,)):
-                        v.append((f"staged nv={nv} u={u} th={th} ctas={ctas}", "staged",
-                                  {"rows.nv": nv, "rows.unroll": u, "rows.threads": th, "rows.ctas_per_sm": ctas}))
     for pf in (0, 1, 2, 3):
         v.append((f"rows pf={pf}", "rows", {"rows.prefetch": pf}))
         v.append((f"rows u=4 pf={pf}", "rows", {"rows.prefetch": pf, "rows.unroll": 4}))
@@ -160,26 +149,12 @@ def cfg2(args, emit, dev):
     emit({"config": "cfg2", "schedule": first.schedule(), "n_rows": n, "nnz": host.nnz})
     for k in [int(x) for x in args.k.split(",")] if args.k else (1, 8, 32, 64):
         fp = abytes(n, host.nnz, k)
-        for R in ([int(x) for x in args.rowblocks.split(",")] if k >= 8 else (0,)):
-            def make(s, R=R):
-                A = spmm.DeviceCSR.from_host(host, dev.index, 0)
-                if R:
-                    A.build_rowblocks(R)
-                return A
-            sets = operand_sets(make, n, n, k, dev, fp)
-            info = sets[0][0].rowblock_info()
-            if R == 0:
-                run_variants("cfg2", sets, k, variant_list(k, args.variants), args.iters, emit, host.nnz, n)
-            else:
-                vs = [(f"rowblock R={R} u={u}", "rowblock", {"rows.unroll": u}) for u in (1, 2)]
-                if args.variants:
-                    vs += [(f"rowblock R={R} u={u} ctas/sm={cs}", "rowblock", {"rows.unroll": u, "rows.ctas_per_sm": cs})
-                           for u in (1, 2) for cs in (1, 2, 3)]
-                run_variants("cfg2", sets, k, vs, args.iters, emit, host.nnz, n, {"rowblock": info})
-            for A, _, _ in sets:
-                A.close()
-            del sets
-            torch.cuda.empty_cache()
+        sets = operand_sets(lambda s: spmm.DeviceCSR.from_host(host, dev.index), n, n, k, dev, fp)
+        run_variants("cfg2", sets, k, variant_list(k, args.variants), args.iters, emit, host.nnz, n)
+        for A, _, _ in sets:
+            A.close()
+        del sets
+        torch.cuda.empty_cache()
         if k >= 2 and k % 2 == 0 and args.tiles:
             for spec in args.tiles.split(","):
                 f = [int(x) for x in spec.split("x")]
@@ -193,7 +168,7 @@ def cfg2(args, emit, dev):
                 group = f[8] if len(f) > 8 else 0
 
                 def make(s, T=T, BR=BR, kt=kt, thr=thr, depth=depth, ns_cap=ns_cap, pool=pool, ksplit=ksplit, group=group):
-                    A = spmm.DeviceCSR.from_host(host, dev.index, 0)
+                    A = spmm.DeviceCSR.from_host(host, dev.index)
                     _cabi.tune("reset", 0)
                     _cabi.tune("tiled.kt", kt)
                     _cabi.tune("tiled.thr", thr)
@@ -224,75 +199,6 @@ def cfg2(args, emit, dev):
                     vs += [(f"{base} ncw={ncw} u=4 npw=8", "tiled", {"tiled.ncw": ncw, "tiled.unroll": 4, "tiled.npw": 8})
                            for ncw in (12, 16)]
                 run_variants("cfg2", sets, k, vs, args.iters, emit, host.nnz, n, {"tiles": info})
-                for A, _, _ in sets:
-                    A.close()
-                del sets
-                torch.cuda.empty_cache()
-        if k >= 2 and k % 2 == 0 and args.unions:
-            for spec in args.unions.split(","):
-                f = [int(x) for x in spec.split("x")] + [0] * 7
-                R, kt, sl, ncw, depth, split, npw = f[:7]
-
-                def make(s, R=R, kt=kt, sl=sl, ncw=ncw, depth=depth, split=split, npw=npw):
-                    A = spmm.DeviceCSR.from_host(host, dev.index, 0)
-                    _cabi.tune("reset", 0)
-                    _cabi.tune("tiled.kt", kt)
-                    _cabi.tune("union.slots", sl)
-                    _cabi.tune("tiled.ncw", ncw)
-                    _cabi.tune("tiled.depth", depth)
-                    _cabi.tune("union.split", split)
-                    _cabi.tune("tiled.npw", npw)
-                    try:
-                        A.build_union(R, k)
-                    finally:
-                        _cabi.tune("reset", 0)
-                    return A
-                try:
-                    sets = operand_sets(make, n, n, k, dev, fp)
-                except Exception as e:
-                    emit({"config": "cfg2", "k": k, "union": spec, "error": str(e)[:200]})
-                    continue
-                info = sets[0][0].union_info()
-                # parity against the CSR row kernel before any timing
-                A0, B0, C0 = sets[0]
-                ref = torch.empty_like(C0)
-                stream = torch.cuda.current_stream().cuda_stream
-                A0.multiply(B0.data_ptr(), k, ref.data_ptr(), "rows", stream)
-                C0.fill_(float("nan"))
-                A0.multiply(B0.data_ptr(), k, C0.data_ptr(), "union", stream)
-                torch.cuda.synchronize()
-                err = ((C0 - ref).abs() / ref.abs().clamp_min(1e-300)).nan_to_num(nan=float("inf")).max().item()
-                info["max_rel_err_vs_rows"] = err
-                vs = [(f"union {spec}", "union", {})]
-                if args.variants:
-                    vs += [(f"union {spec} dbg={d}", "union", {"union.debug": d}) for d in (64, 65, 66)]
-                run_variants("cfg2", sets, k, vs, args.iters, emit, host.nnz, n, {"union": info})
-                for A, _, _ in sets:
-                    A.close()
-                del sets
-                torch.cuda.empty_cache()
-        if k >= 16 and args.packed:
-            for R, kl in ((1, 8), (1, 16), (2, 8), (2, 16)):
-                if (k // 2) % kl:
-                    continue
-
-                def make(s, R=R, kl=kl):
-                    A = spmm.DeviceCSR.from_host(host, dev.index, 0)
-                    if R == 2:
-                        A.build_rowblocks(2)
-                    A.build_packed(R, kl)
-                    return A
-                sets = operand_sets(make, n, n, k, dev, fp)
-                info = sets[0][0].packed_info()
-                vs = [(f"packed R={R} kl={kl}", "packed", {})]
-                vs += [(f"packed R={R} kl={kl} ctas={c}", "packed", {"rows.ctas_per_sm": c}) for c in (1, 2, 3)]
-                vs += [(f"packed R={R} kl={kl} sweep th={th} ctas={c}", "packed", {"rows.sweep": 1, "rows.threads": th, "rows.ctas_per_sm": c})
-                       for th in (256, 512) for c in (1, 2)]
-                nvs = [nv for nv in (1, 2) if (k // 2) % (kl * nv) == 0 and kl * nv * 2 < k]
-                vs += [(f"packed R={R} kl={kl} nv={nv} sweep th=512", "packed", {"rows.sweep": 1, "rows.threads": 512, "rows.nv": nv})
-                       for nv in nvs]
-                vs += [(f"packed R={R} kl={kl} nv={nv}", "packed", {"rows.nv": nv}) for nv in nvs]
-                run_variants("cfg2", sets, k, vs, args.iters, emit, host.nnz, n, {"packed": info})
                 for A, _, _ in sets:
                     A.close()
                 del sets
@@ -507,11 +413,8 @@ def main():
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--variants", action="store_true")
     ap.add_argument("--cpu", action="store_true", help="also time the reference CPU code on cfg2")
-    ap.add_argument("--packed", action="store_true", help="also time the warp-packed stream layouts on cfg2")
-    ap.add_argument("--unions", default="", help="cfg2: union layouts to time, e.g. 2x32x4x6x8x48 (rows per block x k-tile x slots x consumer warps x depth x split length)")
     ap.add_argument("--tiles", default="", help="cfg2: tile layouts to time, e.g. -1x16,64x16,32x8x32x2 (rows_per_tile x box_rows [x k-tile [x box threshold [x depth]]])")
     ap.add_argument("--only", default="", help="regex: run only the variants whose label matches")
-    ap.add_argument("--rowblocks", default="0,2,4", help="row-block layouts to time on cfg2")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "harness.jsonl"))
     args = ap.parse_args()
     global ONLY
