@@ -43,6 +43,9 @@ enum spmm_kernel
 };
 
 const char *spmm_last_error(void);
+/* Name of the kernel family the calling thread's last multiply launched ("spmm_tiled_kernel", "spmm_rows_kernel",
+ * "spmm_merge_kernel", "spmm_stream_kernel"; "" before the first launch): what AUTO chose, for measurement reports. */
+const char *spmm_last_kernel_name(void);
 int spmm_version(void);
 int spmm_device_count(int *count);
 /* multiProcessorCount, L2 bytes, total global memory of `device` */
@@ -104,6 +107,9 @@ int spmm_csr_schedule(spmm_csr_t A, long long bins[8], int *max_row_len, double 
  * box_rows: 0 (= 16), 4, 8, 16 or 32. The CSR arrays are untouched. The reference has no derived
  * layouts; this serves SparseMatrixFatVectorMultiply.cpp:17-28. */
 int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows);
+/* The same, cut for multiplies with k columns the way AUTO does it (8-column k-tile for k <= 8; from k = 32 / 64 the
+ * chunks are longer and shared by 2 / 4 CTAs that take one group of k-tiles each). k = 0: as spmm_csr_build_tiles. */
+int spmm_csr_build_tiles_for_k(spmm_csr_t A, int rows_per_tile, int box_rows, int k);
 /* reuse = non-zeros per B row staged in shared memory (per pass over the matrix); single_fraction =
  * share of the non-zeros whose B row is staged on its own. Zeros when no layout is built. */
 int spmm_csr_tile_info(spmm_csr_t A, int *rows_per_tile, int *box_rows, int *window_slots, int *max_records,
@@ -111,6 +117,9 @@ int spmm_csr_tile_info(spmm_csr_t A, int *rows_per_tile, int *box_rows, int *win
 /* Sub-matrix A[:, col_begin:col_end) with local column ids (column-block strategy,
  * north_star reading of sparseMatrixFatVectorMultiplyColumnWise). Built on the device. */
 int spmm_csr_column_block(spmm_csr_t A, int col_begin, int col_end, spmm_csr_t *out);
+
+/* Smallest and largest column id stored in the handle (-> the rows of B a shard reads; 0, -1 when empty). */
+int spmm_csr_column_span(spmm_csr_t A, int *min_col, int *max_col);
 
 /* ---- a3: sparseMatrixFatVectorMultiply (SparseMatrixFatVectorMultiply.cpp:11-31) ---- */
 
@@ -136,6 +145,16 @@ int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, doubl
  * k-slabs so that the upload of the second overlaps the download of the first (PCIe is full duplex). */
 int spmm_multiply_host(spmm_csr_t A, const double *B, int k, double *C, int kernel);
 
+/* a2: the same with the operands in the memory shape of a FatVector (MatrixDefinitions.h:22): B_rows[i] / C_rows[i]
+ * point at row i (k doubles each, separately allocated). Pack (serialize(), utils.cpp:216-228) and unpack
+ * (deserialize(), :237-253) run on the library's host threads straight into / out of pinned staging memory, chunk by
+ * chunk, overlapped with the copies. C_rows must already point at n_rows buffers of k doubles. */
+int spmm_multiply_host_rows(spmm_csr_t A, const double *const *B_rows, int k, double *const *C_rows, int kernel);
+int spmm_host_threads(void); /* size of that host thread pool (env SPMM_HOST_THREADS, default min(cores, 32)) */
+/* fn(i, ctx) for i in [0, n) on that pool, the caller taking part; returns when all are done (the entry points use it to
+ * allocate the rows of the result FatVector in parallel). */
+void spmm_host_parallel_for(int n, void (*fn)(int, void *), void *ctx);
+
 /* ---- a4: row block [row_begin,row_end) (RowWise.cpp:26-50). d_C_local holds
  * (row_end-row_begin) x k, i.e. the rank's localResult before the Gatherv. ---- */
 int spmm_multiply_rows_device(spmm_csr_t A, int row_begin, int row_end, const double *d_B, int k,
@@ -160,9 +179,38 @@ int spmm_multiply_nnz_range_host(spmm_csr_t A, long long nnz_begin, long long nn
 /* ---- a5, column-block strategy (north_star reading of ColumnWise.cpp): the reduce of the partial C
  * blocks without NCCL. d_out[0..n_elems) = sum over i of d_src_list[i][0..n_elems), added in list order (pass the
  * ranks' partial blocks in ascending rank order: the sum is then reproducible and equals the oracle's rank-order
- * reduce bit for bit). The sources may be peer GPUs' buffers mapped over NVLink; n_src <= 8, n_elems even. ---- */
+ * reduce bit for bit). The sources may be peer GPUs' buffers mapped over NVLink; n_elems even; more than 8 sources
+ * are added in passes of 8 that continue the same left-to-right sum. ---- */
 int spmm_reduce_blocks_device(int device, int n_src, const double *const *d_src_list, long long n_elems,
                               double *d_out, void *stream);
+
+/* ---- strategies whose ranks share one process (compat MPI rank-threads, one GPU per rank): the collectives of
+ * RowWise.cpp:85-87, ColumnWise.cpp:82-84 and NonZeroElement.cpp:88 without host buffers. A rank stages only the rows of
+ * B its shard reads, multiplies with spmm_multiply_scatter_device storing C rows straight into the root rank's device
+ * buffer over NVLink, and the root brings the finished C down once. ---- */
+/* Rows [row_begin,row_end) of B (row pointers as in a FatVector) -> the handle's device image of B (n_cols x k, the other
+ * rows are left as they are); the copies are enqueued on the handle's own stream, returned in *stream. */
+int spmm_stage_b_rows(spmm_csr_t A, const double *const *B_rows, int row_begin, int row_end, int k, const double **d_B,
+                      void **stream);
+/* A flat row-major host block <-> a device buffer through the handle's pinned staging and the host threads (a pinned
+ * block goes straight to the copy engine). Enqueued on `stream` (a stream of A's device); both return when done. */
+int spmm_upload_dense(spmm_csr_t A, const double *src, long long n_rows, int k, double *d_dst, void *stream);
+int spmm_download_dense(spmm_csr_t A, const double *d_src, long long n_rows, int k, double *dst, void *stream);
+int spmm_csr_stream_sync(spmm_csr_t A); /* wait for everything enqueued on the handle's stream */
+/* n_rows x k doubles at d_C (on A's device) -> C_rows[i], through A's pinned staging, unpacked by the host threads. */
+int spmm_fetch_c_rows(spmm_csr_t A, const double *d_C, int n_rows, int k, double *const *C_rows);
+/* A device buffer of at least `bytes` that lives until spmm_device_scratch_release (one per (device, slot)). */
+int spmm_device_scratch(int device, int slot, long long bytes, void **out);
+int spmm_device_scratch_release(void);
+/* Let kernels on `device` load from / store to memory of `peer` (cudaDeviceEnablePeerAccess; idempotent). */
+int spmm_peer_enable(int device, int peer);
+/* d_dst[i] += d_src[i] on `device` (d_src may be peer memory): cut rows of the non-zero strategy, added in rank order. */
+int spmm_add_device(int device, double *d_dst, const double *d_src, long long n_elems, void *stream);
+/* Device-to-device copy enqueued on a stream of `device`; the two buffers may live on any GPUs of the box (rows a rank
+ * owns -> the root's C). */
+int spmm_copy_device(int device, void *d_dst, const void *d_src, long long bytes, void *stream);
+int spmm_fill_zero_device(int device, void *d_dst, long long bytes, void *stream);
+int spmm_device_sync(int device); /* wait for all work enqueued on `device` */
 
 /* ---- partition formulas (bit-for-bit the reference's integer arithmetic) ---- */
 void spmm_partition_rows(int n_rows, int n_ranks, int rank, int *begin, int *end);           /* RowWise.cpp:26-29 */

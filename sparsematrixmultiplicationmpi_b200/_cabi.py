@@ -38,6 +38,7 @@ _pd = C.POINTER(C.c_double)
 # tests/test_cabi_symbols.py checks the header, this table and the built library agree.
 PROTOTYPES = {
     "spmm_last_error": (C.c_char_p, []),
+    "spmm_last_kernel_name": (C.c_char_p, []),
     "spmm_version": (_i, []),
     "spmm_device_count": (_i, [_pi]),
     "spmm_device_info": (_i, [_i, _pi, _pll, _pll]),
@@ -55,6 +56,23 @@ PROTOTYPES = {
     "spmm_csr_schedule": (_i, [_p, _pll, _pi, _pd, _pi]),
     "spmm_csr_column_block": (_i, [_p, _i, _i, C.POINTER(_p)]),
     "spmm_csr_build_tiles": (_i, [_p, _i, _i]),
+    "spmm_csr_build_tiles_for_k": (_i, [_p, _i, _i, _i]),
+    "spmm_csr_column_span": (_i, [_p, _pi, _pi]),
+    "spmm_multiply_host_rows": (_i, [_p, _p, _i, _p, _i]),
+    "spmm_host_threads": (_i, []),
+    "spmm_host_parallel_for": (None, [_i, _p, _p]),
+    "spmm_stage_b_rows": (_i, [_p, _p, _i, _i, _i, C.POINTER(_p), C.POINTER(_p)]),
+    "spmm_csr_stream_sync": (_i, [_p]),
+    "spmm_upload_dense": (_i, [_p, _p, _ll, _i, _p, _p]),
+    "spmm_download_dense": (_i, [_p, _p, _ll, _i, _p, _p]),
+    "spmm_fetch_c_rows": (_i, [_p, _p, _i, _i, _p]),
+    "spmm_device_scratch": (_i, [_i, _i, _ll, C.POINTER(_p)]),
+    "spmm_device_scratch_release": (_i, []),
+    "spmm_peer_enable": (_i, [_i, _i]),
+    "spmm_add_device": (_i, [_i, _p, _p, _ll, _p]),
+    "spmm_copy_device": (_i, [_i, _p, _p, _ll, _p]),
+    "spmm_device_sync": (_i, [_i]),
+    "spmm_fill_zero_device": (_i, [_i, _p, _ll, _p]),
     "spmm_csr_tile_info": (_i, [_p, _pi, _pi, _pi, _pi, _pd, _pd]),
     "spmm_multiply_device": (_i, [_p, _p, _i, _p, _i, _p]),
     "spmm_multiply_scatter_device": (_i, [_p, _p, _i, _i, C.POINTER(_p), _i, _p]),

@@ -6,20 +6,30 @@
 //   sparseMatrixFatVectorMultiplyColumnWise      "Source Code/SparseMatrixFatVectorMultiplyColumnWise.h":15
 //   sparseMatrixFatVectorMultiplyNonZeroElement  "Source Code/SparseMatrixFatVectorMultiplyNonZeroElement.h":15
 //
-// An MPI rank drives GPU (rank mod device count). Rank and size come from the caller's MPI
-// (<mpi.h>: a real one, or include/compat/mpi.h in this image), and — because the result has to
-// land in a host FatVector on rank 0 anyway — the result collective stays the reference's own
-// MPI call on host buffers (Gatherv / Reduce). The NCCL collectives of the one-process-per-GPU
-// layout live in the torch.distributed host layer (strategies.py); see INTEGRATION.md.
+// An MPI rank drives GPU (rank mod device count). Rank and size come from the caller's MPI.
+//
+// Ranks that share this process (include/compat/mpi.h: a rank is a thread, the layout of an 8 x B200 box driven by one
+// process) never move C through host memory between each other. Each rank uploads only the rows of B its shard
+// reads and
+//   row-wise     stores its C rows from the kernel's registers straight into the root rank's device buffer over NVLink
+//                (spmm_multiply_scatter_device with one peer destination)            — replaces MPI_Gatherv, RowWise.cpp:85-87
+//   column-wise  multiplies its column block of A into a partial C on its own GPU; every rank then sums one row block of
+//                all partials over NVLink in rank order into the root's buffer (reduce-scatter + gather, P2P loads)
+//                                                                                    — replaces the collective of ColumnWise.cpp:82-84
+//   non-zero     copies the rows it owns into the root's buffer; the k doubles of each row cut by a range boundary are
+//                added on the root in rank order                                     — replaces MPI_Reduce, NonZeroElement.cpp:88
+// and the root brings the finished C down once. With a real MPI (ranks in different processes) the result collective
+// stays the reference's own call on host buffers.
 //
 // Nothing here computes: a non-zero status from the C-ABI becomes std::runtime_error (the
 // reference's only error convention, utils.cpp:77,114,140). No CPU fallback.
 #include <mpi.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdint>
 #include <cstring>
 #include <map>
-#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -34,6 +44,12 @@
 
 namespace
 {
+
+#ifdef COMPAT_MPI_H
+constexpr bool kRanksShareProcess = true; // compat MPI: device pointers mean the same thing on every rank
+#else
+constexpr bool kRanksShareProcess = false;
+#endif
 
 void ok(int status)
 {
@@ -50,19 +66,245 @@ int device_for_rank(int rank)
     return rank % count;
 }
 
-// serialize() layout (utils.cpp:216-228): row-major flatten of the first n rows x k columns
-std::vector<double> pack(const FatVector &v, size_t n, int k)
+void validate(const SparseMatrix &m, const FatVector &v, int k)
 {
-    if (v.size() < n)
+    if (k < 0)
+        throw std::runtime_error("spmm_b200: vecCols is negative");
+    if (m.numRows < 0 || m.rowPtr.size() != (size_t)m.numRows + 1 || m.values.size() != m.colIndices.size() ||
+        (size_t)m.rowPtr[m.numRows] != m.values.size())
+        throw std::runtime_error("spmm_b200: SparseMatrix arrays are inconsistent");
+    if (v.size() < (size_t)m.numCols)
         throw std::runtime_error("spmm_b200: fatVector has fewer rows than the matrix has columns");
-    std::vector<double> flat(n * (size_t)k);
-    for (size_t i = 0; i < n; ++i)
+}
+
+// row pointers of a FatVector (its memory shape at the C-ABI); every row must hold k doubles
+std::vector<const double *> row_pointers(const FatVector &v, size_t first, size_t count, int k)
+{
+    std::vector<const double *> p(count);
+    for (size_t i = 0; i < count; ++i)
     {
-        if (v[i].size() < (size_t)k)
+        if (v[first + i].size() < (size_t)k)
             throw std::runtime_error("spmm_b200: fatVector row shorter than vecCols");
-        std::memcpy(flat.data() + i * (size_t)k, v[i].data(), sizeof(double) * (size_t)k);
+        p[i] = v[first + i].data();
     }
-    return flat;
+    return p;
+}
+
+// The result: n freshly allocated rows of k doubles (SparseMatrixFatVectorMultiply.cpp:15), allocated on the host threads
+struct AllocCtx
+{
+    FatVector *out;
+    std::vector<double *> *ptr;
+    size_t n, k, per;
+};
+void alloc_rows(int t, void *c)
+{
+    AllocCtx &x = *static_cast<AllocCtx *>(c);
+    const size_t a = (size_t)t * x.per, b = std::min(x.n, a + x.per);
+    for (size_t i = a; i < b; ++i)
+    {
+        (*x.out)[i] = std::vector<double>(x.k);
+        (*x.ptr)[i] = (*x.out)[i].data();
+    }
+}
+FatVector make_result(size_t n, int k, std::vector<double *> *ptr)
+{
+    FatVector out(n);
+    ptr->assign(n, nullptr);
+    AllocCtx ctx{&out, ptr, n, (size_t)k, std::max<size_t>(256, (n + 63) / 64)};
+    spmm_host_parallel_for((int)((n + ctx.per - 1) / ctx.per), alloc_rows, &ctx);
+    return out;
+}
+
+// ---- device copies of matrix shards, per rank-thread --------------------------------------------------------------
+// Keyed on the identity of the host buffers, the sizes and the shard, and checked against a fingerprint of the contents
+// on every hit (the reference functions are pure: a matrix edited in place or a new one at a recycled address must not
+// meet the old shard). One cache per thread = per rank: no other rank's handles are ever touched or destroyed.
+struct Key
+{
+    const void *vals, *cols, *rowptr;
+    size_t nnz;
+    int n_rows, n_cols, tag;
+    long long a, b;
+    bool operator<(const Key &o) const
+    {
+        return std::tie(vals, cols, rowptr, nnz, n_rows, n_cols, tag, a, b) <
+               std::tie(o.vals, o.cols, o.rowptr, o.nnz, o.n_rows, o.n_cols, o.tag, o.a, o.b);
+    }
+};
+struct Shard
+{
+    spmm_csr_t h = nullptr;
+    uint64_t print = 0;
+    int cmin = 0, cmax = -1;       // columns stored (rows of B the shard reads)
+    int first = 0, last = -1;      // non-zero shards: rows touched; column blocks: first / last non-empty row
+    bool mid = false;              // non-zero shards: the first row started in an earlier rank's range
+};
+
+template <typename T>
+uint64_t mix(uint64_t h, const T *p, size_t n)
+{
+    // whole array up to 64 Ki elements, else 64 Ki evenly spaced probes + the last element (~0.1 ms per call)
+    const size_t step = n <= (1u << 16) ? 1 : n / 65536;
+    for (size_t i = 0; i < n; i += step)
+    {
+        uint64_t w = 0;
+        std::memcpy(&w, p + i, sizeof(T));
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+    }
+    if (n)
+    {
+        uint64_t w = 0;
+        std::memcpy(&w, p + n - 1, sizeof(T));
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+    }
+    return h;
+}
+uint64_t fingerprint(const SparseMatrix &m)
+{
+    uint64_t h = 0x243F6A8885A308D3ull ^ (uint64_t)m.values.size();
+    h = mix(h, m.rowPtr.data(), m.rowPtr.size());
+    h = mix(h, m.colIndices.data(), m.colIndices.size());
+    return mix(h, m.values.data(), m.values.size());
+}
+
+struct Cache
+{
+    std::map<Key, Shard> map;
+    ~Cache() { clear(); }
+    void clear()
+    {
+        for (auto &kv : map)
+            spmm_csr_destroy(kv.second.h);
+        map.clear();
+    }
+};
+thread_local Cache t_cache;
+
+template <typename Make>
+Shard &cached(const SparseMatrix &m, int tag, long long a, long long b, Make make)
+{
+    Key key{m.values.data(), m.colIndices.data(), m.rowPtr.data(), m.values.size(), m.numRows, m.numCols, tag, a, b};
+    const uint64_t print = fingerprint(m);
+    auto it = t_cache.map.find(key);
+    if (it != t_cache.map.end())
+    {
+        if (it->second.print == print)
+            return it->second;
+        spmm_csr_destroy(it->second.h); // same address, other contents
+        t_cache.map.erase(it);
+    }
+    if (t_cache.map.size() >= 16)
+        t_cache.clear();
+    Shard s = make();
+    s.print = print;
+    return t_cache.map[key] = s;
+}
+
+Shard &whole_matrix(const SparseMatrix &m, int device)
+{
+    return cached(m, 0, device, 0, [&] {
+        Shard s;
+        ok(spmm_csr_create_host(device, m.numRows, m.numCols, (long long)m.values.size(), m.rowPtr.data(),
+                                m.colIndices.data(), m.values.data(), &s.h));
+        return s;
+    });
+}
+
+// rows [start,end) with the row pointer rebased (RowWise.cpp:26-29)
+Shard &row_shard(const SparseMatrix &m, int device, int start, int end)
+{
+    return cached(m, 1, start, end, [&] {
+        Shard s;
+        const int lo = m.rowPtr[start], hi = m.rowPtr[end];
+        std::vector<int> rp(m.rowPtr.begin() + start, m.rowPtr.begin() + end + 1);
+        for (int &x : rp)
+            x -= lo;
+        ok(spmm_csr_create_host(device, end - start, m.numCols, (long long)hi - lo, rp.data(), m.colIndices.data() + lo,
+                                m.values.data() + lo, &s.h));
+        ok(spmm_csr_column_span(s.h, &s.cmin, &s.cmax));
+        return s;
+    });
+}
+
+// columns [c0,c1) of A with local column ids (column blocks): cut on the device from a transient whole-matrix upload
+Shard &column_shard(const SparseMatrix &m, int device, int c0, int c1)
+{
+    return cached(m, 2, c0, c1, [&] {
+        Shard s;
+        spmm_csr_t whole = nullptr;
+        ok(spmm_csr_create_host(device, m.numRows, m.numCols, (long long)m.values.size(), m.rowPtr.data(),
+                                m.colIndices.data(), m.values.data(), &whole));
+        const int rc = spmm_csr_column_block(whole, c0, c1, &s.h);
+        spmm_csr_destroy(whole);
+        ok(rc);
+        long long nnz = 0;
+        ok(spmm_csr_info(s.h, nullptr, nullptr, &nnz, nullptr));
+        if (nnz > 0)
+            ok(spmm_nnz_range_rows(s.h, 0, nnz, &s.first, &s.last));
+        return s;
+    });
+}
+
+// elements [b,e) of the CSR order as a CSR of the rows they touch, each row clipped to the range (NonZeroElement.cpp:24-51)
+Shard &nnz_shard(const SparseMatrix &m, int device, long long b, long long e)
+{
+    return cached(m, 3, b, e, [&] {
+        Shard s;
+        const int *rp = m.rowPtr.data();
+        s.first = (int)(std::upper_bound(rp, rp + m.numRows + 1, (int)b) - rp) - 1;
+        s.last = (int)(std::upper_bound(rp, rp + m.numRows + 1, (int)(e - 1)) - rp) - 1;
+        s.mid = b > rp[s.first];
+        std::vector<int> local((size_t)(s.last - s.first) + 2);
+        for (int r = s.first; r <= s.last + 1; ++r)
+            local[(size_t)(r - s.first)] = (int)(std::min<long long>(std::max<long long>(rp[r], b), e) - b);
+        ok(spmm_csr_create_host(device, s.last - s.first + 1, m.numCols, e - b, local.data(), m.colIndices.data() + b,
+                                m.values.data() + b, &s.h));
+        ok(spmm_csr_column_span(s.h, &s.cmin, &s.cmax));
+        return s;
+    });
+}
+
+// ---- small exchanges between the ranks (pointer-sized words through the caller's MPI) ---------------------------
+void bcast_word(long long *w)
+{
+    int two[2];
+    std::memcpy(two, w, sizeof two);
+    MPI_Bcast(two, 2, MPI_INT, 0, MPI_COMM_WORLD);
+    std::memcpy(w, two, sizeof two);
+}
+// every rank contributes `n` words, every rank receives all P*n (rank-major)
+std::vector<long long> all_gather_words(const long long *mine, int n, int P)
+{
+    std::vector<long long> all((size_t)P * n);
+    std::vector<int> counts(P, 2 * n), displs(P);
+    for (int r = 0; r < P; ++r)
+        displs[r] = 2 * n * r;
+    MPI_Gatherv(mine, 2 * n, MPI_INT, all.data(), counts.data(), displs.data(), MPI_INT, 0, MPI_COMM_WORLD);
+    MPI_Bcast(all.data(), 2 * n * P, MPI_INT, 0, MPI_COMM_WORLD);
+    return all;
+}
+
+double *root_buffer(int root_device, size_t n, int k, int rank)
+{
+    long long w = 0;
+    if (rank == 0)
+    {
+        void *p = nullptr;
+        ok(spmm_device_scratch(root_device, 0, (long long)(n * (size_t)k * sizeof(double)), &p));
+        w = (long long)(intptr_t)p;
+    }
+    bcast_word(&w);
+    return (double *)(intptr_t)w;
+}
+
+FatVector fetch_result(spmm_csr_t staging_handle, const double *d_C, size_t n, int k)
+{
+    std::vector<double *> rows;
+    FatVector out = make_result(n, k, &rows);
+    ok(spmm_fetch_c_rows(staging_handle, d_C, (int)n, k, rows.data()));
+    return out;
 }
 
 FatVector unpack(const double *flat, size_t n, int k)
@@ -73,198 +315,372 @@ FatVector unpack(const double *flat, size_t n, int k)
     return out;
 }
 
-void validate(const SparseMatrix &m, int k)
-{
-    if (k < 0)
-        throw std::runtime_error("spmm_b200: vecCols is negative");
-    if (m.numRows < 0 || m.rowPtr.size() != (size_t)m.numRows + 1 || m.values.size() != m.colIndices.size() ||
-        (size_t)m.rowPtr[m.numRows] != m.values.size())
-        throw std::runtime_error("spmm_b200: SparseMatrix arrays are inconsistent");
-}
-
-// Device copies of matrix shards, keyed on the host buffers' identity, so main()'s four
-// back-to-back calls on one M upload each shard once. Inputs are borrowed for the call only:
-// the key also carries the sizes, and spmm_entry_clear_cache() drops everything.
-struct Key
-{
-    const void *vals, *cols, *rowptr;
-    size_t nnz;
-    int n_rows, n_cols, tag, a, b;
-    bool operator<(const Key &o) const
-    {
-        return std::tie(vals, cols, rowptr, nnz, n_rows, n_cols, tag, a, b) <
-               std::tie(o.vals, o.cols, o.rowptr, o.nnz, o.n_rows, o.n_cols, o.tag, o.a, o.b);
-    }
-};
-std::mutex g_mu;
-std::map<Key, spmm_csr_t> g_cache;
-
-template <typename Make>
-spmm_csr_t cached(const SparseMatrix &m, int tag, int a, int b, Make make)
-{
-    Key key{m.values.data(), m.colIndices.data(), m.rowPtr.data(), m.values.size(), m.numRows, m.numCols, tag, a, b};
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_cache.find(key);
-    if (it != g_cache.end())
-        return it->second;
-    if (g_cache.size() >= 32)
-    {
-        for (auto &kv : g_cache)
-            spmm_csr_destroy(kv.second);
-        g_cache.clear();
-    }
-    spmm_csr_t h = make();
-    g_cache[key] = h;
-    return h;
-}
-
-spmm_csr_t whole_matrix(const SparseMatrix &m, int device)
-{
-    return cached(m, 0, device, 0, [&] {
-        spmm_csr_t h = nullptr;
-        ok(spmm_csr_create_host(device, m.numRows, m.numCols, (long long)m.values.size(), m.rowPtr.data(),
-                                m.colIndices.data(), m.values.data(), &h));
-        return h;
-    });
-}
-
 } // namespace
 
 extern "C" void spmm_entry_clear_cache()
 {
-    std::lock_guard<std::mutex> lk(g_mu);
-    for (auto &kv : g_cache)
-        spmm_csr_destroy(kv.second);
-    g_cache.clear();
+    t_cache.clear(); // the calling thread's shards (each rank-thread owns its own)
 }
 
 FatVector sparseMatrixFatVectorMultiply(const SparseMatrix &sparseMatrix, const FatVector &fatVector, int vecCols)
 {
-    validate(sparseMatrix, vecCols);
+    validate(sparseMatrix, fatVector, vecCols);
     const size_t n = (size_t)sparseMatrix.numRows;
     if (n == 0 || vecCols == 0)
         return FatVector(n, std::vector<double>((size_t)vecCols, 0.0));
-    spmm_csr_t A = whole_matrix(sparseMatrix, device_for_rank(0));
-    const std::vector<double> B = pack(fatVector, (size_t)sparseMatrix.numCols, vecCols);
-    std::vector<double> C(n * (size_t)vecCols);
-    ok(spmm_multiply_host(A, B.data(), vecCols, C.data(), SPMM_KERNEL_AUTO));
-    return unpack(C.data(), n, vecCols);
+    Shard &A = whole_matrix(sparseMatrix, device_for_rank(0));
+    const std::vector<const double *> B = row_pointers(fatVector, 0, (size_t)sparseMatrix.numCols, vecCols);
+    std::vector<double *> rows;
+    FatVector out = make_result(n, vecCols, &rows);
+    ok(spmm_multiply_host_rows(A.h, B.data(), vecCols, rows.data(), SPMM_KERNEL_AUTO));
+    return out;
 }
 
 FatVector sparseMatrixFatVectorMultiplyRowWise(const SparseMatrix &sparseMatrix, const FatVector &fatVector,
                                                int vecCols)
 {
-    validate(sparseMatrix, vecCols);
+    validate(sparseMatrix, fatVector, vecCols);
     int worldSize = 1, worldRank = 0;
     MPI_Comm_size(MPI_COMM_WORLD, &worldSize);
     MPI_Comm_rank(MPI_COMM_WORLD, &worldRank);
     int start = 0, end = 0;
     spmm_partition_rows(sparseMatrix.numRows, worldSize, worldRank, &start, &end); // RowWise.cpp:26-29
-    const int device = device_for_rank(worldRank);
+    const int device = device_for_rank(worldRank), k = vecCols;
+    const size_t n = (size_t)sparseMatrix.numRows;
+    if (n == 0 || k == 0)
+        return worldRank == 0 ? FatVector(n, std::vector<double>((size_t)k, 0.0)) : FatVector{};
 
-    std::vector<double> local((size_t)(end - start) * (size_t)vecCols);
-    if (end > start && vecCols > 0)
+    if (kRanksShareProcess)
     {
-        // the rank's shard: rows [start,end) with the row pointer rebased
-        spmm_csr_t A = cached(sparseMatrix, 1, start, end, [&] {
-            const int lo = sparseMatrix.rowPtr[start], hi = sparseMatrix.rowPtr[end];
-            std::vector<int> rp(sparseMatrix.rowPtr.begin() + start, sparseMatrix.rowPtr.begin() + end + 1);
-            for (int &x : rp)
-                x -= lo;
-            spmm_csr_t h = nullptr;
-            ok(spmm_csr_create_host(device, end - start, sparseMatrix.numCols, (long long)hi - lo, rp.data(),
-                                    sparseMatrix.colIndices.data() + lo, sparseMatrix.values.data() + lo, &h));
-                return h;
-        });
-        const std::vector<double> B = pack(fatVector, (size_t)sparseMatrix.numCols, vecCols);
-        ok(spmm_multiply_host(A, B.data(), vecCols, local.data(), SPMM_KERNEL_AUTO));
+        const int root_device = device_for_rank(0);
+        double *root_C = root_buffer(root_device, n, k, worldRank);
+        Shard *mine = nullptr;
+        if (end > start)
+        {
+            mine = &row_shard(sparseMatrix, device, start, end);
+            ok(spmm_peer_enable(device, root_device));
+            const std::vector<const double *> B = row_pointers(fatVector, 0, (size_t)sparseMatrix.numCols, k);
+            const double *dB = nullptr;
+            void *stream = nullptr;
+            ok(spmm_stage_b_rows(mine->h, B.data(), mine->cmin, mine->cmax + 1, k, &dB, &stream)); // only the rows this block reads
+            double *dst = root_C + (size_t)start * (size_t)k;
+            ok(spmm_multiply_scatter_device(mine->h, dB, k, 1, &dst, SPMM_KERNEL_AUTO, stream));
+            ok(spmm_csr_stream_sync(mine->h));
+        }
+        MPI_Barrier(MPI_COMM_WORLD); // every block of C has landed in the root's buffer
+        if (worldRank != 0)
+            return FatVector{}; // RowWise.cpp:125
+        return fetch_result(mine->h, root_C, n, k);
     }
 
-    // Gatherv of the row blocks to rank 0 (RowWise.cpp:63-87)
+    // ranks in different processes: multiply on the rank's GPU, Gatherv of the row blocks on host buffers (RowWise.cpp:63-87)
+    std::vector<double> local((size_t)(end - start) * (size_t)k);
+    if (end > start)
+    {
+        Shard &A = row_shard(sparseMatrix, device, start, end);
+        const std::vector<const double *> B = row_pointers(fatVector, 0, (size_t)sparseMatrix.numCols, k);
+        std::vector<double *> rows((size_t)(end - start));
+        for (size_t i = 0; i < rows.size(); ++i)
+            rows[i] = local.data() + i * (size_t)k;
+        ok(spmm_multiply_host_rows(A.h, B.data(), k, rows.data(), SPMM_KERNEL_AUTO));
+    }
     std::vector<int> counts(worldSize), displs(worldSize);
     for (int r = 0, off = 0; r < worldSize; ++r)
     {
         int s, e;
         spmm_partition_rows(sparseMatrix.numRows, worldSize, r, &s, &e);
-        counts[r] = (e - s) * vecCols;
+        counts[r] = (e - s) * k;
         displs[r] = off;
         off += counts[r];
     }
     std::vector<double> gathered;
     if (worldRank == 0)
-        gathered.resize((size_t)sparseMatrix.numRows * (size_t)vecCols + 1);
-    MPI_Gatherv(local.data(), (int)local.size(), MPI_DOUBLE, gathered.data(), counts.data(), displs.data(),
-                MPI_DOUBLE, 0, MPI_COMM_WORLD);
+        gathered.resize(n * (size_t)k + 1);
+    MPI_Gatherv(local.data(), (int)local.size(), MPI_DOUBLE, gathered.data(), counts.data(), displs.data(), MPI_DOUBLE, 0,
+                MPI_COMM_WORLD);
     if (worldRank != 0)
-        return FatVector{}; // RowWise.cpp:125
-    return unpack(gathered.data(), (size_t)sparseMatrix.numRows, vecCols);
+        return FatVector{};
+    return unpack(gathered.data(), n, k);
 }
 
 FatVector sparseMatrixFatVectorMultiplyColumnWise(const SparseMatrix &sparseMatrix, const FatVector &fatVector,
                                                   int vecCols)
 {
     // Column blocks of A (BASELINE.json's reading): rank r owns columns J_r of A and
-    // rows J_r of B, produces a full-size partial C, and the partials are summed to rank 0.
-    validate(sparseMatrix, vecCols);
+    // rows J_r of B, produces a partial C, and the partials are summed in rank order.
+    validate(sparseMatrix, fatVector, vecCols);
     int worldSize = 1, worldRank = 0;
     MPI_Comm_size(MPI_COMM_WORLD, &worldSize);
     MPI_Comm_rank(MPI_COMM_WORLD, &worldRank);
     int c0 = 0, c1 = 0;
     spmm_partition_rows(sparseMatrix.numCols, worldSize, worldRank, &c0, &c1);
-    const int device = device_for_rank(worldRank);
+    const int device = device_for_rank(worldRank), k = vecCols, P = worldSize;
     const size_t n = (size_t)sparseMatrix.numRows;
+    if (n == 0 || k == 0)
+        return worldRank == 0 ? FatVector(n, std::vector<double>((size_t)k, 0.0)) : FatVector{};
 
-    std::vector<double> partial(n * (size_t)vecCols + 1, 0.0);
-    if (n && vecCols > 0)
+    Shard &blk = column_shard(sparseMatrix, device, c0, c1);
+    const std::vector<const double *> B = row_pointers(fatVector, (size_t)c0, (size_t)(c1 - c0), k);
+
+    if (kRanksShareProcess)
     {
-        spmm_csr_t A = cached(sparseMatrix, 2, c0, c1, [&] {
-            spmm_csr_t whole = whole_matrix(sparseMatrix, device), h = nullptr;
-            ok(spmm_csr_column_block(whole, c0, c1, &h));
-            return h;
-        });
-        if (fatVector.size() < (size_t)sparseMatrix.numCols)
-            throw std::runtime_error("spmm_b200: fatVector has fewer rows than the matrix has columns");
-        const FatVector slab(fatVector.begin() + c0, fatVector.begin() + c1);
-        const std::vector<double> B = pack(slab, (size_t)(c1 - c0), vecCols);
-        ok(spmm_multiply_host(A, B.data(), vecCols, partial.data(), SPMM_KERNEL_AUTO));
+        const int root_device = device_for_rank(0);
+        double *root_C = root_buffer(root_device, n, k, worldRank);
+        // partial C of this rank: only the rows its column block touches are computed, [first, last]
+        void *partial_v = nullptr;
+        ok(spmm_device_scratch(device, 1 + worldRank, (long long)(n * (size_t)k * sizeof(double)), &partial_v));
+        double *partial = (double *)partial_v;
+        void *stream = nullptr;
+        const double *dB = nullptr;
+        ok(spmm_stage_b_rows(blk.h, B.data(), 0, c1 - c0, k, &dB, &stream));
+        if (blk.last >= blk.first)
+            ok(spmm_multiply_rows_device(blk.h, blk.first, blk.last + 1, dB, k, partial + (size_t)blk.first * (size_t)k,
+                                         SPMM_KERNEL_AUTO, stream));
+        ok(spmm_csr_stream_sync(blk.h));
+        const long long mine[4] = {(long long)(intptr_t)partial, device, blk.first, blk.last};
+        const std::vector<long long> all = all_gather_words(mine, 4, P); // also the barrier: every partial is complete
+        // reduce-scatter over NVLink: this rank sums row block [rs, re) of every partial that touches it, in rank order,
+        // straight into the root's buffer
+        int rs = 0, re = 0;
+        spmm_partition_rows((int)n, P, worldRank, &rs, &re);
+        if (re > rs)
+        {
+            ok(spmm_peer_enable(device, root_device));
+            // cut the block where the set of contributing ranks changes, so rows a rank never computed are never read
+            std::vector<int> cuts{rs, re};
+            for (int q = 0; q < P; ++q)
+                for (long long edge : {all[(size_t)q * 4 + 2], all[(size_t)q * 4 + 3] + 1})
+                    if (edge > rs && edge < re)
+                        cuts.push_back((int)edge);
+            std::sort(cuts.begin(), cuts.end());
+            cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+            for (size_t c = 0; c + 1 < cuts.size(); ++c)
+            {
+                const int a = cuts[c], b = cuts[c + 1];
+                const long long elems = (long long)(b - a) * k;
+                double *dst = root_C + (size_t)a * (size_t)k;
+                std::vector<const double *> src;
+                for (int q = 0; q < P; ++q)
+                    if (all[(size_t)q * 4 + 2] <= a && b - 1 <= all[(size_t)q * 4 + 3])
+                    {
+                        ok(spmm_peer_enable(device, (int)all[(size_t)q * 4 + 1]));
+                        src.push_back((const double *)(intptr_t)all[(size_t)q * 4] + (size_t)a * (size_t)k);
+                    }
+                if (src.empty())
+                    ok(spmm_fill_zero_device(device, dst, elems * (long long)sizeof(double), stream));
+                else if (elems % 2 == 0 && ((size_t)a * (size_t)k) % 2 == 0)
+                    ok(spmm_reduce_blocks_device(device, (int)src.size(), src.data(), elems, dst, stream));
+                else
+                {
+                    // odd k: 8-byte accesses, same left-to-right order
+                    ok(spmm_copy_device(device, dst, src[0], elems * (long long)sizeof(double), stream));
+                    for (size_t q = 1; q < src.size(); ++q)
+                        ok(spmm_add_device(device, dst, src[q], elems, stream));
+                }
+            }
+            ok(spmm_csr_stream_sync(blk.h));
+        }
+        MPI_Barrier(MPI_COMM_WORLD);
+        if (worldRank != 0)
+            return FatVector{};
+        return fetch_result(blk.h, root_C, n, k);
+    }
+
+    std::vector<double> partial(n * (size_t)k + 1, 0.0);
+    {
+        std::vector<double *> rows(n);
+        for (size_t i = 0; i < n; ++i)
+            rows[i] = partial.data() + i * (size_t)k;
+        ok(spmm_multiply_host_rows(blk.h, B.data(), k, rows.data(), SPMM_KERNEL_AUTO));
     }
     std::vector<double> total;
     if (worldRank == 0)
-        total.resize(n * (size_t)vecCols + 1);
-    MPI_Reduce(partial.data(), total.data(), (int)(n * (size_t)vecCols), MPI_DOUBLE, MPI_SUM, 0, MPI_COMM_WORLD);
+        total.resize(n * (size_t)k + 1);
+    MPI_Reduce(partial.data(), total.data(), (int)(n * (size_t)k), MPI_DOUBLE, MPI_SUM, 0, MPI_COMM_WORLD);
     if (worldRank != 0)
         return FatVector{};
-    return unpack(total.data(), n, vecCols);
+    return unpack(total.data(), n, k);
 }
 
 FatVector sparseMatrixFatVectorMultiplyNonZeroElement(const SparseMatrix &sparseMatrix, const FatVector &fatVector,
                                                       int vecCols)
 {
-    validate(sparseMatrix, vecCols);
+    validate(sparseMatrix, fatVector, vecCols);
     int worldSize = 1, worldRank = 0;
     MPI_Comm_size(MPI_COMM_WORLD, &worldSize);
     MPI_Comm_rank(MPI_COMM_WORLD, &worldRank);
     long long b = 0, e = 0;
     spmm_partition_nnz((long long)sparseMatrix.values.size(), worldSize, worldRank, &b, &e); // NonZeroElement.cpp:24-39
-    const int device = device_for_rank(worldRank);
+    const int device = device_for_rank(worldRank), k = vecCols, P = worldSize;
     const size_t n = (size_t)sparseMatrix.numRows;
+    if (n == 0 || k == 0)
+        return worldRank == 0 ? FatVector(n, std::vector<double>((size_t)k, 0.0)) : FatVector{};
+
+    Shard *mine = e > b ? &nnz_shard(sparseMatrix, device, b, e) : nullptr;
+    const std::vector<const double *> B = row_pointers(fatVector, 0, (size_t)sparseMatrix.numCols, k);
+
+    if (kRanksShareProcess)
+    {
+        const int root_device = device_for_rank(0);
+        void *any_stream = nullptr;
+        double *root_C = nullptr;
+        {
+            // rows no range touches (empty rows between two ranges) must read 0: the root clears its buffer first
+            long long w = 0;
+            if (worldRank == 0)
+            {
+                void *p = nullptr;
+                ok(spmm_device_scratch(root_device, 0, (long long)(n * (size_t)k * sizeof(double)), &p));
+                ok(spmm_fill_zero_device(root_device, p, (long long)(n * (size_t)k * sizeof(double)), nullptr));
+                ok(spmm_device_sync(root_device)); // cleared before any peer copies a row into it
+                w = (long long)(intptr_t)p;
+            }
+            bcast_word(&w);
+            root_C = (double *)(intptr_t)w;
+        }
+        double *local = nullptr;
+        if (mine)
+        {
+            const size_t rows = (size_t)(mine->last - mine->first + 1);
+            void *lv = nullptr;
+            ok(spmm_device_scratch(device, 1 + worldRank, (long long)(rows * (size_t)k * sizeof(double)), &lv));
+            local = (double *)lv;
+            const double *dB = nullptr;
+            ok(spmm_stage_b_rows(mine->h, B.data(), mine->cmin, mine->cmax + 1, k, &dB, &any_stream));
+            ok(spmm_multiply_device(mine->h, dB, k, local, SPMM_KERNEL_AUTO, any_stream));
+            ok(spmm_csr_stream_sync(mine->h));
+        }
+        const long long info[4] = {(long long)(intptr_t)local, device, mine ? mine->first : 0, mine ? (mine->mid ? 1 : 0) : -1};
+        const std::vector<long long> all = all_gather_words(info, 4, P); // barrier: the root's fill and every multiply are done
+        if (mine)
+        {
+            // rows that start inside this range are this rank's to deliver: one contiguous copy into the root's C
+            const int own0 = mine->first + (mine->mid ? 1 : 0);
+            if (mine->last >= own0)
+            {
+                ok(spmm_peer_enable(device, root_device));
+                ok(spmm_copy_device(device, root_C + (size_t)own0 * (size_t)k, local + (size_t)(own0 - mine->first) * (size_t)k,
+                                    (long long)((size_t)(mine->last - own0 + 1) * (size_t)k * sizeof(double)), any_stream));
+                ok(spmm_csr_stream_sync(mine->h));
+            }
+        }
+        MPI_Barrier(MPI_COMM_WORLD);
+        if (worldRank != 0)
+            return FatVector{};
+        // cut rows: the piece of every rank that met the row half-way is added to the owner's piece in rank order
+        // (chains through ranks that lie wholly inside one hub row) — the order of the reference's MPI_Reduce
+        for (int q = 1; q < P; ++q)
+            if (all[(size_t)q * 4 + 3] == 1)
+            {
+                ok(spmm_peer_enable(root_device, (int)all[(size_t)q * 4 + 1]));
+                ok(spmm_add_device(root_device, root_C + (size_t)all[(size_t)q * 4 + 2] * (size_t)k,
+                                   (const double *)(intptr_t)all[(size_t)q * 4], k, nullptr));
+            }
+        ok(spmm_device_sync(root_device)); // the adds ran on the default stream: finished before the download starts
+        return fetch_result(mine ? mine->h : whole_matrix(sparseMatrix, root_device).h, root_C, n, k);
+    }
 
     // full-size zeroed accumulator as in the reference (:54); only the rank's rows are written
-    std::vector<double> local(n * (size_t)vecCols + 1, 0.0);
-    if (e > b && vecCols > 0)
+    std::vector<double> local(n * (size_t)k + 1, 0.0);
+    if (mine)
     {
-        spmm_csr_t A = whole_matrix(sparseMatrix, device);
-        int first = 0, last = -1;
-        ok(spmm_nnz_range_rows(A, b, e, &first, &last));
-        const std::vector<double> B = pack(fatVector, (size_t)sparseMatrix.numCols, vecCols);
-        ok(spmm_multiply_nnz_range_host(A, b, e, first, last, B.data(), vecCols,
-                                        local.data() + (size_t)first * (size_t)vecCols, SPMM_KERNEL_AUTO));
+        std::vector<double *> rows((size_t)(mine->last - mine->first + 1));
+        for (size_t i = 0; i < rows.size(); ++i)
+            rows[i] = local.data() + ((size_t)mine->first + i) * (size_t)k;
+        ok(spmm_multiply_host_rows(mine->h, B.data(), k, rows.data(), SPMM_KERNEL_AUTO));
     }
     std::vector<double> total;
     if (worldRank == 0)
-        total.resize(n * (size_t)vecCols + 1);
-    MPI_Reduce(local.data(), total.data(), (int)(n * (size_t)vecCols), MPI_DOUBLE, MPI_SUM, 0, MPI_COMM_WORLD); // :88
+        total.resize(n * (size_t)k + 1);
+    MPI_Reduce(local.data(), total.data(), (int)(n * (size_t)k), MPI_DOUBLE, MPI_SUM, 0, MPI_COMM_WORLD); // :88
     if (worldRank != 0)
         return FatVector{};
-    return unpack(total.data(), n, vecCols);
+    return unpack(total.data(), n, k);
 }
+
+#ifdef COMPAT_MPI_H
+// Measurement / test hook (not part of the reference surface): run one of the four entry points on P rank-threads the
+// way the reference's main() does (main.cpp:78,162,205,248) — C++ SparseMatrix and FatVector in, FatVector out — and
+// report the first call (shard upload, layout build) and the mean of `steps` further calls. strategy: 0 sequential,
+// 1 row-wise, 2 column-wise, 3 non-zero. C_flat (n_rows*k, may be NULL) receives rank 0's result, serialize()d.
+extern "C" int spmm_entry_run(int strategy, int P, int n_rows, int n_cols, long long nnz, const int *rowptr,
+                              const int *colidx, const double *vals, int k, const double *B_flat, double *C_flat,
+                              int steps, double *first_call_s, double *mean_s, char *err, int err_len)
+{
+    try
+    {
+        SparseMatrix m;
+        m.values.assign(vals, vals + nnz);
+        m.colIndices.assign(colidx, colidx + nnz);
+        m.rowPtr.assign(rowptr, rowptr + n_rows + 1);
+        m.numRows = n_rows;
+        m.numCols = n_cols;
+        FatVector v((size_t)n_cols);
+        for (int i = 0; i < n_cols; ++i)
+            v[(size_t)i].assign(B_flat + (size_t)i * (size_t)k, B_flat + ((size_t)i + 1) * (size_t)k);
+        auto call = [&]() -> FatVector {
+            switch (strategy)
+            {
+            case 0: return sparseMatrixFatVectorMultiply(m, v, k);
+            case 1: return sparseMatrixFatVectorMultiplyRowWise(m, v, k);
+            case 2: return sparseMatrixFatVectorMultiplyColumnWise(m, v, k);
+            default: return sparseMatrixFatVectorMultiplyNonZeroElement(m, v, k);
+            }
+        };
+        std::string failure;
+        double first = 0.0, mean = 0.0;
+        FatVector result;
+        compat_mpi::run(strategy == 0 ? 1 : std::max(1, P), [&](int rank) {
+            try
+            {
+                using clk = std::chrono::steady_clock;
+                MPI_Barrier(MPI_COMM_WORLD);
+                auto t0 = clk::now();
+                FatVector r = call();
+                MPI_Barrier(MPI_COMM_WORLD);
+                const double t_first = std::chrono::duration<double>(clk::now() - t0).count();
+                double t_steps = 0.0;
+                for (int s = 0; s < steps; ++s)
+                {
+                    MPI_Barrier(MPI_COMM_WORLD);
+                    t0 = clk::now();
+                    r = call();
+                    MPI_Barrier(MPI_COMM_WORLD);
+                    t_steps += std::chrono::duration<double>(clk::now() - t0).count();
+                }
+                if (rank == 0)
+                {
+                    first = t_first;
+                    mean = steps > 0 ? t_steps / steps : t_first;
+                    result = std::move(r);
+                }
+                spmm_entry_clear_cache();
+            }
+            catch (const std::exception &ex)
+            {
+                // a failing rank would leave the others waiting in a barrier: report and stop the process-wide run
+                std::fprintf(stderr, "spmm_entry_run: rank %d: %s\n", rank, ex.what());
+                std::fflush(stderr);
+                std::_Exit(3);
+            }
+        });
+        if (first_call_s)
+            *first_call_s = first;
+        if (mean_s)
+            *mean_s = mean;
+        if (C_flat)
+            for (size_t i = 0; i < result.size(); ++i)
+                std::memcpy(C_flat + i * (size_t)k, result[i].data(), sizeof(double) * (size_t)k);
+        return (int)result.size() == n_rows ? 0 : 2;
+    }
+    catch (const std::exception &ex)
+    {
+        if (err && err_len > 0)
+        {
+            std::strncpy(err, ex.what(), (size_t)err_len - 1);
+            err[err_len - 1] = 0;
+        }
+        return 1;
+    }
+}
+#endif

@@ -21,6 +21,9 @@ static thread_local std::string g_last_error;
 
 void set_error(const std::string &msg) { g_last_error = msg; }
 
+static thread_local const char *g_last_kernel = "";
+void note_kernel(const char *name) { g_last_kernel = name; }
+
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 {
     const char *base = std::strrchr(file, '/');
@@ -207,6 +210,7 @@ extern "C"
 {
 
 const char *spmm_last_error(void) { return g_last_error.c_str(); }
+const char *spmm_last_kernel_name(void) { return g_last_kernel; }
 int spmm_version(void) { return 100; }
 
 int spmm_device_count(int *count)
@@ -252,7 +256,6 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "tiled.ksplit") t.tiled_ksplit = value;
     else if (k == "tiled.npw") t.tiled_npw = value;
     else if (k == "host.slabs") t.host_slabs = value;
-    else if (k == "host.pipe") t.host_pipe = value;
     else if (k == "tiled.prefetch") t.tiled_prefetch = value;
     else if (k == "tiled.group") t.tiled_group = value;
     else if (k == "tiled.pdl") t.tiled_pdl = value;
@@ -365,22 +368,19 @@ int spmm_csr_destroy(spmm_csr_t A)
     cudaFree(A->d_C);
     cudaFree(A->d_carry);
     cudaFree(A->d_carry_row);
-    if (A->h_stage)
-        cudaFreeHost(A->h_stage);
+    if (A->h_B)
+        cudaFreeHost(A->h_B);
+    if (A->h_C)
+        cudaFreeHost(A->h_C);
     if (A->stream)
         cudaStreamDestroy(A->stream);
     if (A->stream_up)
     {
         cudaStreamDestroy(A->stream_up);
         cudaStreamDestroy(A->stream_down);
-        for (int i = 0; i < 32; ++i)
-        {
-            if (!A->ev_up[i])
-                continue;
-            cudaEventDestroy(A->ev_up[i]);
-            cudaEventDestroy(A->ev_done[i]);
-        }
     }
+    for (cudaEvent_t e : A->events)
+        cudaEventDestroy(e);
     delete A;
     return SPMM_OK;
 }
@@ -445,14 +445,8 @@ static void auto_tile_layout(spmm_csr_t A, int k)
     if (A->tl_tried || A->tl_T != 0 || tuning().tiled == 0 || k < 4 || k % 2 != 0 || A->nnz < 200000 || A->nnz > (64ll << 20))
         return;
     A->tl_tried = true;
-    const int saved = tuning().tiled_ksplit, saved_kt = tuning().tiled_kt;
-    if (saved == 0)
-        tuning().tiled_ksplit = k >= 64 ? 4 : (k >= 32 ? 2 : 1); // longer chunks shared by several CTAs, one k-tile group each
-    if (saved_kt == 0 && k <= 8)
-        tuning().tiled_kt = 8; // 64-byte window rows: half the bytes staged and read for k <= 8
-    const int brc = spmm_csr_build_tiles(A, -1, 0);
-    tuning().tiled_ksplit = saved;
-    tuning().tiled_kt = saved_kt;
+    const int brc = build_tiles(A, -1, 0, tuning().tiled_kt > 0 ? tuning().tiled_kt : tiles_kt_for(k),
+                                tuning().tiled_ksplit > 0 ? tuning().tiled_ksplit : tiles_ksplit_for(k));
     A->tl_auto = true;
     if (brc != SPMM_OK)
         free_tiles(A);
@@ -645,301 +639,131 @@ __global__ void __launch_bounds__(256) reduce_blocks_kernel(const ReduceSrc src,
 extern "C" int spmm_reduce_blocks_device(int device, int n_src, const double *const *d_src_list, long long n_elems,
                                          double *d_out, void *stream)
 {
-    SPMM_REQUIRE(n_src >= 1 && n_src <= 8, "n_src must be between 1 and 8");
+    SPMM_REQUIRE(n_src >= 1 && n_src <= 1024, "n_src must be between 1 and 1024");
     SPMM_REQUIRE(d_src_list != nullptr && d_out != nullptr, "source list / output is NULL");
     SPMM_REQUIRE(n_elems >= 0 && n_elems % 2 == 0, "n_elems must be even (16-byte accesses)");
     if (n_elems == 0)
         return SPMM_OK;
-    ReduceSrc src = {};
     for (int i = 0; i < n_src; ++i)
-    {
         SPMM_REQUIRE(d_src_list[i] != nullptr && (uintptr_t)d_src_list[i] % 16 == 0, "sources must be 16-byte aligned");
-        src.p[i] = d_src_list[i];
-    }
     SPMM_REQUIRE((uintptr_t)d_out % 16 == 0, "output must be 16-byte aligned");
     SPMM_CUDA(cudaSetDevice(device));
     const long long pairs = n_elems / 2;
     const int grid = (int)std::min<long long>((pairs + 255) / 256, (long long)device_props(device).sm_count * 8);
-    reduce_blocks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, n_src, d_out, pairs);
+    // up to 8 sources per pass; further passes continue the same left-to-right sum from d_out
+    for (int first = 0; first < n_src;)
+    {
+        ReduceSrc src = {};
+        int n = 0;
+        if (first > 0)
+            src.p[n++] = d_out;
+        while (n < 8 && first < n_src)
+            src.p[n++] = d_src_list[first++];
+        reduce_blocks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, n, d_out, pairs);
+        SPMM_CUDA(cudaGetLastError());
+    }
+    return SPMM_OK;
+}
+
+// dst[i] += src[i] (any n, any alignment): the non-zero strategy's cut rows, added on the root device in rank order
+__global__ void __launch_bounds__(256) add_kernel(double *__restrict__ dst, const double *__restrict__ src, long long n)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] += src[i];
+}
+
+extern "C" int spmm_add_device(int device, double *d_dst, const double *d_src, long long n_elems, void *stream)
+{
+    SPMM_REQUIRE(n_elems >= 0, "negative size");
+    if (n_elems == 0)
+        return SPMM_OK;
+    SPMM_REQUIRE(d_dst != nullptr && d_src != nullptr, "d_dst / d_src is NULL");
+    SPMM_CUDA(cudaSetDevice(device));
+    const int grid = (int)std::min<long long>((n_elems + 255) / 256, (long long)device_props(device).sm_count * 8);
+    add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_dst, d_src, n_elems);
     SPMM_CUDA(cudaGetLastError());
     return SPMM_OK;
 }
 
-// device staging buffers of the host-buffer entry points, grown on demand
-static int ensure_host_buffers(spmm_csr_t A, size_t nb, size_t nc)
+extern "C" int spmm_copy_device(int device, void *d_dst, const void *d_src, long long bytes, void *stream)
 {
-    if (A->d_B_elems < nb)
-    {
-        cudaFree(A->d_B);
-        A->d_B = nullptr;
-        A->d_B_elems = 0;
-        SPMM_CUDA(cudaMalloc(&A->d_B, sizeof(double) * std::max<size_t>(nb, 1)));
-        A->d_B_elems = nb;
-    }
-    if (A->d_C_elems < nc)
-    {
-        cudaFree(A->d_C);
-        A->d_C = nullptr;
-        A->d_C_elems = 0;
-        SPMM_CUDA(cudaMalloc(&A->d_C, sizeof(double) * std::max<size_t>(nc, 1)));
-        A->d_C_elems = nc;
-    }
-    return SPMM_OK;
-}
-
-// compute stream + upload / download streams and events of the pipelined host-buffer multiplies
-static int ensure_pipe_streams(spmm_csr_t A)
-{
-    if (!A->stream)
-        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
-    if (!A->stream_up)
-    {
-        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_up, cudaStreamNonBlocking));
-        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_down, cudaStreamNonBlocking));
-        for (int i = 0; i < 32; ++i)
-        {
-            SPMM_CUDA(cudaEventCreateWithFlags(&A->ev_up[i], cudaEventDisableTiming));
-            SPMM_CUDA(cudaEventCreateWithFlags(&A->ev_done[i], cudaEventDisableTiming));
-        }
-    }
-    return SPMM_OK;
-}
-
-// Host-buffer plumbing shared by the *_host entry points: B up, launch, C_local down.
-template <typename Launch>
-static int host_call(spmm_csr_t A, const double *B, size_t nb, double *C, size_t nc, Launch launch)
-{
-    SPMM_CUDA(cudaSetDevice(A->device));
-    if (!A->stream)
-        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
-    {
-        const int rc = ensure_host_buffers(A, nb, nc);
-        if (rc)
-            return rc;
-    }
-    // Pageable host buffers (std::vector / numpy storage) are copied directly; cudaMemcpyAsync
-    // from pageable memory stages through the driver's pinned bounce buffers.
-    if (nb)
-        SPMM_CUDA(cudaMemcpyAsync(A->d_B, B, sizeof(double) * nb, cudaMemcpyHostToDevice, A->stream));
-    int rc = launch(A->d_B, A->d_C, A->stream);
-    if (rc)
-        return rc;
-    SPMM_CUDA(cudaMemcpyAsync(C, A->d_C, sizeof(double) * nc, cudaMemcpyDeviceToHost, A->stream));
-    SPMM_CUDA(cudaStreamSynchronize(A->stream));
-    return SPMM_OK;
-}
-
-// Host-buffer multiply in k-slabs: while slab s is multiplied and its C columns travel down, the B columns of
-// slab s+1 travel up — PCIe is full duplex, so the upload of B and the download of C overlap instead of adding up.
-static int host_call_slabs(spmm_csr_t A, const double *B, int k, double *C, int kernel, int slabs)
-{
-    SPMM_CUDA(cudaSetDevice(A->device));
-    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)A->n_rows * (size_t)k;
-    {
-        int rc = ensure_pipe_streams(A);
-        if (!rc)
-            rc = ensure_host_buffers(A, nb, nc);
-        if (rc)
-            return rc;
-    }
-    const int ks = k / slabs; // columns per slab (k % slabs == 0 checked by the caller)
-    const size_t pitch = sizeof(double) * (size_t)k, width = sizeof(double) * (size_t)ks;
-    for (int sidx = 0; sidx < slabs; ++sidx)
-    {
-        const int k0 = sidx * ks;
-        SPMM_CUDA(cudaMemcpy2DAsync(A->d_B + k0, pitch, B + k0, pitch, width, (size_t)A->n_cols, cudaMemcpyHostToDevice,
-                                    A->stream_up));
-        SPMM_CUDA(cudaEventRecord(A->ev_up[sidx], A->stream_up));
-        SPMM_CUDA(cudaStreamWaitEvent(A->stream, A->ev_up[sidx], 0));
-        const int rc = spmm_multiply_strided_device(A, A->d_B, k, A->d_C, k, k0, ks, kernel, A->stream);
-        if (rc)
-            return rc;
-        SPMM_CUDA(cudaEventRecord(A->ev_done[sidx], A->stream));
-        SPMM_CUDA(cudaStreamWaitEvent(A->stream_down, A->ev_done[sidx], 0));
-        SPMM_CUDA(cudaMemcpy2DAsync(C + k0, pitch, A->d_C + k0, pitch, width, (size_t)A->n_rows, cudaMemcpyDeviceToHost,
-                                    A->stream_down));
-    }
-    SPMM_CUDA(cudaStreamSynchronize(A->stream_down));
-    return SPMM_OK;
-}
-
-// ---- row-block pipeline of the host-buffer multiply ------------------------------------------------------------------
-// For matrices whose rows look only a little beyond their own index (banded / FEM-like), B is uploaded in row order and
-// block j of C is multiplied as soon as the B rows it reads have arrived, then travels down while later blocks are still
-// being uploaded and multiplied: both PCIe directions run on contiguous pieces (the k-slab pipeline above moves strided
-// slabs and still waits for whole slabs). hp_need[j] = 1 + the largest column the rows of blocks 0..j hold.
-// Measured on the B200 box (cfg2 k=64, 62 MB each way): 1.94 ms against 1.82 ms for two k-slabs — with both directions busy
-// all the time each runs at ~32 GB/s (56 GB/s alone), so the overlap buys nothing there; opt-in (spmm_tune_set("host.pipe", 1 | -1)).
-constexpr int HP_BLOCKS = 16;
-
-__global__ void block_maxcol_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx, const int *__restrict__ cut,
-                                    int *__restrict__ out)
-{
-    const int e0 = rowptr[cut[blockIdx.x]], e1 = rowptr[cut[blockIdx.x + 1]];
-    int m = -1;
-    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x)
-        m = max(m, colidx[e]);
-    m = __reduce_max_sync(0xFFFFFFFFu, m);
-    if ((threadIdx.x & 31) == 0)
-        atomicMax(out + blockIdx.x, m);
-}
-
-static int host_pipe_prepare(spmm_csr_t A)
-{
-    if (A->hp_blocks)
+    SPMM_REQUIRE(bytes >= 0, "negative size");
+    if (bytes == 0)
         return SPMM_OK;
-    const int nb = std::max(1, std::min(HP_BLOCKS, A->n_rows));
-    std::vector<int> cut((size_t)nb + 1), need((size_t)nb, 0);
-    for (int j = 0; j <= nb; ++j)
-        cut[j] = (int)((long long)A->n_rows * j / nb);
+    SPMM_REQUIRE(d_dst != nullptr && d_src != nullptr, "d_dst / d_src is NULL");
+    SPMM_CUDA(cudaSetDevice(device));
+    // unified addressing: the runtime routes the copy between whichever devices own the two buffers (NVLink when peers)
+    SPMM_CUDA(cudaMemcpyAsync(d_dst, d_src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return SPMM_OK;
+}
+
+extern "C" int spmm_fill_zero_device(int device, void *d_dst, long long bytes, void *stream)
+{
+    SPMM_REQUIRE(bytes >= 0 && (d_dst != nullptr || bytes == 0), "bad fill request");
+    SPMM_CUDA(cudaSetDevice(device));
+    if (bytes)
+        SPMM_CUDA(cudaMemsetAsync(d_dst, 0, (size_t)bytes, (cudaStream_t)stream));
+    return SPMM_OK;
+}
+
+extern "C" int spmm_device_sync(int device)
+{
+    SPMM_CUDA(cudaSetDevice(device));
+    SPMM_CUDA(cudaDeviceSynchronize());
+    return SPMM_OK;
+}
+
+// smallest and largest column id of a handle: the B rows a shard reads lie in [min, max]
+__global__ void __launch_bounds__(256) column_span_kernel(const int *__restrict__ colidx, long long nnz, int *out)
+{
+    int lo = 0x7FFFFFFF, hi = -1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride)
+    {
+        const int c = colidx[i];
+        lo = min(lo, c);
+        hi = max(hi, c);
+    }
+    lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+    hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    if ((threadIdx.x & 31) == 0)
+    {
+        atomicMin(out, lo);
+        atomicMax(out + 1, hi);
+    }
+}
+
+extern "C" int spmm_csr_column_span(spmm_csr_t A, int *min_col, int *max_col)
+{
+    SPMM_REQUIRE(A != nullptr && min_col && max_col, "handle / output is NULL");
+    *min_col = 0;
+    *max_col = -1;
+    if (A->nnz == 0)
+        return SPMM_OK;
+    SPMM_CUDA(cudaSetDevice(A->device));
     int *d = nullptr;
-    SPMM_CUDA(cudaMalloc(&d, sizeof(int) * (2 * (size_t)nb + 1)));
-    cudaError_t e = cudaMemcpy(d, cut.data(), sizeof(int) * ((size_t)nb + 1), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess)
-        e = cudaMemset(d + nb + 1, 0xFF, sizeof(int) * (size_t)nb); // -1
+    SPMM_CUDA(cudaMalloc(&d, 2 * sizeof(int)));
+    const int init[2] = {0x7FFFFFFF, -1};
+    cudaError_t e = cudaMemcpy(d, init, sizeof init, cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
     {
-        block_maxcol_kernel<<<nb, 1024>>>(A->d_rowptr, A->d_colidx, d, d + nb + 1);
+        const int grid = (int)std::min<long long>((A->nnz + 255) / 256, (long long)device_props(A->device).sm_count * 8);
+        column_span_kernel<<<grid, 256>>>(A->d_colidx, A->nnz, d);
         e = cudaGetLastError();
     }
+    int h[2] = {0, -1};
     if (e == cudaSuccess)
-        e = cudaMemcpy(need.data(), d + nb + 1, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost);
+        e = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
     cudaFree(d);
     SPMM_CUDA(e);
-    int run = 0;
-    for (int j = 0; j < nb; ++j)
-    {
-        run = std::max(run, need[j] + 1);
-        need[j] = run;
-    }
-    A->hp_cut = cut;
-    A->hp_need = need;
-    A->hp_blocks = nb;
+    *min_col = h[0];
+    *max_col = h[1];
     return SPMM_OK;
-}
-
-// time of the pipeline in units of "bytes over one PCIe direction": upload in row order, block j after its rows, download in order
-static double host_pipe_estimate(const spmm_csr_s *A)
-{
-    double t_done = 0.0, t_down = 0.0;
-    for (int j = 0; j < A->hp_blocks; ++j)
-    {
-        t_done = std::max(t_done, (double)A->hp_need[j]);
-        t_down = std::max(t_down, t_done) + (double)(A->hp_cut[j + 1] - A->hp_cut[j]);
-    }
-    return t_down; // in rows (x k x 8 bytes)
-}
-
-static int host_call_rowpipe(spmm_csr_t A, const double *B, int k, double *C, int kernel)
-{
-    SPMM_CUDA(cudaSetDevice(A->device));
-    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)A->n_rows * (size_t)k;
-    {
-        int rc = ensure_pipe_streams(A);
-        if (!rc)
-            rc = ensure_host_buffers(A, nb, nc);
-        if (rc)
-            return rc;
-    }
-    // B travels up in HP_BLOCKS contiguous pieces of rows
-    const int nup = std::max(1, std::min(HP_BLOCKS, A->n_cols));
-    std::vector<int> up_cut((size_t)nup + 1);
-    for (int i = 0; i <= nup; ++i)
-        up_cut[i] = (int)((long long)A->n_cols * i / nup);
-    int issued = 0; // upload pieces issued so far
-    for (int j = 0; j < A->hp_blocks; ++j)
-    {
-        const int r0 = A->hp_cut[j], r1 = A->hp_cut[j + 1];
-        while (issued < nup && up_cut[issued] < A->hp_need[j])
-        {
-            const size_t o = (size_t)up_cut[issued] * k, n = (size_t)(up_cut[issued + 1] - up_cut[issued]) * k;
-            SPMM_CUDA(cudaMemcpyAsync(A->d_B + o, B + o, sizeof(double) * n, cudaMemcpyHostToDevice, A->stream_up));
-            SPMM_CUDA(cudaEventRecord(A->ev_up[issued], A->stream_up));
-            ++issued;
-        }
-        if (issued > 0)
-            SPMM_CUDA(cudaStreamWaitEvent(A->stream, A->ev_up[issued - 1], 0));
-        if (r1 > r0)
-        {
-            const int rc = spmm_multiply_rows_device(A, r0, r1, A->d_B, k, A->d_C + (size_t)r0 * k, kernel, A->stream);
-            if (rc)
-                return rc;
-            SPMM_CUDA(cudaEventRecord(A->ev_done[j], A->stream));
-            SPMM_CUDA(cudaStreamWaitEvent(A->stream_down, A->ev_done[j], 0));
-            SPMM_CUDA(cudaMemcpyAsync(C + (size_t)r0 * k, A->d_C + (size_t)r0 * k, sizeof(double) * (size_t)(r1 - r0) * k,
-                                      cudaMemcpyDeviceToHost, A->stream_down));
-        }
-    }
-    // (rows of B no block reads are not uploaded at all)
-    SPMM_CUDA(cudaStreamSynchronize(A->stream_down));
-    SPMM_CUDA(cudaStreamSynchronize(A->stream));
-    return SPMM_OK;
-}
-
-extern "C" int spmm_multiply_host(spmm_csr_t A, const double *B, int k, double *C, int kernel)
-{
-    SPMM_REQUIRE(A != nullptr, "handle is NULL");
-    SPMM_REQUIRE(k >= 0, "k is negative");
-    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)A->n_rows * (size_t)k;
-    if (nc == 0)
-        return SPMM_OK;
-    SPMM_REQUIRE(C != nullptr && (B != nullptr || nb == 0), "B/C is NULL");
-    const bool large = (nb + nc) * sizeof(double) >= (16u << 20);
-    // banded / FEM-like matrices: row-block pipeline when it beats the k-slab pipeline (1.5 x the larger direction)
-    if (nb > 0 && A->nnz > 0 && tuning().host_pipe != 0 && (large || tuning().host_pipe == 1) &&
-        (kernel == SPMM_KERNEL_AUTO || kernel == SPMM_KERNEL_ROWS || kernel == SPMM_KERNEL_MERGE))
-    {
-        const int prc = host_pipe_prepare(A);
-        if (prc)
-            return prc;
-        const double slab_units = 1.5 * (double)std::max(A->n_rows, A->n_cols);
-        if (tuning().host_pipe == 1 || host_pipe_estimate(A) <= 0.85 * slab_units)
-            return host_call_rowpipe(A, B, k, C, kernel);
-    }
-    // large operands: pipeline two k-slabs so that the two PCIe directions overlap
-    int slabs = tuning().host_slabs;
-    if (slabs <= 0)
-        slabs = ((nb + nc) * sizeof(double) >= (16u << 20) && k >= 32) ? 2 : 1; // measured: 2.35 -> 1.90 ms at k=64; 4 slabs of 128-byte rows copy slower
-    while (slabs > 1 && (k % slabs != 0 || (k / slabs) % 2 != 0))
-        --slabs;
-    if (slabs > 1 && slabs <= 8 && nb > 0)
-        return host_call_slabs(A, B, k, C, kernel, slabs);
-    return host_call(A, B, nb, C, nc, [&](const double *dB, double *dC, cudaStream_t s) {
-        return spmm_multiply_device(A, dB, k, dC, kernel, s);
-    });
 }
 
 extern "C"
 {
-
-int spmm_multiply_rows_host(spmm_csr_t A, int row_begin, int row_end, const double *B, int k, double *C_local,
-                            int kernel)
-{
-    SPMM_REQUIRE(A != nullptr, "handle is NULL");
-    SPMM_REQUIRE(k >= 0, "k is negative");
-    SPMM_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= A->n_rows, "row range outside the matrix");
-    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)(row_end - row_begin) * (size_t)k;
-    if (nc == 0)
-        return SPMM_OK;
-    SPMM_REQUIRE(C_local != nullptr && (B != nullptr || nb == 0), "B/C is NULL");
-    return host_call(A, B, nb, C_local, nc, [&](const double *dB, double *dC, cudaStream_t s) {
-        return spmm_multiply_rows_device(A, row_begin, row_end, dB, k, dC, kernel, s);
-    });
-}
-
-int spmm_multiply_nnz_range_host(spmm_csr_t A, long long nnz_begin, long long nnz_end, int first_row, int last_row,
-                                 const double *B, int k, double *C_local, int kernel)
-{
-    SPMM_REQUIRE(A != nullptr, "handle is NULL");
-    SPMM_REQUIRE(k >= 0, "k is negative");
-    if (last_row < first_row || k == 0 || nnz_begin == nnz_end)
-        return SPMM_OK;
-    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)(last_row - first_row + 1) * (size_t)k;
-    SPMM_REQUIRE(C_local != nullptr && B != nullptr, "B/C is NULL");
-    return host_call(A, B, nb, C_local, nc, [&](const double *dB, double *dC, cudaStream_t s) {
-        return spmm_multiply_nnz_range_device(A, nnz_begin, nnz_end, first_row, last_row, dB, k, dC, kernel, s);
-    });
-}
 
 // ---- partition formulas -------------------------------------------------------------
 

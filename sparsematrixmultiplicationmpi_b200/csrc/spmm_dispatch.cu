@@ -142,11 +142,13 @@ int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_l
     args.b_bytes = (ldb == kc) ? (long long)A->n_cols * ldb * 8 : 0;
     if (sweep)
     {
+        note_kernel("spmm_rows_sweep_kernel");
         const int rc = launch_sweep_w2(A, s.kl, s.nv, np, u, t.rows_threads > 0 ? t.rows_threads : 512, args, s.tiles,
                                        A->device, stream);
         if (rc != -1)
             return rc;
     }
+    note_kernel("spmm_rows_kernel");
     return s.w == 2 ? launch_rows_w2(A, s.kl, s.nv, np, u, args, s.tiles, A->device, stream)
                     : launch_rows_w1(A, s.kl, s.nv, np, u, args, s.tiles, A->device, stream);
 }
@@ -208,6 +210,7 @@ int launch_merge(spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, lo
     args.carry = A->d_carry;
     args.carry_row = A->d_carry_row;
     args.ldcarry = ldcarry;
+    note_kernel("spmm_merge_kernel");
     return s.w == 2 ? launch_merge_w2(s.kl, s.nv, u, args, s.tiles, stream)
                     : launch_merge_w1(s.kl, s.nv, u, args, s.tiles, stream);
 }

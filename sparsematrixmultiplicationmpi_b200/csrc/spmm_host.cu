@@ -1,0 +1,652 @@
+// spmm_host.cu — the host-buffer half of the C-ABI: what the reference-shaped entry points call.
+//
+// The reference's operands are host objects: SparseMatrix (three std::vector) and FatVector =
+// std::vector<std::vector<double>>, i.e. N separately allocated rows of k doubles
+// ("Source Code/MatrixDefinitions.h":14-22). Crossing to the device therefore means
+//   pack (N row buffers -> one row-major image, the reference's serialize(), utils.cpp:216-228)
+//   -> H2D -> kernel -> D2H -> unpack (deserialize(), utils.cpp:237-253).
+// Here pack and unpack run on a small host thread pool straight into / out of pinned staging
+// memory owned by the handle, in row chunks, so the copy engine moves chunk c while the CPU packs
+// chunk c+1; wide operands additionally travel in two k-slabs so that the upload of the second
+// overlaps the download of the first (PCIe is full duplex). A flat pageable buffer (a C caller's
+// malloc, numpy storage) takes the same route with "row i = base + i*k"; a flat pinned buffer is
+// handed to the copy engine as it is.
+//
+// Multi-rank strategies inside one process (compat MPI rank-threads, one GPU per rank): helpers to
+// stage only the B rows a shard reads, to let the kernel store C rows straight into the root
+// rank's device buffer over NVLink (peer access), and to bring the finished C down once.
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "spmm_internal.h"
+
+namespace spmm
+{
+
+// ---- host thread pool: parallel_for over chunk indices; the caller takes part ----------------------------------------
+namespace
+{
+struct Job
+{
+    std::function<void(int)> fn;
+    int n = 0;
+    std::atomic<int> next{0}, done{0};
+};
+
+class Pool
+{
+  public:
+    Pool()
+    {
+        int n = (int)std::thread::hardware_concurrency();
+        if (const char *e = getenv("SPMM_HOST_THREADS"))
+            n = atoi(e);
+        n = std::max(1, std::min(n, 32));
+        for (int i = 1; i < n; ++i) // the caller is the n-th
+            th_.emplace_back([this] { worker(); });
+    }
+    ~Pool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_)
+            t.join();
+    }
+    int threads() const { return (int)th_.size() + 1; }
+    void parallel_for(int n, const std::function<void(int)> &fn)
+    {
+        if (n <= 0)
+            return;
+        if (n == 1 || th_.empty())
+        {
+            for (int i = 0; i < n; ++i)
+                fn(i);
+            return;
+        }
+        auto job = std::make_shared<Job>();
+        job->fn = fn;
+        job->n = n;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            q_.push_back(job);
+        }
+        cv_.notify_all();
+        run(job);
+        while (job->done.load(std::memory_order_acquire) < n)
+            std::this_thread::yield();
+    }
+
+  private:
+    void run(const std::shared_ptr<Job> &j)
+    {
+        for (;;)
+        {
+            const int i = j->next.fetch_add(1);
+            if (i >= j->n)
+                break;
+            j->fn(i);
+            j->done.fetch_add(1, std::memory_order_release);
+        }
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto it = q_.begin(); it != q_.end(); ++it)
+            if (*it == j)
+            {
+                q_.erase(it);
+                break;
+            }
+    }
+    void worker()
+    {
+        for (;;)
+        {
+            std::shared_ptr<Job> j;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (stop_)
+                    return;
+                j = q_.front();
+            }
+            run(j);
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::shared_ptr<Job>> q_;
+    bool stop_ = false;
+};
+
+Pool &pool()
+{
+    static Pool p;
+    return p;
+}
+
+// A dense host operand: either N row pointers (the memory shape of a FatVector) or one flat row-major block.
+struct HostRows
+{
+    const double *const *rows = nullptr; // rows[i] -> k doubles
+    const double *flat = nullptr;        // row i at flat + i*ld
+    long long ld = 0;
+    const double *at(long long i) const { return rows ? rows[i] : flat + i * ld; }
+};
+struct HostRowsOut
+{
+    double *const *rows = nullptr;
+    double *flat = nullptr;
+    long long ld = 0;
+    double *at(long long i) const { return rows ? rows[i] : flat + i * ld; }
+};
+
+bool is_pinned(const void *p)
+{
+    if (!p)
+        return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+constexpr size_t CHUNK_BYTES = 2u << 20; // rows per pipeline chunk: about 2 MB of the slab being moved
+
+int ensure_pinned(double **buf, size_t *have, size_t want)
+{
+    if (*have >= want)
+        return SPMM_OK;
+    if (*buf)
+        cudaFreeHost(*buf);
+    *buf = nullptr;
+    *have = 0;
+    SPMM_CUDA(cudaHostAlloc((void **)buf, sizeof(double) * std::max<size_t>(want, 1), cudaHostAllocDefault));
+    *have = want;
+    return SPMM_OK;
+}
+
+int ensure_device(double **buf, size_t *have, size_t want)
+{
+    if (*have >= want)
+        return SPMM_OK;
+    cudaFree(*buf);
+    *buf = nullptr;
+    *have = 0;
+    SPMM_CUDA(cudaMalloc((void **)buf, sizeof(double) * std::max<size_t>(want, 1)));
+    *have = want;
+    return SPMM_OK;
+}
+
+int ensure_streams(spmm_csr_t A)
+{
+    if (!A->stream)
+        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
+    if (!A->stream_up)
+    {
+        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_up, cudaStreamNonBlocking));
+        SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_down, cudaStreamNonBlocking));
+    }
+    return SPMM_OK;
+}
+
+int event_at(spmm_csr_t A, size_t i, cudaEvent_t *out)
+{
+    while (A->events.size() <= i)
+    {
+        cudaEvent_t e;
+        SPMM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        A->events.push_back(e);
+    }
+    *out = A->events[i];
+    return SPMM_OK;
+}
+
+// Rows [r0, r1) x columns [k0, k0+kc) of `src` -> the device image d (leading dimension k, row r at d + r*k), enqueued on
+// `s`. Pageable / row-pointer sources are packed chunk by chunk into the pinned mirror `stage` (same geometry as d) by the
+// pool while the copy engine moves the chunks already packed.
+int upload_rows(const HostRows &src, bool direct, double *stage, double *d, int r0, int r1, int k, int k0, int kc,
+                cudaStream_t s)
+{
+    if (r1 <= r0 || kc <= 0)
+        return SPMM_OK;
+    const size_t pitch = sizeof(double) * (size_t)k, width = sizeof(double) * (size_t)kc;
+    if (direct)
+    {
+        const double *h = src.flat + (long long)r0 * src.ld + k0;
+        if (kc == k && src.ld == k)
+            SPMM_CUDA(cudaMemcpyAsync(d + (size_t)r0 * k, h, pitch * (size_t)(r1 - r0), cudaMemcpyHostToDevice, s));
+        else
+            SPMM_CUDA(cudaMemcpy2DAsync(d + (size_t)r0 * k + k0, pitch, h, sizeof(double) * (size_t)src.ld, width,
+                                        (size_t)(r1 - r0), cudaMemcpyHostToDevice, s));
+        return SPMM_OK;
+    }
+    const int rows_per_chunk = (int)std::max<size_t>(64, CHUNK_BYTES / width);
+    const int sub = std::max(16, rows_per_chunk / (4 * pool().threads())); // rows per pool task
+    for (int c0 = r0; c0 < r1; c0 += rows_per_chunk)
+    {
+        const int c1 = std::min(r1, c0 + rows_per_chunk);
+        pool().parallel_for((c1 - c0 + sub - 1) / sub, [&](int t) {
+            const int a = c0 + t * sub, b = std::min(c1, a + sub);
+            for (int r = a; r < b; ++r)
+                std::memcpy(stage + (size_t)r * k + k0, src.at(r) + k0, width);
+        });
+        if (kc == k)
+            SPMM_CUDA(cudaMemcpyAsync(d + (size_t)c0 * k, stage + (size_t)c0 * k, pitch * (size_t)(c1 - c0),
+                                      cudaMemcpyHostToDevice, s));
+        else
+            SPMM_CUDA(cudaMemcpy2DAsync(d + (size_t)c0 * k + k0, pitch, stage + (size_t)c0 * k + k0, pitch, width,
+                                        (size_t)(c1 - c0), cudaMemcpyHostToDevice, s));
+    }
+    return SPMM_OK;
+}
+
+// One pending download chunk: rows [c0,c1) x columns [k0,k0+kc) land in the pinned mirror; `ev` says when.
+struct Pending
+{
+    int c0, c1, k0, kc;
+    cudaEvent_t ev;
+};
+
+// Enqueue the download of rows [0,n) x columns [k0,k0+kc) of the device image d_c (ld k) on `s`.
+int download_rows(spmm_csr_t A, const HostRowsOut &dst, bool direct, double *stage, const double *d_c, int n, int k,
+                  int k0, int kc, cudaStream_t s, std::vector<Pending> *pending, size_t *next_event)
+{
+    if (n <= 0 || kc <= 0)
+        return SPMM_OK;
+    const size_t pitch = sizeof(double) * (size_t)k, width = sizeof(double) * (size_t)kc;
+    if (direct)
+    {
+        if (kc == k && dst.ld == k)
+            SPMM_CUDA(cudaMemcpyAsync(dst.flat, d_c, pitch * (size_t)n, cudaMemcpyDeviceToHost, s));
+        else
+            SPMM_CUDA(cudaMemcpy2DAsync(dst.flat + k0, sizeof(double) * (size_t)dst.ld, d_c + k0, pitch, width, (size_t)n,
+                                        cudaMemcpyDeviceToHost, s));
+        return SPMM_OK;
+    }
+    const int rows_per_chunk = (int)std::max<size_t>(64, CHUNK_BYTES / width);
+    for (int c0 = 0; c0 < n; c0 += rows_per_chunk)
+    {
+        const int c1 = std::min(n, c0 + rows_per_chunk);
+        if (kc == k)
+            SPMM_CUDA(cudaMemcpyAsync(stage + (size_t)c0 * k, d_c + (size_t)c0 * k, pitch * (size_t)(c1 - c0),
+                                      cudaMemcpyDeviceToHost, s));
+        else
+            SPMM_CUDA(cudaMemcpy2DAsync(stage + (size_t)c0 * k + k0, pitch, d_c + (size_t)c0 * k + k0, pitch, width,
+                                        (size_t)(c1 - c0), cudaMemcpyDeviceToHost, s));
+        Pending p{c0, c1, k0, kc, nullptr};
+        const int rc = event_at(A, (*next_event)++, &p.ev);
+        if (rc)
+            return rc;
+        SPMM_CUDA(cudaEventRecord(p.ev, s));
+        pending->push_back(p);
+    }
+    return SPMM_OK;
+}
+
+// Unpack the chunks as they arrive (deserialize(), utils.cpp:237-253, chunk by chunk on the pool).
+int unpack_pending(const HostRowsOut &dst, const double *stage, int k, const std::vector<Pending> &pending)
+{
+    for (const Pending &p : pending)
+    {
+        SPMM_CUDA(cudaEventSynchronize(p.ev));
+        const size_t width = sizeof(double) * (size_t)p.kc;
+        const int sub = std::max(16, (p.c1 - p.c0) / (4 * pool().threads()));
+        pool().parallel_for((p.c1 - p.c0 + sub - 1) / sub, [&](int t) {
+            const int a = p.c0 + t * sub, b = std::min(p.c1, a + sub);
+            for (int r = a; r < b; ++r)
+                std::memcpy(dst.at(r) + p.k0, stage + (size_t)r * k + p.k0, width);
+        });
+    }
+    return SPMM_OK;
+}
+
+// The whole host-buffer call: rows [b0,b1) of B up (all other rows of the device image are not read by this launch),
+// `launch(dB, dC, k0, kc, stream)` per k-slab, c_rows rows of C down.
+template <typename Launch>
+int host_multiply(spmm_csr_t A, const HostRows &B, int b0, int b1, int k, const HostRowsOut &C, int c_rows, int slabs,
+                  Launch launch)
+{
+    SPMM_CUDA(cudaSetDevice(A->device));
+    std::lock_guard<std::mutex> guard(A->host_mu); // staging buffers and streams of a handle serve one call at a time
+    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)c_rows * (size_t)k;
+    int rc = ensure_streams(A);
+    if (!rc)
+        rc = ensure_device(&A->d_B, &A->d_B_elems, nb);
+    if (!rc)
+        rc = ensure_device(&A->d_C, &A->d_C_elems, nc);
+    const bool b_direct = !B.rows && is_pinned(B.flat), c_direct = !C.rows && is_pinned(C.flat);
+    if (!rc && !b_direct)
+        rc = ensure_pinned(&A->h_B, &A->h_B_elems, nb);
+    if (!rc && !c_direct)
+        rc = ensure_pinned(&A->h_C, &A->h_C_elems, nc);
+    if (rc)
+        return rc;
+    while (slabs > 1 && (k % slabs != 0 || (k / slabs) % 2 != 0))
+        --slabs;
+    slabs = std::max(1, std::min(slabs, 8));
+    const int ks = k / slabs;
+    std::vector<Pending> pending;
+    size_t ev = 0; // events of the handle used by this call
+    for (int sidx = 0; sidx < slabs; ++sidx)
+    {
+        const int k0 = sidx * ks;
+        cudaEvent_t up, done;
+        rc = upload_rows(B, b_direct, A->h_B, A->d_B, b0, b1, k, k0, ks, A->stream_up);
+        if (!rc)
+            rc = event_at(A, ev++, &up);
+        if (!rc)
+            rc = event_at(A, ev++, &done);
+        if (rc)
+            return rc;
+        SPMM_CUDA(cudaEventRecord(up, A->stream_up));
+        SPMM_CUDA(cudaStreamWaitEvent(A->stream, up, 0));
+        rc = launch(A->d_B, A->d_C, k0, ks, A->stream);
+        if (rc)
+            return rc;
+        SPMM_CUDA(cudaEventRecord(done, A->stream));
+        SPMM_CUDA(cudaStreamWaitEvent(A->stream_down, done, 0));
+        rc = download_rows(A, C, c_direct, A->h_C, A->d_C, c_rows, k, k0, ks, A->stream_down, &pending, &ev);
+        if (rc)
+            return rc;
+    }
+    if (!c_direct)
+        rc = unpack_pending(C, A->h_C, k, pending);
+    cudaError_t e = cudaStreamSynchronize(A->stream_down);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(A->stream);
+    SPMM_CUDA(e);
+    return rc;
+}
+
+int auto_slabs(size_t bytes, int k)
+{
+    int slabs = tuning().host_slabs;
+    if (slabs <= 0)
+        slabs = (bytes >= (16u << 20) && k >= 32) ? 2 : 1; // measured: 2.35 -> 1.90 ms at cfg2 k=64; 4 slabs of 128-byte rows copy slower
+    return slabs;
+}
+
+// per-device scratch buffers (the root rank's C of a multi-rank strategy)
+std::mutex g_scratch_mu;
+std::map<std::pair<int, int>, std::pair<void *, size_t>> g_scratch;
+
+} // namespace
+} // namespace spmm
+
+using namespace spmm;
+
+extern "C"
+{
+
+int spmm_multiply_host(spmm_csr_t A, const double *B, int k, double *C, int kernel)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(k >= 0, "k is negative");
+    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)A->n_rows * (size_t)k;
+    if (nc == 0)
+        return SPMM_OK;
+    SPMM_REQUIRE(C != nullptr && (B != nullptr || nb == 0), "B/C is NULL");
+    HostRows b;
+    b.flat = B;
+    b.ld = k;
+    HostRowsOut c;
+    c.flat = C;
+    c.ld = k;
+    return host_multiply(A, b, 0, A->n_cols, k, c, A->n_rows, auto_slabs((nb + nc) * sizeof(double), k),
+                         [&](const double *dB, double *dC, int k0, int kc, cudaStream_t s) {
+                             return spmm_multiply_strided_device(A, dB, k, dC, k, k0, kc, kernel, s);
+                         });
+}
+
+int spmm_multiply_host_rows(spmm_csr_t A, const double *const *B_rows, int k, double *const *C_rows, int kernel)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(k >= 0, "k is negative");
+    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)A->n_rows * (size_t)k;
+    if (nc == 0)
+        return SPMM_OK;
+    SPMM_REQUIRE(C_rows != nullptr && (B_rows != nullptr || nb == 0), "B_rows/C_rows is NULL");
+    HostRows b;
+    b.rows = B_rows;
+    HostRowsOut c;
+    c.rows = C_rows;
+    return host_multiply(A, b, 0, A->n_cols, k, c, A->n_rows, auto_slabs((nb + nc) * sizeof(double), k),
+                         [&](const double *dB, double *dC, int k0, int kc, cudaStream_t s) {
+                             return spmm_multiply_strided_device(A, dB, k, dC, k, k0, kc, kernel, s);
+                         });
+}
+
+int spmm_multiply_rows_host(spmm_csr_t A, int row_begin, int row_end, const double *B, int k, double *C_local,
+                            int kernel)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(k >= 0, "k is negative");
+    SPMM_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= A->n_rows, "row range outside the matrix");
+    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)(row_end - row_begin) * (size_t)k;
+    if (nc == 0)
+        return SPMM_OK;
+    SPMM_REQUIRE(C_local != nullptr && (B != nullptr || nb == 0), "B/C is NULL");
+    HostRows b;
+    b.flat = B;
+    b.ld = k;
+    HostRowsOut c;
+    c.flat = C_local;
+    c.ld = k;
+    return host_multiply(A, b, 0, A->n_cols, k, c, row_end - row_begin, 1,
+                         [&](const double *dB, double *dC, int, int, cudaStream_t s) {
+                             return spmm_multiply_rows_device(A, row_begin, row_end, dB, k, dC, kernel, s);
+                         });
+}
+
+int spmm_multiply_nnz_range_host(spmm_csr_t A, long long nnz_begin, long long nnz_end, int first_row, int last_row,
+                                 const double *B, int k, double *C_local, int kernel)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(k >= 0, "k is negative");
+    if (last_row < first_row || k == 0 || nnz_begin == nnz_end)
+        return SPMM_OK;
+    SPMM_REQUIRE(C_local != nullptr && B != nullptr, "B/C is NULL");
+    HostRows b;
+    b.flat = B;
+    b.ld = k;
+    HostRowsOut c;
+    c.flat = C_local;
+    c.ld = k;
+    return host_multiply(A, b, 0, A->n_cols, k, c, last_row - first_row + 1, 1,
+                         [&](const double *dB, double *dC, int, int, cudaStream_t s) {
+                             return spmm_multiply_nnz_range_device(A, nnz_begin, nnz_end, first_row, last_row, dB, k, dC,
+                                                                   kernel, s);
+                         });
+}
+
+// ---- pieces for strategies whose ranks share a process (one GPU per rank-thread) ----
+
+int spmm_stage_b_rows(spmm_csr_t A, const double *const *B_rows, int row_begin, int row_end, int k, const double **d_B,
+                      void **stream)
+{
+    SPMM_REQUIRE(A != nullptr && d_B != nullptr, "handle / output is NULL");
+    SPMM_REQUIRE(k >= 0 && 0 <= row_begin && row_begin <= row_end && row_end <= A->n_cols, "row range outside B");
+    SPMM_CUDA(cudaSetDevice(A->device));
+    std::lock_guard<std::mutex> guard(A->host_mu);
+    const size_t nb = (size_t)A->n_cols * (size_t)k;
+    int rc = ensure_streams(A);
+    if (!rc)
+        rc = ensure_device(&A->d_B, &A->d_B_elems, nb);
+    if (!rc && row_end > row_begin)
+        rc = ensure_pinned(&A->h_B, &A->h_B_elems, nb);
+    if (rc)
+        return rc;
+    SPMM_REQUIRE(B_rows != nullptr || row_end == row_begin, "B_rows is NULL");
+    HostRows b;
+    b.rows = B_rows;
+    rc = upload_rows(b, false, A->h_B, A->d_B, row_begin, row_end, k, 0, k, A->stream);
+    if (rc)
+        return rc;
+    *d_B = A->d_B;
+    if (stream)
+        *stream = (void *)A->stream;
+    return SPMM_OK;
+}
+
+int spmm_fetch_c_rows(spmm_csr_t A, const double *d_C, int n_rows, int k, double *const *C_rows)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(n_rows >= 0 && k >= 0, "negative size");
+    if (n_rows == 0 || k == 0)
+        return SPMM_OK;
+    SPMM_REQUIRE(d_C != nullptr && C_rows != nullptr, "d_C / C_rows is NULL");
+    SPMM_CUDA(cudaSetDevice(A->device));
+    std::lock_guard<std::mutex> guard(A->host_mu);
+    int rc = ensure_streams(A);
+    if (!rc)
+        rc = ensure_pinned(&A->h_C, &A->h_C_elems, (size_t)n_rows * (size_t)k);
+    if (rc)
+        return rc;
+    HostRowsOut c;
+    c.rows = C_rows;
+    std::vector<Pending> pending;
+    size_t ev = 0;
+    rc = download_rows(A, c, false, A->h_C, d_C, n_rows, k, 0, k, A->stream_down, &pending, &ev);
+    if (!rc)
+        rc = unpack_pending(c, A->h_C, k, pending);
+    SPMM_CUDA(cudaStreamSynchronize(A->stream_down));
+    return rc;
+}
+
+int spmm_upload_dense(spmm_csr_t A, const double *src, long long n_rows, int k, double *d_dst, void *stream)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(n_rows >= 0 && k >= 0 && n_rows <= 2147483647LL, "bad size");
+    if (n_rows == 0 || k == 0)
+        return SPMM_OK;
+    SPMM_REQUIRE(src != nullptr && d_dst != nullptr, "src / d_dst is NULL");
+    SPMM_CUDA(cudaSetDevice(A->device));
+    std::lock_guard<std::mutex> guard(A->host_mu);
+    HostRows b;
+    b.flat = src;
+    b.ld = k;
+    const bool direct = is_pinned(src);
+    if (!direct)
+    {
+        const int rc = ensure_pinned(&A->h_B, &A->h_B_elems, (size_t)n_rows * (size_t)k);
+        if (rc)
+            return rc;
+    }
+    const int rc = upload_rows(b, direct, A->h_B, d_dst, 0, (int)n_rows, k, 0, k, (cudaStream_t)stream);
+    if (rc)
+        return rc;
+    SPMM_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); // the staging mirror is free again on return
+    return SPMM_OK;
+}
+
+int spmm_download_dense(spmm_csr_t A, const double *d_src, long long n_rows, int k, double *dst, void *stream)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(n_rows >= 0 && k >= 0 && n_rows <= 2147483647LL, "bad size");
+    if (n_rows == 0 || k == 0)
+        return SPMM_OK;
+    SPMM_REQUIRE(d_src != nullptr && dst != nullptr, "d_src / dst is NULL");
+    SPMM_CUDA(cudaSetDevice(A->device));
+    std::lock_guard<std::mutex> guard(A->host_mu);
+    HostRowsOut c;
+    c.flat = dst;
+    c.ld = k;
+    const bool direct = is_pinned(dst);
+    if (!direct)
+    {
+        const int rc = ensure_pinned(&A->h_C, &A->h_C_elems, (size_t)n_rows * (size_t)k);
+        if (rc)
+            return rc;
+    }
+    std::vector<Pending> pending;
+    size_t ev = 0;
+    int rc = download_rows(A, c, direct, A->h_C, d_src, (int)n_rows, k, 0, k, (cudaStream_t)stream, &pending, &ev);
+    if (!rc && !direct)
+        rc = unpack_pending(c, A->h_C, k, pending);
+    SPMM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return rc;
+}
+
+int spmm_csr_stream_sync(spmm_csr_t A)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_CUDA(cudaSetDevice(A->device));
+    if (A->stream)
+        SPMM_CUDA(cudaStreamSynchronize(A->stream));
+    return SPMM_OK;
+}
+
+int spmm_device_scratch(int device, int slot, long long bytes, void **out)
+{
+    SPMM_REQUIRE(out != nullptr && bytes >= 0 && slot >= 0, "bad scratch request");
+    SPMM_CUDA(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    auto &e = g_scratch[{device, slot}];
+    if (e.second < (size_t)bytes)
+    {
+        cudaFree(e.first);
+        e = {nullptr, 0};
+        SPMM_CUDA(cudaMalloc(&e.first, std::max<size_t>((size_t)bytes, 16)));
+        e.second = (size_t)bytes;
+    }
+    *out = e.first;
+    return SPMM_OK;
+}
+
+int spmm_device_scratch_release(void)
+{
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    for (auto &kv : g_scratch)
+    {
+        cudaSetDevice(kv.first.first);
+        cudaFree(kv.second.first);
+    }
+    g_scratch.clear();
+    return SPMM_OK;
+}
+
+int spmm_peer_enable(int device, int peer)
+{
+    if (device == peer)
+        return SPMM_OK;
+    SPMM_CUDA(cudaSetDevice(device));
+    int can = 0;
+    SPMM_CUDA(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can)
+    {
+        set_error("device " + std::to_string(device) + " cannot access device " + std::to_string(peer) + " (no NVLink/PCIe peer path)");
+        return SPMM_ERR_UNSUPPORTED;
+    }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled)
+    {
+        cudaGetLastError();
+        return SPMM_OK;
+    }
+    SPMM_CUDA(e);
+    return SPMM_OK;
+}
+
+int spmm_host_threads(void) { return pool().threads(); }
+
+void spmm_host_parallel_for(int n, void (*fn)(int, void *), void *ctx)
+{
+    if (fn)
+        pool().parallel_for(n, [&](int i) { fn(i, ctx); });
+}
+
+} // extern "C"

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <functional>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -13,6 +14,7 @@ namespace spmm
 {
 
 void set_error(const std::string &msg);
+void note_kernel(const char *name); // kernel family of the calling thread's last launch (spmm_last_kernel_name)
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
 #define SPMM_CUDA(call)                                                        \
@@ -68,8 +70,6 @@ struct Tuning
     int tiled_ksplit = 0;   // build: CTAs that share one chunk, each taking a group of k-tiles (0/1 none)
     int tiled_npw = 0;      // launch: producer warps (4, 8)
     int host_slabs = 0;     // host-buffer multiply: k-slabs in the PCIe pipeline (0 auto, 1 none)
-    int host_pipe = 0;      // host-buffer multiply: row-block pipeline for banded matrices (0 off, 1 always, -1 when its estimate beats the k-slabs);
-                            // off by default: measured 1.94 ms against 1.82 ms for two k-slabs on cfg2 k=64 — both directions together cap at ~65 GB/s on this host
     int tiled_pdl = 1;      // launch: programmatic dependent launch of the tiled kernel (0 off)
     int tiled_group = 0;    // build: tiles one far-band apart walked in turn, this many bands per group (0 auto = 2, 1 off)
     int tiled_stride = 0;   // build: far-band distance in rows (0 = detect from the matrix)
@@ -100,17 +100,15 @@ struct spmm_csr_s
     double *d_vals = nullptr;
     bool owns = false;
     spmm::Schedule sched;
-    // staging for the host-buffer entry point
-    double *h_stage = nullptr; // pinned
-    size_t h_stage_elems = 0;
+    // staging of the host-buffer entry points (spmm_host.cu): pinned mirrors of B and C, their device images, streams
+    std::mutex host_mu; // one host-buffer call per handle at a time
+    double *h_B = nullptr, *h_C = nullptr;
+    size_t h_B_elems = 0, h_C_elems = 0;
     double *d_B = nullptr, *d_C = nullptr;
     size_t d_B_elems = 0, d_C_elems = 0;
-    cudaStream_t stream = nullptr; // owned, for host-buffer calls
-    cudaStream_t stream_up = nullptr, stream_down = nullptr; // k-slab pipeline of the host-buffer multiply
-    cudaEvent_t ev_up[32] = {}, ev_done[32] = {};
-    // row-block pipeline of the host-buffer multiply: block j of C needs the B rows [0, hp_need[j])
-    int hp_blocks = 0;
-    std::vector<int> hp_cut, hp_need;
+    cudaStream_t stream = nullptr; // compute
+    cudaStream_t stream_up = nullptr, stream_down = nullptr; // the two PCIe directions
+    std::vector<cudaEvent_t> events;
     // B-staged row tiles (spmm_tiled.cu), optional
     int tl_T = 0, tl_BR = 0, tl_tiles = 0, tl_NS = 0, tl_POOL = 0, tl_max_recs = 0, tl_max_blob = 0, tl_chunk = 0, tl_kt = 0, tl_depth = 0, tl_drains = 0, tl_ksplit = 0;
     long long tl_box_rows_loaded = 0, tl_single_rows = 0; // B rows staged per pass over the matrix
@@ -143,6 +141,10 @@ bool tiled_shape_ok(const spmm_csr_s *A, const double *d_B, long long ldb, const
 int launch_tiled(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int kc,
                  cudaStream_t stream, const struct ExtraDst *extra = nullptr);
 void free_tiles(spmm_csr_s *A);
+int build_tiles(spmm_csr_s *A, int rows_per_tile, int box_rows, int kt_want, int ksplit_want);
+// what AUTO cuts the tile layout for: 64-byte window rows for k <= 8; chunks shared by 2 / 4 CTAs (one k-tile group each) from k = 32 / 64
+inline int tiles_kt_for(int k) { return k <= 8 ? 8 : 16; }
+inline int tiles_ksplit_for(int k) { return k >= 64 ? 4 : (k >= 32 ? 2 : 1); }
 bool stream_shape_ok(const spmm_csr_s *A, const double *d_B, long long ldb, const double *d_C, long long ldc, int kc);
 int launch_stream(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int kc,
                   cudaStream_t stream);

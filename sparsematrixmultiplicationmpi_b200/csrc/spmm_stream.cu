@@ -135,6 +135,7 @@ bool stream_shape_ok(const spmm_csr_s *A, const double *d_B, long long ldb, cons
 int launch_stream(const spmm_csr_s *A, const double *d_B, long long ldb, double *d_C, long long ldc, int kc,
                   cudaStream_t stream)
 {
+    note_kernel("spmm_stream_kernel");
     const int cap = stream_cap(A, kc);
     const int tile_nnz = cap - A->sched.max_len; // a tile starts at the first row at or after a multiple of tile_nnz
     const int n_tiles = (int)((A->nnz + tile_nnz - 1) / tile_nnz);

@@ -1391,6 +1391,7 @@ int launch_tiled(const spmm_csr_s *A, const double *d_B, long long ldb, double *
 {
     const ExtraDst x = extra ? *extra : ExtraDst();
     const Tuning &t = tuning();
+    note_kernel("spmm_tiled_kernel");
     const int kt = t.tiled_kt > 0 ? t.tiled_kt : A->tl_kt;
     const int ncw = t.tiled_ncw > 0 ? t.tiled_ncw : 16;
     const int u = t.tiled_unroll > 0 ? t.tiled_unroll : 4;
@@ -1416,12 +1417,11 @@ int launch_tiled(const spmm_csr_s *A, const double *d_B, long long ldb, double *
 
 } // namespace spmm
 
-using namespace spmm;
-
-extern "C"
+namespace spmm
 {
-
-int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
+// kt_want / ksplit_want: k-tile width and CTAs per chunk the layout is cut for (0 = the tuning knob, else its default).
+// Explicit parameters, not the process-wide tuning: concurrent multiplies of rank-threads build their layouts side by side.
+int build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows, int kt_want, int ksplit_want)
 {
     SPMM_REQUIRE(A != nullptr, "handle is NULL");
     SPMM_REQUIRE(rows_per_tile == 0 || rows_per_tile == -1 ||
@@ -1437,13 +1437,13 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
         return SPMM_OK;
     const Tuning &tn = tuning();
     const int BR = box_rows ? box_rows : 16;
-    const int kt = tn.tiled_kt > 0 ? tn.tiled_kt : 16; // k-tile the window is sized for
+    const int kt = kt_want > 0 ? kt_want : (tn.tiled_kt > 0 ? tn.tiled_kt : 16); // k-tile the window is sized for
     const int sms = device_props(A->device).sm_count;
     // measured on the cop20k_A shape (profiles/r1_tiled.md): tall tiles and a wide window beat a deeper pipeline
-    const int kt_for_depth = tn.tiled_kt > 0 ? tn.tiled_kt : 16;
+    const int kt_for_depth = kt;
     // (64-byte window rows leave room for a third work item in flight: measured 20.6 against 22.7 us at k=8, T=96)
     const int depth = (tn.tiled_depth >= 2 && tn.tiled_depth <= TB_DMAX) ? tn.tiled_depth : (kt_for_depth == 8 ? 3 : 2);
-    const int ksplit = std::max(1, std::min(8, tn.tiled_ksplit)); // CTAs per chunk (set from k by AUTO / the Python wrapper)
+    const int ksplit = std::max(1, std::min(8, ksplit_want > 0 ? ksplit_want : tn.tiled_ksplit)); // CTAs per chunk
 
     BuildParams p = {};
     p.n_rows = A->n_rows;
@@ -1571,6 +1571,23 @@ int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows)
     A->tl_box_rows_loaded = (long long)res.totals[TOT_LOADS] * BR;
     A->tl_single_rows = (long long)res.totals[TOT_SINGLES];
     return SPMM_OK;
+}
+
+} // namespace spmm
+
+using namespace spmm;
+
+extern "C"
+{
+
+int spmm_csr_build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows) { return build_tiles(A, rows_per_tile, box_rows, 0, 0); }
+
+int spmm_csr_build_tiles_for_k(spmm_csr_t A, int rows_per_tile, int box_rows, int k)
+{
+    SPMM_REQUIRE(k >= 0, "k is negative");
+    if (k == 0)
+        return build_tiles(A, rows_per_tile, box_rows, 0, 0);
+    return build_tiles(A, rows_per_tile, box_rows, tiles_kt_for(k), tiles_ksplit_for(k));
 }
 
 int spmm_csr_tile_info(spmm_csr_t A, int *rows_per_tile, int *box_rows, int *window_slots, int *max_records,

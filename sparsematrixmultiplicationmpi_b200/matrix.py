@@ -141,17 +141,7 @@ class DeviceCSR:
         """Row tiles with TMA-staged B rows (spmm_tiled.cu); -1 = tallest tile that fits shared memory.
         k (optional): the number of B columns the layout will mostly be used with — from 32 columns up the chunks are
         made longer and shared by 2 or 4 CTAs, each taking a group of k-tiles (what AUTO does on its own)."""
-        if k > 0:
-            _cabi.tune("tiled.ksplit", 4 if k >= 64 else (2 if k >= 32 else 1))
-            if k <= 8:
-                _cabi.tune("tiled.kt", 8)  # 64-byte window rows
-        try:
-            _cabi.check(_cabi.lib().spmm_csr_build_tiles(self.handle, rows_per_tile, box_rows))
-        finally:
-            if k > 0:
-                _cabi.tune("tiled.ksplit", 0)
-                if k <= 8:
-                    _cabi.tune("tiled.kt", 0)
+        _cabi.check(_cabi.lib().spmm_csr_build_tiles_for_k(self.handle, rows_per_tile, box_rows, k))
         return self.tile_info()
 
     def tile_info(self) -> dict:
@@ -198,6 +188,20 @@ class DeviceCSR:
         _cabi.check(_cabi.lib().spmm_multiply_host(self.handle, B.ctypes.data, k, Cm.ctypes.data,
                                                    _cabi.KERNELS[kernel]))
         return Cm
+
+    def upload_dense(self, src: np.ndarray, d_dst: int, stream: int = 0) -> None:
+        """(n, k) float64 host block -> device buffer d_dst through the handle's pinned staging and the library's host
+        threads (spmm_upload_dense); returns when the copy is done."""
+        src = as_fat_vector(src)
+        _cabi.check(_cabi.lib().spmm_upload_dense(self.handle, src.ctypes.data, src.shape[0], src.shape[1],
+                                                  C.c_void_p(d_dst), C.c_void_p(stream)))
+
+    def download_dense(self, d_src: int, n_rows: int, k: int, stream: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+        """Device buffer -> (n_rows, k) float64 host block (spmm_download_dense)."""
+        dst = out if out is not None else np.empty((n_rows, k), dtype=np.float64)
+        _cabi.check(_cabi.lib().spmm_download_dense(self.handle, C.c_void_p(d_src), n_rows, k, dst.ctypes.data,
+                                                    C.c_void_p(stream)))
+        return dst
 
     # -- lifetime --
     def close(self) -> None:

@@ -18,6 +18,8 @@ checks nothing about its arguments; here sizes are validated and errors surface 
 """
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -36,13 +38,28 @@ def _engine() -> CudaCompute:
     return _compute
 
 
+def _close(plan) -> None:
+    A = getattr(plan, "A", plan)
+    if isinstance(A, DeviceCSR):
+        A.close()
+
+
 def clear_cache() -> None:
-    """Drop every cached device shard (call after mutating a SparseMatrix in place)."""
-    for plan in _cache.values():
-        A = getattr(plan, "A", plan)
-        if isinstance(A, DeviceCSR):
-            A.close()
+    """Drop every cached device shard."""
+    for _, _, plan in _cache.values():
+        _close(plan)
     _cache.clear()
+
+
+def _fingerprint(m: SparseMatrix) -> int:
+    """Cheap content check of a cache hit (the reference functions are pure: a matrix edited in place, or a new one
+    at a recycled address, must not meet the old shard): every array whole up to 64 Ki elements, else 64 Ki evenly
+    spaced probes."""
+    h = 0
+    for a in (m.rowPtr, m.colIndices, m.values):
+        step = 1 if a.size <= (1 << 16) else a.size // (1 << 16)
+        h = hash((h, a[::step].tobytes(), a[-1:].tobytes()))
+    return h
 
 
 def _key(m: SparseMatrix, tag: str, k: int | None):
@@ -51,13 +68,27 @@ def _key(m: SparseMatrix, tag: str, k: int | None):
             tag, k, rank, P)
 
 
+def _evict(key) -> None:
+    entry = _cache.pop(key, None)
+    if entry is not None:
+        _close(entry[2])
+
+
 def _cached(m: SparseMatrix, tag: str, k: int | None, make):
+    """Device shard of (matrix, strategy, rank layout). An entry lives as long as its SparseMatrix (weakref.finalize
+    evicts it) and is rebuilt when the matrix's contents no longer match the fingerprint taken at upload."""
     key = _key(m, tag, k)
-    if key not in _cache:
-        if len(_cache) >= _CACHE_MAX:
-            clear_cache()
-        _cache[key] = make()
-    return _cache[key]
+    print_now = _fingerprint(m)
+    hit = _cache.get(key)
+    if hit is not None and hit[0]() is m and hit[1] == print_now:
+        return hit[2]
+    _evict(key)
+    if len(_cache) >= _CACHE_MAX:
+        clear_cache()
+    plan = make()
+    _cache[key] = (weakref.ref(m), print_now, plan)
+    weakref.finalize(m, _evict, key)
+    return plan
 
 
 def _check(m: SparseMatrix, v, k: int) -> np.ndarray:
@@ -73,14 +104,21 @@ def _check(m: SparseMatrix, v, k: int) -> np.ndarray:
     return B
 
 
-def _to_device(B: np.ndarray, eng: CudaCompute) -> torch.Tensor:
-    return torch.from_numpy(B).to(eng.device, non_blocking=False)
+def _to_device(B: np.ndarray, eng: CudaCompute, plan) -> torch.Tensor:
+    """Host fat vector -> device tensor through the shard's pinned staging and the library's host threads."""
+    out = torch.empty(B.shape, dtype=torch.float64, device=eng.device)
+    if B.size:
+        plan.A.upload_dense(B, out.data_ptr(), torch.cuda.current_stream(eng.device).cuda_stream)
+    return out
 
 
-def _to_host(Cd: torch.Tensor | None, k: int) -> np.ndarray:
+def _to_host(Cd: torch.Tensor | None, k: int, eng: CudaCompute, plan) -> np.ndarray:
     if Cd is None:
         return np.empty((0, k), dtype=np.float64)  # FatVector{} on non-root ranks
-    return Cd.cpu().numpy()
+    if Cd.numel() == 0:
+        return np.empty(tuple(Cd.shape), dtype=np.float64)
+    Cd = Cd.contiguous()
+    return plan.A.download_dense(Cd.data_ptr(), Cd.shape[0], Cd.shape[1], torch.cuda.current_stream(eng.device).cuda_stream)
 
 
 def sparseMatrixFatVectorMultiply(sparseMatrix: SparseMatrix, fatVector, vecCols: int, out=None) -> np.ndarray:
@@ -96,7 +134,7 @@ def sparseMatrixFatVectorMultiplyRowWise(sparseMatrix: SparseMatrix, fatVector, 
     B = _check(sparseMatrix, fatVector, vecCols)
     eng = _engine()
     plan = _cached(sparseMatrix, "row", vecCols, lambda: RowWise.from_host(eng, sparseMatrix, vecCols))
-    return _to_host(plan.run(_to_device(B, eng)), vecCols)
+    return _to_host(plan.run(_to_device(B, eng, plan)), vecCols, eng, plan)
 
 
 def sparseMatrixFatVectorMultiplyColumnWise(sparseMatrix: SparseMatrix, fatVector, vecCols: int,
@@ -107,16 +145,16 @@ def sparseMatrixFatVectorMultiplyColumnWise(sparseMatrix: SparseMatrix, fatVecto
     eng = _engine()
     if mode == "slabs":
         plan = _cached(sparseMatrix, "colslab", vecCols, lambda: ColumnSlabs.from_host(eng, sparseMatrix, vecCols))
-        return _to_host(plan.run(_to_device(B, eng)), vecCols)
+        return _to_host(plan.run(_to_device(B, eng, plan)), vecCols, eng, plan)
     if mode != "blocks":
         raise RuntimeError("mode must be 'blocks' or 'slabs'")
     plan = _cached(sparseMatrix, "colblk", vecCols, lambda: ColumnBlocks.from_host(eng, sparseMatrix, vecCols))
-    B_local = _to_device(np.ascontiguousarray(B[plan.col_start:plan.col_end]), eng)
-    return _to_host(plan.run(B_local), vecCols)
+    B_local = _to_device(np.ascontiguousarray(B[plan.col_start:plan.col_end]), eng, plan)
+    return _to_host(plan.run(B_local), vecCols, eng, plan)
 
 
 def sparseMatrixFatVectorMultiplyNonZeroElement(sparseMatrix: SparseMatrix, fatVector, vecCols: int) -> np.ndarray:
     B = _check(sparseMatrix, fatVector, vecCols)
     eng = _engine()
     plan = _cached(sparseMatrix, "nnz", vecCols, lambda: NonZeroRanges.from_host(eng, sparseMatrix, vecCols))
-    return _to_host(plan.run(_to_device(B, eng)), vecCols)
+    return _to_host(plan.run(_to_device(B, eng, plan)), vecCols, eng, plan)

@@ -180,6 +180,12 @@ class RowWise:
         buf, hdl = self._symmetric_C(B.device)
         off = self.start * self.k * 8  # this rank's rows start here in every copy of C
         ptrs = [int(hdl.buffer_ptrs[p]) + off for p in peers]
+        lo, hi = buf.data_ptr(), buf.data_ptr() + buf.numel() * 8
+        if B.data_ptr() < hi and B.data_ptr() + B.numel() * 8 > lo:
+            # the previous result fed back as B (an iterative caller): peers would overwrite rows this rank still reads
+            B = B.clone()
+        # a fast rank must not store into a peer's copy while that peer still reads the previous result
+        hdl.barrier(channel=0)
         if self.end > self.start and self.k:
             self.A.multiply_scatter(B.data_ptr(), self.k, ptrs, self.compute.kernel,
                                     torch.cuda.current_stream(B.device).cuda_stream)
