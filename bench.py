@@ -6,17 +6,25 @@
 One "step" = one pass C = A*B of the cop20k_A-shaped k=64 SpMM (BASELINE.json configs[1], the
 configuration the north_star target is quoted on) over one resident operand set. With N > 1 (one
 process per GPU under torchrun) every rank owns one cop20k_A-shaped diagonal block of a
-(N*121,192)-row matrix — the row-wise partition (RowWise.cpp:26-29) with B replicated and C left
-row-sharded, no collective inside the timed region (weak scaling); the NCCL broadcast of B and
-the all-gather of C are timed separately and reported under "collectives".
+(N*121,192)-row block-diagonal matrix — the row-wise partition (RowWise.cpp:26-29) of a matrix whose
+blocks read only their own rows of B, so no byte has to cross a link (weak scaling, no collective
+invented). What the north_star's scaling cases cost WITH their exchange steps is measured in the same
+run and printed under "north_star_scaling": the large banded row-partitioned case (cfg4: B sharded by
+rows, halo rows exchanged peer to peer, kernel, optional gather of C) and the column-block case (cfg5:
+kernel + reduce-scatter of the partial C), each with the 1-GPU time of the same problem beside it, and
+"parity_ok": the three strategies on this process group against the oracle on a small matrix.
 
 Printed by rank 0: ONE JSON line with metric / value (GFLOP/s = 2*nnz*k/t, whole job) plus
-roofline (algorithmic bytes / kernel time vs the measured HBM copy peak), e2e (the same multiply
-through the reference-shaped host entry point, host buffers, copies inside the timed region) and
-cpu_baseline (the reference's own CPU code on the host cores).
+roofline (algorithmic bytes / kernel time vs the measured HBM copy peak; the kernel name is what the
+library reports it launched), e2e (the same multiply through the reference's own C++ entry point:
+std::vector<std::vector<double>> in and out, pack / H2D / kernel / D2H / unpack inside the timed region;
+"e2e_first_call" adds the upload of A and the layout build, the reference's one-call-per-run pattern
+main.cpp:78; "e2e_pinned" is the flat pinned-buffer C-ABI call) and cpu_baseline (the reference's own
+CPU code on the host cores). At N = 1 "configs_1gpu" adds the kernel times of BASELINE.json configs 3-5.
 
 --impl reference times the reference's own CPU implementation (oracle/_ref, compiled from the
-reference sources; else the oracle port) on the same workload, all host threads, rank 0 only.
+reference sources; else the oracle port) on the same TOTAL workload (the N-block matrix at --gpus N),
+all host threads, rank 0 only.
 """
 from __future__ import annotations
 
@@ -51,12 +59,14 @@ def measured_peak_gbs() -> tuple[float, str]:
 
 
 def recorded_traffic(k: int):
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, or None."""
+    """(dram bytes per launch of the dominant kernel, where it was recorded): read from the committed ncu --set full
+    capture named in profiles/traffic.json — a RECORDED figure, not measured in this run (ncu cannot run inside it)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(f"cop20k_k{k}")
+            d = json.load(f)
+            return d.get(f"cop20k_k{k}"), "recorded: " + d.get("source", "profiles/traffic.json")
     except Exception:
-        return None
+        return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -112,6 +122,23 @@ def build_workload(k: int, seed: int = 20):
     return gen.cop20k_A_shaped(n=N_ROWS, nnz=NNZ, seed=seed)
 
 
+def block_diagonal_host(n_blocks: int, k: int):
+    """Host CSR of the N-block block-diagonal matrix the N ranks of the GPU arm multiply (block r = seed 20 + r)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    from sparsematrixmultiplicationmpi_b200.matrix import SparseMatrix
+    orc = pyoracle.Oracle()
+    rps, cis, vas = [], [], []
+    for b in range(n_blocks):
+        n, nc, r, c, v, sym = build_workload(k, seed=20 + b)
+        rp, ci, va = orc.csr_from_coo(n, r, c, v, sym)  # the reference loader's CSR assembly
+        rps.append(rp[1:].astype(np.int64) + b * NNZ if b else rp.astype(np.int64))
+        cis.append(ci + b * N_ROWS)
+        vas.append(va)
+    return SparseMatrix(np.concatenate(vas), np.concatenate(cis).astype(np.int32), np.concatenate(rps).astype(np.int32),
+                        n_blocks * N_ROWS, n_blocks * N_ROWS)
+
+
 def cpu_reference_run(host, B, k, steps, warmup, max_seconds=60.0):
     """The reference's own CPU code on the host cores: row-wise strategy at P = all hardware threads
     (its "mpirun" path on compat MPI) and the sequential function; returns the faster one."""
@@ -145,13 +172,39 @@ def cpu_reference_run(host, B, k, steps, warmup, max_seconds=60.0):
         best[(strategy, P)] = statistics.mean(times)
     (strategy, P), t = min(best.items(), key=lambda kv: kv[1])
     flops = 2.0 * host.nnz * k
+    blocks = max(1, host.numRows // N_ROWS)
     return {"value": flops / t / 1e9, "unit": "GFLOP/s", "cores": P, "kind": kind,
-            "sample": f"full cop20k_A-shaped k={k} multiply, reference {strategy} strategy at P={P} "
+            "sample": f"full cop20k_A-shaped k={k} multiply ({blocks} diagonal block{'s' if blocks > 1 else ''}), reference {strategy} strategy at P={P} "
                       f"(-O3 -march=x86-64-v3, compat MPI rank-threads), mean of {len(times)} calls",
             "seconds_per_step": t,
             "sequential_gflops": flops / best[("seq", 1)] / 1e9 if ("seq", 1) in best else None,
             "rowwise_all_cores_gflops": flops / best[("row", cores)] / 1e9 if ("row", cores) in best else None,
             "host_cores": os.cpu_count()}
+
+
+def entry_lib():
+    """libspmm_entry.so: the reference's four C++ entry points + the spmm_entry_run measurement hook."""
+    import ctypes as C
+    lib = C.CDLL(os.path.join(ROOT, "sparsematrixmultiplicationmpi_b200", "libspmm_entry.so"))
+    lib.spmm_entry_run.restype = C.c_int
+    lib.spmm_entry_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                   C.c_char_p, C.c_int]
+    return lib
+
+
+def entry_run(lib, strategy, P, host, B, k, steps, want_result=False):
+    """C++ SparseMatrix + FatVector in, FatVector out, `steps` calls after the first: (first_call_s, mean_s, C or None)."""
+    import ctypes as C
+    out = np.empty((host.numRows, k)) if want_result else None
+    first, mean = C.c_double(), C.c_double()
+    err = C.create_string_buffer(512)
+    rc = lib.spmm_entry_run(strategy, P, host.numRows, host.numCols, host.nnz, host.rowPtr.ctypes.data,
+                            host.colIndices.ctypes.data, host.values.ctypes.data, k, B.ctypes.data,
+                            out.ctypes.data if want_result else None, steps, C.byref(first), C.byref(mean), err, 512)
+    if rc:
+        raise RuntimeError(err.value.decode() or f"spmm_entry_run status {rc}")
+    return first.value, mean.value, out
 
 
 def main():
@@ -172,32 +225,33 @@ def main():
     ap.add_argument("--k", type=int, default=64)
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip configs_1gpu / north_star_scaling (profiling runs)")
     args = ap.parse_args()
     k = args.k
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # host threads of the pack / unpack pool: the ranks of one box share its cores
+    os.environ.setdefault("SPMM_HOST_THREADS", str(max(2, min(16, (os.cpu_count() or 8) // max(1, world)))))
     metric = "SpMM GFLOP/s and HBM GB/s (% roofline) at 1/2/4/8 B200 vs ref CPU MPI"
+    n_blocks = max(1, args.gpus if args.impl == "reference" else world)
     config = {"workload": f"cop20k_A-shaped synthetic FEM matrix {N_ROWS}x{N_ROWS}, {NNZ} nnz, k={k}, FP64 "
-                          f"(BASELINE.json configs[1]); one such diagonal block per GPU, row-wise partition",
-              "n_rows_per_gpu": N_ROWS, "nnz_per_gpu": NNZ, "k": k,
+                          f"(BASELINE.json configs[1]); one such diagonal block per GPU, row-wise partition "
+                          f"({n_blocks} block{'s' if n_blocks > 1 else ''} in this run)",
+              "n_rows_per_gpu": N_ROWS, "nnz_per_gpu": NNZ, "k": k, "blocks": n_blocks,
               "l2": f"{OPERAND_SETS} rotating resident operand sets (> 126 MB L2) so every step reads cold operands"}
 
     if args.impl == "reference":
         if rank != 0:
             return
         import sparsematrixmultiplicationmpi_b200  # noqa: F401  (generators only; no GPU work on this arm)
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import pyoracle
-        n, nc, r, c, v, sym = build_workload(k)
-        rp, ci, va = pyoracle.Oracle().csr_from_coo(n, r, c, v, sym)  # the reference loader's CSR assembly
-        from sparsematrixmultiplicationmpi_b200.matrix import SparseMatrix
-        host = SparseMatrix(va, ci, rp, n, nc)
-        B = np.random.default_rng(1).integers(1, 101, (n, k)).astype(np.float64)
-        steps = min(args.steps, 20)
-        res = cpu_reference_run(host, B, k, steps, min(args.warmup, 2))
+        host = block_diagonal_host(n_blocks, k)  # the same TOTAL work as the GPU arm at this N
+        B = np.random.default_rng(1).integers(1, 101, (host.numCols, k)).astype(np.float64)
+        steps = min(args.steps, 20 if n_blocks == 1 else 5)
+        warm = min(args.warmup, 2 if n_blocks == 1 else 1)
+        res = cpu_reference_run(host, B, k, steps, warm, max_seconds=60.0 if n_blocks == 1 else 120.0)
         line = {"impl": "reference", "metric": metric, "value": res["value"], "unit": "GFLOP/s", "n_gpus": args.gpus,
-                "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": res["seconds_per_step"] * 1e3,
+                "steps": steps, "warmup": warm, "ms_per_step": res["seconds_per_step"] * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "cpu_baseline": res,
                 "e2e": {"value": res["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -208,6 +262,7 @@ def main():
     import torch
     import torch.distributed as dist
     import sparsematrixmultiplicationmpi_b200 as spmm
+    from sparsematrixmultiplicationmpi_b200 import _cabi
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the SpMM path has no CPU fallback")
@@ -217,6 +272,32 @@ def main():
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.current_stream().cuda_stream
 
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def tmax(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, iters, warm=2):
+        """Mean device ms of fn over `iters` calls: CUDA events on the launching stream, barrier on both sides, max over ranks."""
+        for _ in range(warm):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        barrier()
+        return tmax(a.elapsed_time(b) / iters)
+
     # ---- operands resident in HBM: OPERAND_SETS copies of this rank's diagonal block ----
     n, nc, r, c, v, sym = build_workload(k, seed=20 + rank)
     first = spmm.DeviceCSR.from_coo_host(n, nc, r, c, v, sym, device=local_rank)
@@ -225,7 +306,7 @@ def main():
     for s in range(OPERAND_SETS):
         A = first if s == 0 else spmm.DeviceCSR.from_host(host, local_rank)
         if args.kernel in ("auto", "tiled"):
-            A.build_tiles(-1, 0, k)  # what AUTO does by itself on its first k>=16 multiply; done here so it is outside any timing
+            A.build_tiles(-1, 0, k)  # what AUTO does by itself on its first multiply; done here so it is outside any timing
         Bd = torch.randint(1, 101, (n, k), device=dev).double()
         Cd = torch.empty((n, k), dtype=torch.float64, device=dev)
         sets.append((A, Bd, Cd))
@@ -236,14 +317,9 @@ def main():
         A, Bd, Cd = sets[i % OPERAND_SETS]
         A.multiply(Bd.data_ptr(), k, Cd.data_ptr(), args.kernel, stream)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for i in range(max(args.warmup, 3)):
         step(i)
+    kernel_name = (_cabi.lib().spmm_last_kernel_name() or b"").decode()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -256,12 +332,7 @@ def main():
     barrier()
     wall = time.perf_counter() - t_wall
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
+    ms_per_step = tmax(ev0.elapsed_time(ev1)) / args.steps
     flops_per_step = 2.0 * NNZ * k * world
     value = flops_per_step / (ms_per_step * 1e-3) / 1e9
 
@@ -269,91 +340,50 @@ def main():
     peak, peak_kind = measured_peak_gbs()
     abytes = algorithmic_bytes(N_ROWS, NNZ, k)
     achieved = abytes / (ms_per_step * 1e-3) / 1e9
+    traffic, traffic_source = recorded_traffic(k)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic(k), "peak_kind": peak_kind, "algorithmic_bytes_per_launch": abytes,
-                "frac_of_8TBs_nominal": achieved / 8000.0,
-                "kernel": "spmm_tiled_kernel" if tiles["rows_per_tile"] and k >= 8 and k % 2 == 0 and args.kernel in ("auto", "tiled")
-                else ("spmm_merge_kernel" if args.kernel == "merge" else "spmm_rows_kernel"),
-                "tiles": tiles}
+                "traffic": traffic, "traffic_source": traffic_source, "peak_kind": peak_kind,
+                "algorithmic_bytes_per_launch": abytes, "frac_of_8TBs_nominal": achieved / 8000.0,
+                "kernel": kernel_name, "tiles": tiles}
 
-    # ---- e2e: the reference-shaped host entry point, pinned host buffers, copies inside the timed region ----
-    Bh = torch.randint(1, 101, (n, k)).double().pin_memory()
-    Ch = torch.empty((n, k), dtype=torch.float64).pin_memory()
-    Bh_np, Ch_np = Bh.numpy(), Ch.numpy()
-    e2e_steps = max(3, min(args.steps, 30))
+    # ---- e2e through the reference's own boundary: C++ SparseMatrix / FatVector objects, the entry point of
+    # SparseMatrixFatVectorMultiply.h:14-15 (pack, H2D, kernel, D2H, unpack all inside the timed region) ----
+    spmm.clear_cache()
+    Bh = np.random.default_rng(7).integers(1, 101, (n, k)).astype(np.float64)
+    e2e_steps = max(3, min(args.steps, 20))
+    lib = entry_lib()
+    barrier()
+    first_s, mean_s, _ = entry_run(lib, 0, 1, host, Bh, k, e2e_steps)
+    first_s, mean_s = tmax(first_s), tmax(mean_s)
+    e2e = {"value": flops_per_step / mean_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": n * k * 8,
+           "d2h_bytes_per_step": n * k * 8, "ms_per_step": mean_s * 1e3,
+           "api": "C++ sparseMatrixFatVectorMultiply(const SparseMatrix&, const FatVector&, int) of libspmm_entry.so: "
+                  "vector<vector<double>> in and out, A cached in HBM after the first call",
+           "host_threads": int(os.environ["SPMM_HOST_THREADS"])}
+    e2e_first = {"value": flops_per_step / first_s / 1e9, "unit": "GFLOP/s", "ms": first_s * 1e3,
+                 "what": "first call on a new matrix: upload of A (32 MB), tile layout build, pinned staging allocation, "
+                         "then the multiply as above — the reference's one-call-per-run pattern (main.cpp:78)"}
+    # the flat C-ABI call with pinned host buffers (no pack / unpack): what a caller that owns row-major storage gets
+    Bp = torch.randint(1, 101, (n, k)).double().pin_memory()
+    Cp = torch.empty((n, k), dtype=torch.float64).pin_memory()
+    Bp_np, Cp_np = Bp.numpy(), Cp.numpy()
+    A0 = sets[0][0]
     for _ in range(3):
-        spmm.sparseMatrixFatVectorMultiply(host, Bh_np, k, out=Ch_np)
+        A0.multiply_host(Bp_np, k, args.kernel if args.kernel in ("auto", "rows", "merge", "tiled") else "auto", Cp_np)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        spmm.sparseMatrixFatVectorMultiply(host, Bh_np, k, out=Ch_np)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = {"value": flops_per_step / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": n * k * 8,
-           "d2h_bytes_per_step": n * k * 8, "ms_per_step": e2e_s * 1e3,
-           "api": "sparseMatrixFatVectorMultiply(M, B_host, k) with A cached in HBM after the first call"}
+        A0.multiply_host(Bp_np, k, "auto", Cp_np)
+    pinned_s = tmax((time.perf_counter() - t0) / e2e_steps)
+    e2e_pinned = {"value": flops_per_step / pinned_s / 1e9, "unit": "GFLOP/s", "ms_per_step": pinned_s * 1e3,
+                  "api": "spmm_multiply_host(A, B, k, C) with pinned row-major host buffers"}
 
-    # ---- N > 1: the collectives of the row-wise strategy, timed on their own ----
-    collectives = None
-    if world > 1:
-        plan_counts = [N_ROWS] * world
-        Bfull = torch.empty((N_ROWS * world, k), dtype=torch.float64, device=dev)
-        Call = torch.empty((N_ROWS * world, k), dtype=torch.float64, device=dev)
-        out = {}
-        for name, fn in (("broadcast_B", lambda: dist.broadcast(Bfull, src=0)),
-                         ("all_gather_C", lambda: dist.all_gather_into_tensor(Call, sets[0][2]))):
-            for _ in range(3):
-                fn()
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(10):
-                fn()
-            b.record()
-            barrier()
-            t = torch.tensor([a.elapsed_time(b) / 10], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            out[name + "_ms"] = float(t.item())
-        out["bytes"] = N_ROWS * world * k * 8
-
-        # the same all-gather fused into the multiply (C rows stored from registers into every peer's buffer
-        # over NVLink, spmm_multiply_scatter_device) against multiply + NCCL all-gather, both timed as one unit
-        def timed_unit(fn, iters=10):
-            for _ in range(3):
-                fn()
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(iters):
-                fn()
-            b.record()
-            barrier()
-            t = torch.tensor([a.elapsed_time(b) / iters], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-
-        A0, B0, C0 = sets[0]
-        out["multiply+all_gather_nccl_ms"] = timed_unit(
-            lambda: (A0.multiply(B0.data_ptr(), k, C0.data_ptr(), args.kernel, stream),
-                     dist.all_gather_into_tensor(Call, C0)))
+    extras = {}
+    if not args.no_extras:
         try:
-            import torch.distributed._symmetric_memory as symm_mem
-            sym = symm_mem.empty((N_ROWS * world, k), dtype=torch.float64, device=dev)
-            hdl = symm_mem.rendezvous(sym, dist.group.WORLD)
-            ptrs = [int(hdl.buffer_ptrs[(rank + i) % world]) + rank * N_ROWS * k * 8 for i in range(world)]
-            out["multiply+all_gather_fused_p2p_ms"] = timed_unit(
-                lambda: (A0.multiply_scatter(B0.data_ptr(), k, ptrs, args.kernel if args.kernel in ("auto", "rows", "merge", "tiled") else "auto", stream),
-                         hdl.barrier(channel=0)))
-            torch.cuda.synchronize()
-            out["fused_p2p_matches_nccl"] = bool(torch.equal(sym, Call))
-        except Exception as e:  # symmetric memory unavailable on this box: report, do not fail the bench line
-            out["multiply+all_gather_fused_p2p_error"] = str(e)[:200]
-        collectives = out
-        del plan_counts
+            extras = north_star_extras(spmm, torch, dist, dev, rank, world, timed, barrier)
+        except Exception as e:  # never lose the headline line to an extra
+            extras = {"extras_error": f"{type(e).__name__}: {e}"[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -364,14 +394,192 @@ def main():
         line = {"metric": metric, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+                "clocks": clocks, "e2e": e2e, "e2e_first_call": e2e_first, "e2e_pinned": e2e_pinned,
+                "gpu_launches": launches_per_step * args.steps,
                 "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": wall,
                 "hbm_gbs_per_gpu": achieved, "kernel_arg": args.kernel}
-        if collectives:
-            line["collectives"] = collectives
+        line.update(extras)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def north_star_extras(spmm, torch, dist, dev, rank, world, timed, barrier):
+    """BASELINE.json configs 3-5 in the same run: kernel times on one GPU (world == 1) or the partitioned strategies with
+    their exchange steps and the 1-GPU time of the same problem beside them (world > 1); multi-GPU parity vs the oracle."""
+    eng = spmm.CudaCompute(dev.index)
+    peak, _ = measured_peak_gbs()
+
+    def gbs(n_rows, nnz, k, ms, b_rows=None):
+        b = nnz * 12 + (n_rows + 1) * 4 + ((b_rows if b_rows is not None else n_rows) + n_rows) * k * 8
+        return b / (ms * 1e-3) / 1e9
+
+    out = {}
+    # ---- cfg4: banded 2^25 rows x 32 per row, k = 16, row blocks (RowWise.cpp:26-29) ----
+    n, npr, hb, k = 1 << 25, 32, 4096, 16
+    nnz = n * npr
+
+    def cfg4_single():
+        with spmm.DeviceCSR.banded(n, npr, hb, seed=7, device=dev.index) as A:
+            B = torch.randint(1, 101, (n, k), device=dev).double()
+            C = torch.empty((n, k), dtype=torch.float64, device=dev)
+            s = torch.cuda.current_stream().cuda_stream
+            ms = timed_local(torch, lambda: A.multiply(B.data_ptr(), k, C.data_ptr(), "auto", s), 5)
+            del B, C
+        torch.cuda.empty_cache()
+        return ms
+
+    # ---- cfg5: 2^23 rows x 32 uniformly scattered columns per row, k = 64, column blocks + reduce-scatter ----
+    n5, k5 = 1 << 23, 64
+    nnz5 = n5 * 32
+
+    def cfg5_single():
+        with spmm.DeviceCSR.banded(n5, 32, n5 // 2, seed=9, device=dev.index) as A:
+            B = torch.randint(1, 101, (n5, k5), device=dev).double()
+            C = torch.empty((n5, k5), dtype=torch.float64, device=dev)
+            s = torch.cuda.current_stream().cuda_stream
+            ms = timed_local(torch, lambda: A.multiply(B.data_ptr(), k5, C.data_ptr(), "auto", s), 3)
+            del B, C
+        torch.cuda.empty_cache()
+        return ms
+
+    if world == 1:
+        with spmm.DeviceCSR.rmat(22, 16 << 22, seed=11, device=dev.index) as A:  # cfg3: R-MAT 4M x 4M, 64M edges, k = 32
+            k3 = 32
+            B = torch.randint(1, 101, (A.n_rows, k3), device=dev).double()
+            C = torch.empty((A.n_rows, k3), dtype=torch.float64, device=dev)
+            s = torch.cuda.current_stream().cuda_stream
+            ms3 = timed_local(torch, lambda: A.multiply(B.data_ptr(), k3, C.data_ptr(), "auto", s), 5)
+            ms3_rows = timed_local(torch, lambda: A.multiply(B.data_ptr(), k3, C.data_ptr(), "rows", s), 3)
+            n3, nnz3 = A.n_rows, A.nnz
+            del B, C
+        torch.cuda.empty_cache()
+        ms4, ms5 = cfg4_single(), cfg5_single()
+        out["configs_1gpu"] = {
+            "cfg3_rmat_4M_64M_k32": {"kernel_ms": ms3, "row_kernel_ms": ms3_rows, "gflops": 2.0 * nnz3 * k3 / (ms3 * 1e-3) / 1e9,
+                                    "frac_measured_peak": gbs(n3, nnz3, k3, ms3) / peak, "kernel": "nnz-balanced merge-path (AUTO)"},
+            "cfg4_banded_32M_1B_k16": {"kernel_ms": ms4, "gflops": 2.0 * nnz * k / (ms4 * 1e-3) / 1e9,
+                                       "frac_measured_peak": gbs(n, nnz, k, ms4) / peak},
+            "cfg5_uniform_8M_256M_k64": {"kernel_ms": ms5, "gflops": 2.0 * nnz5 * k5 / (ms5 * 1e-3) / 1e9,
+                                         "frac_measured_peak": gbs(n5, nnz5, k5, ms5) / peak}}
+        return out
+
+    # ---- world > 1 ----
+    s0, e0 = spmm.partition_rows(n, world, rank)
+    A = spmm.DeviceCSR.banded(n, npr, hb, seed=7, device=dev.index, row_begin=s0, row_end=e0)
+    plan = spmm.RowWise(eng, n, k, A)
+    B_own = torch.randint(1, 101, (e0 - s0, k), device=dev).double()  # B sharded by rows like C
+    C_own = torch.empty((e0 - s0, k), dtype=torch.float64, device=dev)
+    window, w0 = plan.exchange_halo(B_own)
+    t_halo = timed(lambda: plan.exchange_halo(B_own), 5)
+    t_kernel = timed(lambda: eng.multiply_window(A, window, w0, k, C_own), 10)
+    t_all = timed(lambda: plan.multiply_sharded(B_own, C_own), 5)
+    t_gather = timed(lambda: plan.gather(C_own), 3)
+    halo_bytes = (window.shape[0] - (e0 - s0)) * k * 8
+    A.close()
+    del window, B_own, C_own, plan
+    torch.cuda.empty_cache()
+    barrier()
+    one = cfg4_single() if rank == 0 else 0.0
+    barrier()
+    one = float(_bcast(torch, dist, dev, one))
+    out_cfg4 = {"strategy": "row blocks, B sharded by rows, halo rows exchanged peer to peer (NCCL send/recv over NVLink), C left "
+                            "row-sharded", "n_rows": n, "nnz": nnz, "k": k, "kernel_ms": t_kernel, "halo_exchange_ms": t_halo,
+                "halo_bytes_per_rank": halo_bytes, "exchange_plus_kernel_ms": t_all, "gather_C_to_root_ms": t_gather,
+                "one_gpu_kernel_ms": one, "kernel_speedup_vs_1gpu": one / t_kernel, "all_in_speedup_vs_1gpu": one / t_all,
+                "gflops_all_in": 2.0 * nnz * k / (t_all * 1e-3) / 1e9,
+                "frac_measured_peak_per_gpu": gbs(e0 - s0, nnz // world, k, t_kernel, b_rows=(e0 - s0) + 2 * hb) / peak}
+
+    whole = spmm.DeviceCSR.banded(n5, 32, n5 // 2, seed=9, device=dev.index)
+    c0, c1 = spmm.partition_rows(n5, world, rank)
+    Ab = whole.column_block(c0, c1)
+    whole.close()
+    planb = spmm.ColumnBlocks(eng, n5, n5, k5, Ab)
+    Bl = torch.randint(1, 101, (c1 - c0, k5), device=dev).double()
+    partial = torch.empty((planb.block * world, k5), dtype=torch.float64, device=dev)
+    mine = torch.empty((planb.block, k5), dtype=torch.float64, device=dev)
+    t_k5 = timed(lambda: planb.multiply_local(Bl, partial), 5)
+    t_rs = timed(lambda: planb.reduce_scatter(partial, mine), 3)
+    t_all5 = timed(lambda: planb.reduce_scatter(planb.multiply_local(Bl, partial), mine), 3)
+    try:
+        t_p2p = timed(lambda: planb.multiply_reduce_scatter_p2p(Bl, mine), 3)
+    except Exception as e:
+        t_p2p = None
+        out["cfg5_p2p_error"] = str(e)[:200]
+    Ab.close()
+    del partial, mine, Bl, planb
+    torch.cuda.empty_cache()
+    barrier()
+    one5 = cfg5_single() if rank == 0 else 0.0
+    barrier()
+    one5 = float(_bcast(torch, dist, dev, one5))
+    best5 = min(x for x in (t_all5, t_p2p) if x)
+    out_cfg5 = {"strategy": "column blocks of A, partial C summed by reduce-scatter over NVLink", "n_rows": n5, "nnz": nnz5,
+                "k": k5, "kernel_ms": t_k5, "reduce_scatter_nccl_ms": t_rs, "kernel_plus_reduce_scatter_nccl_ms": t_all5,
+                "kernel_plus_p2p_rank_order_reduce_ms": t_p2p, "one_gpu_kernel_ms": one5,
+                "kernel_speedup_vs_1gpu": one5 / t_k5, "all_in_speedup_vs_1gpu": one5 / best5,
+                "reduce_scatter_bus_GBs": (world - 1) / world * n5 * k5 * 8 / (t_rs * 1e-3) / 1e9}
+    out["north_star_scaling"] = {"cfg4_banded_32M_1B_k16": out_cfg4, "cfg5_uniform_8M_256M_k64": out_cfg5}
+    out["parity_ok"] = multi_gpu_parity(spmm, torch, dist, dev, rank, world)
+    return out
+
+
+def timed_local(torch, fn, iters, warm=2):
+    """Mean device ms on this rank only (no barrier: the other ranks are idle)."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def _bcast(torch, dist, dev, x):
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.broadcast(t, src=0)
+    return t.item()
+
+
+def multi_gpu_parity(spmm, torch, dist, dev, rank, world) -> bool:
+    """The three strategies on THIS process group (NCCL over NVLink) against the oracle on a small cop20k_A-shaped
+    matrix: |x - ref| <= 1e-12 |ref| per entry (the north_star tolerance). The oracle is the checker only."""
+    from sparsematrixmultiplicationmpi_b200 import generators as gen
+    n, nc, r, c, v, sym = gen.cop20k_A_shaped(n=20_000, nnz=420_001, nx=27, ny=27, seed=4)
+    k = 16
+    with spmm.DeviceCSR.from_coo_host(n, nc, r, c, v, sym, device=dev.index) as A:
+        host = A.download()
+    B = np.random.default_rng(3).integers(1, 101, (n, k)).astype(np.float64)
+    Bd = torch.from_numpy(B).to(dev)
+    eng = spmm.CudaCompute(dev.index)
+    results = {}
+    row = spmm.RowWise.from_host(eng, host, k)
+    bs, be = spmm.partition_rows(n, world, rank)
+    results["row_wise_halo"] = row.gather(row.multiply_sharded(Bd[bs:be].contiguous()))
+    results["row_wise_p2p"] = row.run_p2p(Bd)
+    blk = spmm.ColumnBlocks.from_host(eng, host, k)
+    results["column_blocks"] = blk.run(blk.local_B(Bd))
+    results["non_zero_ranges"] = spmm.NonZeroRanges.from_host(eng, host, k).run(Bd)
+    torch.cuda.synchronize()
+    ok = True
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyoracle
+        ref = pyoracle.Oracle().spmm(host.rowPtr, host.colIndices, host.values, B, k)
+        for name, t in results.items():
+            got = t.cpu().numpy()
+            good = got.shape == ref.shape and bool(np.all(np.abs(got - ref) <= 1e-12 * np.abs(ref)))
+            if not good:
+                print(f"bench.py: multi-GPU parity FAILED for {name}", file=sys.stderr)
+            ok = ok and good
+    flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+    dist.broadcast(flag, src=0)
+    for A_ in (row.A, blk.A):
+        A_.close()
+    return bool(flag.item() == 1.0)
 
 
 if __name__ == "__main__":

@@ -135,6 +135,12 @@ int spmm_multiply_device(spmm_csr_t A, const double *d_B, int k, double *d_C, in
 int spmm_multiply_scatter_device(spmm_csr_t A, const double *d_B, int k, int n_dst, double *const *d_C_list,
                                  int kernel, void *stream);
 
+/* Row-wise strategy without replicating B (RowWise.cpp:36-50 reads fatVector[colIndices[j]] only): d_B_window holds the
+ * rows [window_first_row, window_first_row + window_rows) of B — the rows this shard's column ids name (see
+ * spmm_csr_column_span), e.g. the rank's own rows plus a halo fetched from its neighbours. kernel: AUTO, ROWS or MERGE. */
+int spmm_multiply_window_device(spmm_csr_t A, const double *d_B_window, int window_first_row, int window_rows, int k,
+                                double *d_C, int kernel, void *stream);
+
 /* Strided form: B has leading dimension ldb, C has ldc; columns [k_begin, k_begin+k_count)
  * of B/C are computed (the k-slab split of ColumnWise.cpp:25-48). */
 int spmm_multiply_strided_device(spmm_csr_t A, const double *d_B, int ldb, double *d_C, int ldc,

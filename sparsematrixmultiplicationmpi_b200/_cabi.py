@@ -76,6 +76,7 @@ PROTOTYPES = {
     "spmm_csr_tile_info": (_i, [_p, _pi, _pi, _pi, _pi, _pd, _pd]),
     "spmm_multiply_device": (_i, [_p, _p, _i, _p, _i, _p]),
     "spmm_multiply_scatter_device": (_i, [_p, _p, _i, _i, C.POINTER(_p), _i, _p]),
+    "spmm_multiply_window_device": (_i, [_p, _p, _i, _i, _i, _p, _i, _p]),
     "spmm_multiply_strided_device": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _p]),
     "spmm_multiply_host": (_i, [_p, _p, _i, _p, _i]),
     "spmm_multiply_rows_device": (_i, [_p, _i, _i, _p, _i, _p, _i, _p]),

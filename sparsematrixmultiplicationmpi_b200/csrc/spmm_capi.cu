@@ -529,6 +529,28 @@ int spmm_multiply_device(spmm_csr_t A, const double *d_B, int k, double *d_C, in
     return spmm_multiply_strided_device(A, d_B, k, d_C, k, 0, k, kernel, stream);
 }
 
+int spmm_multiply_window_device(spmm_csr_t A, const double *d_B_window, int window_first_row, int window_rows, int k,
+                                double *d_C, int kernel, void *stream)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(k >= 0 && window_first_row >= 0 && window_rows >= 0 && (long long)window_first_row + window_rows <= A->n_cols,
+                 "window outside B");
+    if (A->n_rows == 0 || k == 0)
+        return SPMM_OK;
+    SPMM_REQUIRE(d_C != nullptr && (d_B_window != nullptr || A->nnz == 0), "d_B_window / d_C is NULL");
+    SPMM_REQUIRE(kernel == SPMM_KERNEL_AUTO || kernel == SPMM_KERNEL_ROWS || kernel == SPMM_KERNEL_MERGE,
+                 "window multiply: kernel must be auto, rows or merge (the CSR kernels read B rows one by one)");
+    SPMM_CUDA(cudaSetDevice(A->device));
+    // virtual base: row j of B sits at d_B_window + (j - window_first_row) * k; only rows named by column ids are read
+    const double *base = d_B_window - (long long)window_first_row * k;
+    if (select_kernel(A, kernel) == SPMM_KERNEL_MERGE)
+        return launch_merge(A, 0, A->n_rows, 0, A->nnz, 0, base, k, d_C, k, k, (cudaStream_t)stream);
+    set_b_window(true);
+    const int rc = launch_rows(A, 0, A->n_rows, 0, A->nnz, 0, base, k, d_C, k, k, 0, (cudaStream_t)stream);
+    set_b_window(false);
+    return rc;
+}
+
 int spmm_multiply_rows_device(spmm_csr_t A, int row_begin, int row_end, const double *d_B, int k,
                               double *d_C_local, int kernel, void *stream)
 {

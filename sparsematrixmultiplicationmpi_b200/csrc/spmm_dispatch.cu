@@ -72,6 +72,11 @@ Shape pick_shape(const double *d_B, long long ldb, const double *d_C, long long 
 }
 } // namespace
 
+// set around a launch whose B pointer is the virtual base of a window of rows (rows outside the window are not mapped):
+// nothing may touch B beyond the rows the matrix's column ids name — no bulk prefetch of "all of B"
+static thread_local bool t_b_is_window = false;
+void set_b_window(bool on) { t_b_is_window = on; }
+
 int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
                 const double *d_B, long long ldb, double *d_C, long long ldc, int kc, int derived,
                 cudaStream_t stream, const ExtraDst *extra)
@@ -139,7 +144,7 @@ int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_l
     // at column 0 of its rows (no k-slab), and the A arrays are the handle's own (padded) allocations
     const bool aligned = ((uintptr_t)A->d_colidx % 16 == 0) && ((uintptr_t)A->d_vals % 16 == 0) && ((uintptr_t)d_B % 16 == 0);
     args.prefetch = aligned ? (t.rows_prefetch >= 0 ? t.rows_prefetch : 3) : 0;
-    args.b_bytes = (ldb == kc) ? (long long)A->n_cols * ldb * 8 : 0;
+    args.b_bytes = (ldb == kc && !t_b_is_window) ? (long long)A->n_cols * ldb * 8 : 0;
     if (sweep)
     {
         note_kernel("spmm_rows_sweep_kernel");

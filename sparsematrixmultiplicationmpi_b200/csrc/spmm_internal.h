@@ -134,6 +134,7 @@ namespace spmm
 int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
                 const double *d_B, long long ldb, double *d_C, long long ldc, int kc, int derived,
                 cudaStream_t stream, const struct ExtraDst *extra = nullptr); // derived: 0 CSR row kernel only, 1 best available, 6 tiled
+void set_b_window(bool on); // the next launch_rows of this thread gets a window of B rows (no whole-B prefetch)
 int launch_merge(spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, long long nnz_hi, int c_row0,
                  const double *d_B, long long ldb, double *d_C, long long ldc, int kc, cudaStream_t stream,
                  const struct ExtraDst *extra = nullptr);

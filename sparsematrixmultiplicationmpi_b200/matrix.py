@@ -189,6 +189,18 @@ class DeviceCSR:
                                                    _cabi.KERNELS[kernel]))
         return Cm
 
+    def column_span(self) -> tuple[int, int]:
+        """(min, max) column id stored: the rows of B this shard reads (spmm_csr_column_span); (0, -1) when empty."""
+        lo, hi = C.c_int(), C.c_int()
+        _cabi.check(_cabi.lib().spmm_csr_column_span(self.handle, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def multiply_window(self, d_B_window: int, first_row: int, n_rows: int, k: int, d_C: int, kernel: str = "auto",
+                        stream: int = 0) -> None:
+        """C = A*B with only the rows [first_row, first_row+n_rows) of B resident (spmm_multiply_window_device)."""
+        _cabi.check(_cabi.lib().spmm_multiply_window_device(self.handle, C.c_void_p(d_B_window), first_row, n_rows, k,
+                                                            C.c_void_p(d_C), _cabi.KERNELS[kernel], C.c_void_p(stream)))
+
     def upload_dense(self, src: np.ndarray, d_dst: int, stream: int = 0) -> None:
         """(n, k) float64 host block -> device buffer d_dst through the handle's pinned staging and the library's host
         threads (spmm_upload_dense); returns when the copy is done."""

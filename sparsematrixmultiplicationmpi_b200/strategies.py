@@ -83,6 +83,20 @@ class CudaCompute:
             A.multiply(B.data_ptr(), k, out.data_ptr(), self.kernel, torch.cuda.current_stream(self.device).cuda_stream)
         return out
 
+    def column_span(self, A: DeviceCSR) -> tuple[int, int]:
+        return A.column_span()
+
+    def multiply_window(self, A: DeviceCSR, window: torch.Tensor, first_row: int, k: int,
+                        out: torch.Tensor | None = None) -> torch.Tensor:
+        """out = A * B where only the rows [first_row, first_row + len(window)) of B are resident (the block's halo window)."""
+        if out is None:
+            out = torch.empty((A.n_rows, k), dtype=torch.float64, device=self.device)
+        if A.n_rows and k:
+            A.multiply_window(window.data_ptr(), first_row, window.shape[0], k, out.data_ptr(),
+                              self.kernel if self.kernel in ("auto", "rows", "merge") else "auto",
+                              torch.cuda.current_stream(self.device).cuda_stream)
+        return out
+
     def multiply_rows(self, A: DeviceCSR, row_begin: int, row_end: int, B: torch.Tensor, k: int, out: torch.Tensor):
         """out[row_end-row_begin, k] = A[row_begin:row_end, :] * B (a row block of the shard, RowWise.cpp:36-50)."""
         if row_end > row_begin and k:
@@ -163,6 +177,55 @@ class RowWise:
     def run(self, B: torch.Tensor) -> torch.Tensor | None:
         """The reference call: local rows, then Gatherv to rank 0; None on the other ranks."""
         return self.gather(self.multiply_local(B))
+
+    # ---- B row-sharded like C: only the rows of B a block's columns name cross the links (halo exchange) ----
+    # The reference replicates all of B on every rank (main.cpp:137); its row loop reads fatVector[colIndices[j]] only
+    # (RowWise.cpp:36-50). With B sharded by rows the way C is (rank q owns B[bs_q:be_q], what an iterative caller has
+    # after a multiply), a banded block needs its own rows plus a halo of half a bandwidth from its neighbours —
+    # kilobytes over NVLink instead of a broadcast of the whole fat vector.
+    def halo_plan(self):
+        """Column span [lo, hi] of every rank's block (exchanged once) and the B rows every rank owns."""
+        if getattr(self, "_halo", None) is None:
+            n_cols = self.A.n_cols
+            lo, hi = self.compute.column_span(self.A)
+            spans = [(lo, hi)]
+            if self.P > 1:
+                spans = [None] * self.P
+                dist.all_gather_object(spans, (lo, hi), group=self.group)
+            owners = [partition_rows(n_cols, self.P, q) for q in range(self.P)]
+            self._halo = (spans, owners)
+        return self._halo
+
+    def exchange_halo(self, B_own: torch.Tensor) -> tuple[torch.Tensor, int]:
+        """B_own = this rank's rows of B. Returns (window, first_row): the rows [first_row, first_row + len(window)) of B
+        that this rank's block reads, its own part copied locally, the rest received peer to peer from their owners."""
+        spans, owners = self.halo_plan()
+        lo, hi = spans[self.rank]
+        bs, be = owners[self.rank]
+        assert B_own.shape[0] == be - bs
+        window = torch.empty((max(0, hi - lo + 1), self.k), dtype=B_own.dtype, device=B_own.device)
+        ops = []
+        for q in range(self.P):
+            qs, qe = owners[q]
+            a, b = max(lo, qs), min(hi + 1, qe)  # rows of mine that q owns
+            if b > a:
+                if q == self.rank:
+                    window[a - lo:b - lo].copy_(B_own[a - bs:b - bs])
+                else:
+                    ops.append(dist.P2POp(dist.irecv, window[a - lo:b - lo], q, group=self.group))
+            qlo, qhi = spans[q]
+            a, b = max(qlo, bs), min(qhi + 1, be)  # rows of q's window that I own
+            if b > a and q != self.rank:
+                ops.append(dist.P2POp(dist.isend, B_own[a - bs:b - bs].contiguous(), q, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return window, lo
+
+    def multiply_sharded(self, B_own: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """C[start:end] from B sharded by rows: halo exchange, then the block multiply on the window."""
+        window, first = self.exchange_halo(B_own)
+        return self.compute.multiply_window(self.A, window, first, self.k, out)
 
     # ---- gather fused into the multiply: C rows stored straight into the peers' buffers over NVLink ----
     def _symmetric_C(self, device: torch.device):

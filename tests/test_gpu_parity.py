@@ -675,7 +675,6 @@ def test_host_multiply_k_slab_pipeline(oracle, slabs):
     ref = oracle.spmm(rp, ci, va, B, k)
     _cabi.tune("reset", 0)
     _cabi.tune("host.slabs", slabs)
-    _cabi.tune("host.pipe", 0)  # this test is about the k-slab pipeline
     try:
         with spmm.DeviceCSR.from_host(m, 0) as A:
             got = A.multiply_host(B, k, "auto")
@@ -687,10 +686,10 @@ def test_host_multiply_k_slab_pipeline(oracle, slabs):
 
 
 @pytest.mark.parametrize("shape", ["banded", "random", "rect_wide", "rect_tall", "mostly_empty"])
-@pytest.mark.parametrize("pipe", [-1, 1])
-def test_host_multiply_row_block_pipeline(oracle, shape, pipe):
-    """spmm_multiply_host with the row-block pipeline (host.pipe): block j of C is multiplied once the B rows it reads have
-    arrived. Forced (1) on shapes where block 0 already needs all of B, automatic (-1) where the estimate decides."""
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_multiply_rows_and_flat_buffers(oracle, shape, pinned):
+    """spmm_multiply_host (flat buffer: pinned goes straight to the copy engine, pageable through the pinned staging and
+    the host threads) and spmm_multiply_host_rows (one pointer per row: the memory shape of a FatVector) give the oracle's C."""
     k = 64
     if shape == "banded":
         n, nc = 40_000, 40_000
@@ -702,15 +701,42 @@ def test_host_multiply_row_block_pipeline(oracle, shape, pipe):
     m = spmm.SparseMatrix(va, ci, rp, n, nc)
     B = np.random.default_rng(9).integers(1, 101, (nc, k)).astype(np.float64)
     ref = oracle.spmm(rp, ci, va, B, k)
-    _cabi.tune("reset", 0)
-    _cabi.tune("host.pipe", pipe)
-    try:
-        with spmm.DeviceCSR.from_host(m, 0) as A:
-            for kernel in ("auto", "rows"):
-                got = A.multiply_host(B, k, kernel)
-                assert_close_rel(got, ref, tol=REL_TOL)
-    finally:
-        _cabi.tune("reset", 0)
+    with spmm.DeviceCSR.from_host(m, 0) as A:
+        if pinned:
+            Bp = torch.from_numpy(B).pin_memory()
+            Cp = torch.empty((n, k), dtype=torch.float64).pin_memory()
+            got = A.multiply_host(Bp.numpy(), k, "auto", Cp.numpy())
+        else:
+            got = A.multiply_host(B, k, "auto")
+        assert_close_rel(got, ref, tol=REL_TOL)
+        # FatVector shape: every row its own allocation
+        rows_in = [np.ascontiguousarray(B[i]) for i in range(nc)]
+        rows_out = [np.full(k, np.nan) for _ in range(n)]
+        pin = (C.c_void_p * nc)(*[r.ctypes.data for r in rows_in])
+        pout = (C.c_void_p * n)(*[r.ctypes.data for r in rows_out])
+        _cabi.check(_cabi.lib().spmm_multiply_host_rows(A.handle, pin, k, pout, _cabi.KERNEL_AUTO))
+        assert_close_rel(np.stack(rows_out), ref, tol=REL_TOL)
+
+
+def test_window_multiply_reads_only_the_rows_it_is_given(oracle):
+    """spmm_multiply_window_device: a row block of a banded matrix with only its own rows of B plus the halo resident."""
+    n, k = 20_000, 16
+    rp, ci, va = banded_csr(67, n, 12, 40, (-300, 0, 300))
+    m = spmm.SparseMatrix(va, ci, rp, n, n)
+    B = np.random.default_rng(2).integers(1, 101, (n, k)).astype(np.float64)
+    ref = oracle.spmm(rp, ci, va, B, k)
+    for P, r in ((4, 0), (4, 2), (4, 3), (1, 0)):
+        s, e = spmm.partition_rows(n, P, r)
+        with spmm.DeviceCSR.from_host(m.row_block(s, e), 0) as A:
+            lo, hi = A.column_span()
+            assert lo == ci[rp[s]:rp[e]].min() and hi == ci[rp[s]:rp[e]].max()
+            window = dev(B[lo:hi + 1])  # nothing else of B exists on the device
+            out = torch.full((e - s, k), np.nan, dtype=torch.float64, device="cuda")
+            for kernel in ("rows", "merge", "auto"):
+                A.multiply_window(window.data_ptr(), lo, hi - lo + 1, k, out.data_ptr(), kernel,
+                                  torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                assert_close_rel(out.cpu().numpy(), ref[s:e], tol=REL_TOL)
 
 
 def test_reduce_blocks_rank_order():

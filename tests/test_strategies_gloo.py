@@ -42,6 +42,23 @@ class OracleCompute:
         out.copy_(t)
         return out
 
+    def column_span(self, A):
+        return (int(A.m.colIndices.min()), int(A.m.colIndices.max())) if A.m.nnz else (0, -1)
+
+    def multiply_window(self, A, window, first_row, k, out=None):
+        full = np.full((A.m.numCols, k), np.nan)  # rows outside the window must never be read with a non-zero weight
+        full[first_row:first_row + window.shape[0]] = window.numpy()
+        m = A.m
+        C = self.o.spmm(m.rowPtr, m.colIndices, m.values, np.nan_to_num(full, nan=0.0), k) if m.numRows else np.zeros((0, k))
+        touched = np.zeros(m.numCols, bool)
+        touched[m.colIndices] = True
+        assert not np.isnan(full[touched]).any(), "the window misses a row of B the block reads"
+        t = torch.from_numpy(np.ascontiguousarray(C))
+        if out is None:
+            return t
+        out.copy_(t)
+        return out
+
     def multiply_rows(self, A, row_begin, row_end, B, k, out):
         m = A.m
         if row_end > row_begin:
@@ -80,11 +97,14 @@ def _worker(rank, world, port, case, results):
                  "row_overlap": row.multiply_all_gather_overlapped(Bt, chunks=3)}
         assert torch.equal(extra["colblk_overlap"], extra["colblk_plain"])  # same sums in the same order
         out["nnz"] = spmm.NonZeroRanges.from_host(eng, m, k).run(Bt)
+        # B sharded by rows like C: halo exchange, then the block multiply on the window; gathered for the check
+        bs, be = spmm.partition_rows(n, world, rank)
+        out["row_sharded"] = row.gather(row.multiply_sharded(Bt[bs:be].clone()))
         results[f"row_overlap_{rank}"] = extra["row_overlap"].numpy().copy()
         if rank == 0:
             results.update({name: t.numpy().copy() for name, t in out.items()})
         else:
-            assert all(out[name] is None for name in ("row", "colblk", "colslab", "nnz"))  # FatVector{} off-root
+            assert all(out[name] is None for name in ("row", "colblk", "colslab", "nnz", "row_sharded"))  # FatVector{} off-root
             results[f"allgather_{rank}"] = out["row_allgather"].numpy().copy()
     finally:
         dist.destroy_process_group()
@@ -118,6 +138,7 @@ def test_strategies_world(oracle, world, case):
     assert np.array_equal(results["row"], seq)
     assert np.array_equal(results["colslab"], oracle.spmm(rowptr, colidx, vals, B, k, "col", world))
     assert np.array_equal(results["row_allgather"], seq)
+    assert np.array_equal(results["row_sharded"], seq)  # halo exchange instead of a replicated B: same rows, same order
     for r in range(1, world):
         assert np.array_equal(results[f"allgather_{r}"], seq)
     for r in range(world):
