@@ -156,6 +156,12 @@ int spmm_multiply_host(spmm_csr_t A, const double *B, int k, double *C, int kern
  * (deserialize(), :237-253) run on the library's host threads straight into / out of pinned staging memory, chunk by
  * chunk, overlapped with the copies. C_rows must already point at n_rows buffers of k doubles. */
 int spmm_multiply_host_rows(spmm_csr_t A, const double *const *B_rows, int k, double *const *C_rows, int kernel);
+/* The same, with the result handed to the caller chunk by chunk while later chunks are still on their way down:
+ * sink(row_begin, row_end, rows, ctx) receives rows [row_begin, row_end) of C (row-major, leading dimension k) and is
+ * called from the library's host threads on disjoint row ranges — the C++ entry points construct the rows of the
+ * result FatVector in it (allocation and copy in one pass, SparseMatrixFatVectorMultiply.cpp:15). */
+typedef void (*spmm_rows_sink)(int row_begin, int row_end, const double *rows, void *ctx);
+int spmm_multiply_host_sink(spmm_csr_t A, const double *const *B_rows, int k, spmm_rows_sink sink, void *ctx, int kernel);
 int spmm_host_threads(void); /* size of that host thread pool (env SPMM_HOST_THREADS, default min(cores, 32)) */
 /* fn(i, ctx) for i in [0, n) on that pool, the caller taking part; returns when all are done (the entry points use it to
  * allocate the rows of the result FatVector in parallel). */
@@ -205,6 +211,7 @@ int spmm_download_dense(spmm_csr_t A, const double *d_src, long long n_rows, int
 int spmm_csr_stream_sync(spmm_csr_t A); /* wait for everything enqueued on the handle's stream */
 /* n_rows x k doubles at d_C (on A's device) -> C_rows[i], through A's pinned staging, unpacked by the host threads. */
 int spmm_fetch_c_rows(spmm_csr_t A, const double *d_C, int n_rows, int k, double *const *C_rows);
+int spmm_fetch_c_sink(spmm_csr_t A, const double *d_C, int n_rows, int k, spmm_rows_sink sink, void *ctx);
 /* A device buffer of at least `bytes` that lives until spmm_device_scratch_release (one per (device, slot)). */
 int spmm_device_scratch(int device, int slot, long long bytes, void **out);
 int spmm_device_scratch_release(void);

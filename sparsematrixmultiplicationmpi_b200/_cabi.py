@@ -59,6 +59,8 @@ PROTOTYPES = {
     "spmm_csr_build_tiles_for_k": (_i, [_p, _i, _i, _i]),
     "spmm_csr_column_span": (_i, [_p, _pi, _pi]),
     "spmm_multiply_host_rows": (_i, [_p, _p, _i, _p, _i]),
+    "spmm_multiply_host_sink": (_i, [_p, _p, _i, _p, _p, _i]),
+    "spmm_fetch_c_sink": (_i, [_p, _p, _i, _i, _p, _p]),
     "spmm_host_threads": (_i, []),
     "spmm_host_parallel_for": (None, [_i, _p, _p]),
     "spmm_stage_b_rows": (_i, [_p, _p, _i, _i, _i, C.POINTER(_p), C.POINTER(_p)]),

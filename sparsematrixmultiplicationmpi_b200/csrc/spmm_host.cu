@@ -164,20 +164,8 @@ bool is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
-constexpr size_t CHUNK_BYTES = 2u << 20; // rows per pipeline chunk: about 2 MB of the slab being moved
-
-int ensure_pinned(double **buf, size_t *have, size_t want)
-{
-    if (*have >= want)
-        return SPMM_OK;
-    if (*buf)
-        cudaFreeHost(*buf);
-    *buf = nullptr;
-    *have = 0;
-    SPMM_CUDA(cudaHostAlloc((void **)buf, sizeof(double) * std::max<size_t>(want, 1), cudaHostAllocDefault));
-    *have = want;
-    return SPMM_OK;
-}
+constexpr size_t CHUNK_BYTES = 2u << 20; // pipeline chunk: about 2 MB of rows
+constexpr int RING_SLOTS = 6;            // chunks in flight per direction (pinned staging ring: 2 x 6 x 2 MB per handle)
 
 int ensure_device(double **buf, size_t *have, size_t want)
 {
@@ -200,158 +188,149 @@ int ensure_streams(spmm_csr_t A)
         SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_up, cudaStreamNonBlocking));
         SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_down, cudaStreamNonBlocking));
     }
-    return SPMM_OK;
-}
-
-int event_at(spmm_csr_t A, size_t i, cudaEvent_t *out)
-{
-    while (A->events.size() <= i)
+    while (A->events.size() < 2 * RING_SLOTS + 16)
     {
         cudaEvent_t e;
         SPMM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         A->events.push_back(e);
     }
-    *out = A->events[i];
     return SPMM_OK;
 }
 
-// Rows [r0, r1) x columns [k0, k0+kc) of `src` -> the device image d (leading dimension k, row r at d + r*k), enqueued on
-// `s`. Pageable / row-pointer sources are packed chunk by chunk into the pinned mirror `stage` (same geometry as d) by the
-// pool while the copy engine moves the chunks already packed.
-int upload_rows(const HostRows &src, bool direct, double *stage, double *d, int r0, int r1, int k, int k0, int kc,
-                cudaStream_t s)
+// Pinned staging ring of the handle: RING_SLOTS chunks per direction. A small ring instead of full mirrors of B and C keeps
+// the first call on a new matrix cheap (page-locking 124 MB costs tens of milliseconds; the reference calls each function once).
+int ensure_ring(spmm_csr_t A)
 {
-    if (r1 <= r0 || kc <= 0)
+    if (A->h_ring)
         return SPMM_OK;
-    const size_t pitch = sizeof(double) * (size_t)k, width = sizeof(double) * (size_t)kc;
-    if (direct)
-    {
-        const double *h = src.flat + (long long)r0 * src.ld + k0;
-        if (kc == k && src.ld == k)
-            SPMM_CUDA(cudaMemcpyAsync(d + (size_t)r0 * k, h, pitch * (size_t)(r1 - r0), cudaMemcpyHostToDevice, s));
-        else
-            SPMM_CUDA(cudaMemcpy2DAsync(d + (size_t)r0 * k + k0, pitch, h, sizeof(double) * (size_t)src.ld, width,
-                                        (size_t)(r1 - r0), cudaMemcpyHostToDevice, s));
+    SPMM_CUDA(cudaHostAlloc((void **)&A->h_ring, 2 * RING_SLOTS * CHUNK_BYTES, cudaHostAllocDefault));
+    return SPMM_OK;
+}
+double *ring_slot(spmm_csr_t A, int dir, int slot) { return A->h_ring + ((size_t)(dir * RING_SLOTS + slot) * CHUNK_BYTES) / sizeof(double); }
+cudaEvent_t ring_event(spmm_csr_t A, int dir, int slot) { return A->events[16 + dir * RING_SLOTS + slot]; }
+
+int rows_per_chunk(int k) { return (int)std::max<size_t>(1, CHUNK_BYTES / (sizeof(double) * (size_t)std::max(k, 1))); }
+
+// Rows [r0, r1) of `src` (all k columns) -> the device image d (row r at d + r*k), enqueued on `s`: packed chunk by chunk into
+// the ring by the pool while the copy engine moves the chunks already packed (serialize(), utils.cpp:216-228, pipelined).
+int staged_upload(spmm_csr_t A, const HostRows &src, double *d, int r0, int r1, int k, cudaStream_t s)
+{
+    if (r1 <= r0 || k <= 0)
         return SPMM_OK;
-    }
-    const int rows_per_chunk = (int)std::max<size_t>(64, CHUNK_BYTES / width);
-    const int sub = std::max(16, rows_per_chunk / (4 * pool().threads())); // rows per pool task
-    for (int c0 = r0; c0 < r1; c0 += rows_per_chunk)
+    const int rpc = rows_per_chunk(k);
+    const size_t width = sizeof(double) * (size_t)k;
+    const int sub = std::max(8, rpc / (2 * pool().threads())); // rows per pool task
+    int used = 0;
+    for (int c0 = r0; c0 < r1; c0 += rpc, ++used)
     {
-        const int c1 = std::min(r1, c0 + rows_per_chunk);
+        const int c1 = std::min(r1, c0 + rpc), slot = used % RING_SLOTS;
+        if (used >= RING_SLOTS)
+            SPMM_CUDA(cudaEventSynchronize(ring_event(A, 0, slot))); // the chunk that used this slot has left the host
+        double *stage = ring_slot(A, 0, slot);
         pool().parallel_for((c1 - c0 + sub - 1) / sub, [&](int t) {
             const int a = c0 + t * sub, b = std::min(c1, a + sub);
             for (int r = a; r < b; ++r)
-                std::memcpy(stage + (size_t)r * k + k0, src.at(r) + k0, width);
+                std::memcpy(stage + (size_t)(r - c0) * k, src.at(r), width);
         });
-        if (kc == k)
-            SPMM_CUDA(cudaMemcpyAsync(d + (size_t)c0 * k, stage + (size_t)c0 * k, pitch * (size_t)(c1 - c0),
-                                      cudaMemcpyHostToDevice, s));
-        else
-            SPMM_CUDA(cudaMemcpy2DAsync(d + (size_t)c0 * k + k0, pitch, stage + (size_t)c0 * k + k0, pitch, width,
-                                        (size_t)(c1 - c0), cudaMemcpyHostToDevice, s));
+        SPMM_CUDA(cudaMemcpyAsync(d + (size_t)c0 * k, stage, width * (size_t)(c1 - c0), cudaMemcpyHostToDevice, s));
+        SPMM_CUDA(cudaEventRecord(ring_event(A, 0, slot), s));
     }
     return SPMM_OK;
 }
 
-// One pending download chunk: rows [c0,c1) x columns [k0,k0+kc) land in the pinned mirror; `ev` says when.
-struct Pending
+// n rows x k at d_c -> sink(row_begin, row_end, rows, ctx) chunk by chunk as they arrive (`rows` = row_begin's first double,
+// leading dimension k); the sink runs on the pool threads over disjoint row ranges (deserialize(), utils.cpp:237-253).
+typedef void (*RowsSink)(int, int, const double *, void *);
+int staged_download(spmm_csr_t A, const double *d_c, int n, int k, cudaStream_t s, RowsSink sink, void *ctx)
 {
-    int c0, c1, k0, kc;
-    cudaEvent_t ev;
+    if (n <= 0 || k <= 0)
+        return SPMM_OK;
+    const int rpc = rows_per_chunk(k);
+    const size_t width = sizeof(double) * (size_t)k;
+    const int n_chunks = (n + rpc - 1) / rpc;
+    const int sub = std::max(8, rpc / (2 * pool().threads()));
+    auto issue = [&](int c) -> cudaError_t {
+        const int c0 = c * rpc, c1 = std::min(n, c0 + rpc), slot = c % RING_SLOTS;
+        cudaError_t e = cudaMemcpyAsync(ring_slot(A, 1, slot), d_c + (size_t)c0 * k, width * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, s);
+        return e == cudaSuccess ? cudaEventRecord(ring_event(A, 1, slot), s) : e;
+    };
+    for (int c = 0; c < std::min(n_chunks, RING_SLOTS); ++c)
+        SPMM_CUDA(issue(c));
+    for (int c = 0; c < n_chunks; ++c)
+    {
+        const int c0 = c * rpc, c1 = std::min(n, c0 + rpc), slot = c % RING_SLOTS;
+        SPMM_CUDA(cudaEventSynchronize(ring_event(A, 1, slot)));
+        const double *stage = ring_slot(A, 1, slot);
+        pool().parallel_for((c1 - c0 + sub - 1) / sub, [&](int t) {
+            const int a = c0 + t * sub, b = std::min(c1, a + sub);
+            sink(a, b, stage + (size_t)(a - c0) * k, ctx);
+        });
+        if (c + RING_SLOTS < n_chunks)
+            SPMM_CUDA(issue(c + RING_SLOTS));
+    }
+    return SPMM_OK;
+}
+
+struct CopySink
+{
+    HostRowsOut dst;
+    int k;
 };
-
-// Enqueue the download of rows [0,n) x columns [k0,k0+kc) of the device image d_c (ld k) on `s`.
-int download_rows(spmm_csr_t A, const HostRowsOut &dst, bool direct, double *stage, const double *d_c, int n, int k,
-                  int k0, int kc, cudaStream_t s, std::vector<Pending> *pending, size_t *next_event)
+void copy_sink(int r0, int r1, const double *rows, void *ctx)
 {
-    if (n <= 0 || kc <= 0)
-        return SPMM_OK;
-    const size_t pitch = sizeof(double) * (size_t)k, width = sizeof(double) * (size_t)kc;
-    if (direct)
-    {
-        if (kc == k && dst.ld == k)
-            SPMM_CUDA(cudaMemcpyAsync(dst.flat, d_c, pitch * (size_t)n, cudaMemcpyDeviceToHost, s));
-        else
-            SPMM_CUDA(cudaMemcpy2DAsync(dst.flat + k0, sizeof(double) * (size_t)dst.ld, d_c + k0, pitch, width, (size_t)n,
-                                        cudaMemcpyDeviceToHost, s));
-        return SPMM_OK;
-    }
-    const int rows_per_chunk = (int)std::max<size_t>(64, CHUNK_BYTES / width);
-    for (int c0 = 0; c0 < n; c0 += rows_per_chunk)
-    {
-        const int c1 = std::min(n, c0 + rows_per_chunk);
-        if (kc == k)
-            SPMM_CUDA(cudaMemcpyAsync(stage + (size_t)c0 * k, d_c + (size_t)c0 * k, pitch * (size_t)(c1 - c0),
-                                      cudaMemcpyDeviceToHost, s));
-        else
-            SPMM_CUDA(cudaMemcpy2DAsync(stage + (size_t)c0 * k + k0, pitch, d_c + (size_t)c0 * k + k0, pitch, width,
-                                        (size_t)(c1 - c0), cudaMemcpyDeviceToHost, s));
-        Pending p{c0, c1, k0, kc, nullptr};
-        const int rc = event_at(A, (*next_event)++, &p.ev);
-        if (rc)
-            return rc;
-        SPMM_CUDA(cudaEventRecord(p.ev, s));
-        pending->push_back(p);
-    }
-    return SPMM_OK;
+    const CopySink &c = *static_cast<const CopySink *>(ctx);
+    for (int r = r0; r < r1; ++r)
+        std::memcpy(c.dst.at(r), rows + (size_t)(r - r0) * c.k, sizeof(double) * (size_t)c.k);
 }
 
-// Unpack the chunks as they arrive (deserialize(), utils.cpp:237-253, chunk by chunk on the pool).
-int unpack_pending(const HostRowsOut &dst, const double *stage, int k, const std::vector<Pending> &pending)
-{
-    for (const Pending &p : pending)
-    {
-        SPMM_CUDA(cudaEventSynchronize(p.ev));
-        const size_t width = sizeof(double) * (size_t)p.kc;
-        const int sub = std::max(16, (p.c1 - p.c0) / (4 * pool().threads()));
-        pool().parallel_for((p.c1 - p.c0 + sub - 1) / sub, [&](int t) {
-            const int a = p.c0 + t * sub, b = std::min(p.c1, a + sub);
-            for (int r = a; r < b; ++r)
-                std::memcpy(dst.at(r) + p.k0, stage + (size_t)r * k + p.k0, width);
-        });
-    }
-    return SPMM_OK;
-}
-
-// The whole host-buffer call: rows [b0,b1) of B up (all other rows of the device image are not read by this launch),
-// `launch(dB, dC, k0, kc, stream)` per k-slab, c_rows rows of C down.
+// The whole host-buffer call: rows [b0,b1) of B up (the other rows of the device image are not read by this launch),
+// `launch(dB, dC, k0, kc, stream)`, c_rows rows of C down. Pinned flat buffers go to the copy engine as they are, wide ones
+// in `slabs` k-slabs so that the upload of slab s+1 overlaps the download of slab s (PCIe is full duplex); everything else
+// is staged through the ring in one pass (packing per slab would touch every source row once per slab: measured 3.3 ms with
+// one slab against 4.3 / 5.2 ms with two / four on cfg2 k=64, gpurun_out/r2b_e2e.json).
 template <typename Launch>
-int host_multiply(spmm_csr_t A, const HostRows &B, int b0, int b1, int k, const HostRowsOut &C, int c_rows, int slabs,
-                  Launch launch)
+int host_multiply(spmm_csr_t A, const HostRows &B, int b0, int b1, int k, const HostRowsOut &C, RowsSink sink, void *sink_ctx,
+                  int c_rows, int slabs, Launch launch)
 {
     SPMM_CUDA(cudaSetDevice(A->device));
-    std::lock_guard<std::mutex> guard(A->host_mu); // staging buffers and streams of a handle serve one call at a time
+    std::lock_guard<std::mutex> guard(A->host_mu); // staging ring and streams of a handle serve one call at a time
     const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)c_rows * (size_t)k;
     int rc = ensure_streams(A);
     if (!rc)
         rc = ensure_device(&A->d_B, &A->d_B_elems, nb);
     if (!rc)
         rc = ensure_device(&A->d_C, &A->d_C_elems, nc);
-    const bool b_direct = !B.rows && is_pinned(B.flat), c_direct = !C.rows && is_pinned(C.flat);
-    if (!rc && !b_direct)
-        rc = ensure_pinned(&A->h_B, &A->h_B_elems, nb);
-    if (!rc && !c_direct)
-        rc = ensure_pinned(&A->h_C, &A->h_C_elems, nc);
+    const bool b_direct = !B.rows && is_pinned(B.flat), c_direct = !sink && !C.rows && is_pinned(C.flat);
+    if (!rc && !(b_direct && c_direct))
+        rc = ensure_ring(A);
     if (rc)
         return rc;
+    if (!(b_direct && c_direct))
+        slabs = 1;
     while (slabs > 1 && (k % slabs != 0 || (k / slabs) % 2 != 0))
         --slabs;
     slabs = std::max(1, std::min(slabs, 8));
     const int ks = k / slabs;
-    std::vector<Pending> pending;
-    size_t ev = 0; // events of the handle used by this call
+    const size_t pitch = sizeof(double) * (size_t)k, width = sizeof(double) * (size_t)ks;
     for (int sidx = 0; sidx < slabs; ++sidx)
     {
         const int k0 = sidx * ks;
-        cudaEvent_t up, done;
-        rc = upload_rows(B, b_direct, A->h_B, A->d_B, b0, b1, k, k0, ks, A->stream_up);
-        if (!rc)
-            rc = event_at(A, ev++, &up);
-        if (!rc)
-            rc = event_at(A, ev++, &done);
-        if (rc)
-            return rc;
+        cudaEvent_t up = A->events[2 * sidx], done = A->events[2 * sidx + 1];
+        if (b_direct && b1 > b0)
+        {
+            const double *h = B.flat + (long long)b0 * B.ld + k0;
+            if (slabs == 1 && B.ld == k)
+                SPMM_CUDA(cudaMemcpyAsync(A->d_B + (size_t)b0 * k, h, pitch * (size_t)(b1 - b0), cudaMemcpyHostToDevice, A->stream_up));
+            else
+                SPMM_CUDA(cudaMemcpy2DAsync(A->d_B + (size_t)b0 * k + k0, pitch, h, sizeof(double) * (size_t)B.ld, width,
+                                            (size_t)(b1 - b0), cudaMemcpyHostToDevice, A->stream_up));
+        }
+        else
+        {
+            rc = staged_upload(A, B, A->d_B, b0, b1, k, A->stream_up);
+            if (rc)
+                return rc;
+        }
         SPMM_CUDA(cudaEventRecord(up, A->stream_up));
         SPMM_CUDA(cudaStreamWaitEvent(A->stream, up, 0));
         rc = launch(A->d_B, A->d_C, k0, ks, A->stream);
@@ -359,12 +338,22 @@ int host_multiply(spmm_csr_t A, const HostRows &B, int b0, int b1, int k, const 
             return rc;
         SPMM_CUDA(cudaEventRecord(done, A->stream));
         SPMM_CUDA(cudaStreamWaitEvent(A->stream_down, done, 0));
-        rc = download_rows(A, C, c_direct, A->h_C, A->d_C, c_rows, k, k0, ks, A->stream_down, &pending, &ev);
-        if (rc)
-            return rc;
+        if (c_direct)
+        {
+            if (slabs == 1 && C.ld == k)
+                SPMM_CUDA(cudaMemcpyAsync(C.flat, A->d_C, pitch * (size_t)c_rows, cudaMemcpyDeviceToHost, A->stream_down));
+            else
+                SPMM_CUDA(cudaMemcpy2DAsync(C.flat + k0, sizeof(double) * (size_t)C.ld, A->d_C + k0, pitch, width, (size_t)c_rows,
+                                            cudaMemcpyDeviceToHost, A->stream_down));
+        }
+        else
+        {
+            CopySink cs{C, k};
+            rc = staged_download(A, A->d_C, c_rows, k, A->stream_down, sink ? sink : copy_sink, sink ? sink_ctx : &cs);
+            if (rc)
+                return rc;
+        }
     }
-    if (!c_direct)
-        rc = unpack_pending(C, A->h_C, k, pending);
     cudaError_t e = cudaStreamSynchronize(A->stream_down);
     if (e == cudaSuccess)
         e = cudaStreamSynchronize(A->stream);
@@ -406,7 +395,24 @@ int spmm_multiply_host(spmm_csr_t A, const double *B, int k, double *C, int kern
     HostRowsOut c;
     c.flat = C;
     c.ld = k;
-    return host_multiply(A, b, 0, A->n_cols, k, c, A->n_rows, auto_slabs((nb + nc) * sizeof(double), k),
+    return host_multiply(A, b, 0, A->n_cols, k, c, nullptr, nullptr, A->n_rows, auto_slabs((nb + nc) * sizeof(double), k),
+                         [&](const double *dB, double *dC, int k0, int kc, cudaStream_t s) {
+                             return spmm_multiply_strided_device(A, dB, k, dC, k, k0, kc, kernel, s);
+                         });
+}
+
+int spmm_multiply_host_sink(spmm_csr_t A, const double *const *B_rows, int k, spmm_rows_sink sink, void *ctx, int kernel)
+{
+    SPMM_REQUIRE(A != nullptr, "handle is NULL");
+    SPMM_REQUIRE(k >= 0, "k is negative");
+    const size_t nb = (size_t)A->n_cols * (size_t)k, nc = (size_t)A->n_rows * (size_t)k;
+    if (nc == 0)
+        return SPMM_OK;
+    SPMM_REQUIRE(sink != nullptr && (B_rows != nullptr || nb == 0), "B_rows / sink is NULL");
+    HostRows b;
+    b.rows = B_rows;
+    HostRowsOut none;
+    return host_multiply(A, b, 0, A->n_cols, k, none, sink, ctx, A->n_rows, 1,
                          [&](const double *dB, double *dC, int k0, int kc, cudaStream_t s) {
                              return spmm_multiply_strided_device(A, dB, k, dC, k, k0, kc, kernel, s);
                          });
@@ -424,7 +430,7 @@ int spmm_multiply_host_rows(spmm_csr_t A, const double *const *B_rows, int k, do
     b.rows = B_rows;
     HostRowsOut c;
     c.rows = C_rows;
-    return host_multiply(A, b, 0, A->n_cols, k, c, A->n_rows, auto_slabs((nb + nc) * sizeof(double), k),
+    return host_multiply(A, b, 0, A->n_cols, k, c, nullptr, nullptr, A->n_rows, 1,
                          [&](const double *dB, double *dC, int k0, int kc, cudaStream_t s) {
                              return spmm_multiply_strided_device(A, dB, k, dC, k, k0, kc, kernel, s);
                          });
@@ -446,7 +452,7 @@ int spmm_multiply_rows_host(spmm_csr_t A, int row_begin, int row_end, const doub
     HostRowsOut c;
     c.flat = C_local;
     c.ld = k;
-    return host_multiply(A, b, 0, A->n_cols, k, c, row_end - row_begin, 1,
+    return host_multiply(A, b, 0, A->n_cols, k, c, nullptr, nullptr, row_end - row_begin, 1,
                          [&](const double *dB, double *dC, int, int, cudaStream_t s) {
                              return spmm_multiply_rows_device(A, row_begin, row_end, dB, k, dC, kernel, s);
                          });
@@ -466,7 +472,7 @@ int spmm_multiply_nnz_range_host(spmm_csr_t A, long long nnz_begin, long long nn
     HostRowsOut c;
     c.flat = C_local;
     c.ld = k;
-    return host_multiply(A, b, 0, A->n_cols, k, c, last_row - first_row + 1, 1,
+    return host_multiply(A, b, 0, A->n_cols, k, c, nullptr, nullptr, last_row - first_row + 1, 1,
                          [&](const double *dB, double *dC, int, int, cudaStream_t s) {
                              return spmm_multiply_nnz_range_device(A, nnz_begin, nnz_end, first_row, last_row, dB, k, dC,
                                                                    kernel, s);
@@ -487,13 +493,13 @@ int spmm_stage_b_rows(spmm_csr_t A, const double *const *B_rows, int row_begin, 
     if (!rc)
         rc = ensure_device(&A->d_B, &A->d_B_elems, nb);
     if (!rc && row_end > row_begin)
-        rc = ensure_pinned(&A->h_B, &A->h_B_elems, nb);
+        rc = ensure_ring(A);
     if (rc)
         return rc;
     SPMM_REQUIRE(B_rows != nullptr || row_end == row_begin, "B_rows is NULL");
     HostRows b;
     b.rows = B_rows;
-    rc = upload_rows(b, false, A->h_B, A->d_B, row_begin, row_end, k, 0, k, A->stream);
+    rc = staged_upload(A, b, A->d_B, row_begin, row_end, k, A->stream);
     if (rc)
         return rc;
     *d_B = A->d_B;
@@ -502,29 +508,32 @@ int spmm_stage_b_rows(spmm_csr_t A, const double *const *B_rows, int row_begin, 
     return SPMM_OK;
 }
 
-int spmm_fetch_c_rows(spmm_csr_t A, const double *d_C, int n_rows, int k, double *const *C_rows)
+int spmm_fetch_c_sink(spmm_csr_t A, const double *d_C, int n_rows, int k, spmm_rows_sink sink, void *ctx)
 {
     SPMM_REQUIRE(A != nullptr, "handle is NULL");
     SPMM_REQUIRE(n_rows >= 0 && k >= 0, "negative size");
     if (n_rows == 0 || k == 0)
         return SPMM_OK;
-    SPMM_REQUIRE(d_C != nullptr && C_rows != nullptr, "d_C / C_rows is NULL");
+    SPMM_REQUIRE(d_C != nullptr && sink != nullptr, "d_C / sink is NULL");
     SPMM_CUDA(cudaSetDevice(A->device));
     std::lock_guard<std::mutex> guard(A->host_mu);
     int rc = ensure_streams(A);
     if (!rc)
-        rc = ensure_pinned(&A->h_C, &A->h_C_elems, (size_t)n_rows * (size_t)k);
+        rc = ensure_ring(A);
     if (rc)
         return rc;
-    HostRowsOut c;
-    c.rows = C_rows;
-    std::vector<Pending> pending;
-    size_t ev = 0;
-    rc = download_rows(A, c, false, A->h_C, d_C, n_rows, k, 0, k, A->stream_down, &pending, &ev);
-    if (!rc)
-        rc = unpack_pending(c, A->h_C, k, pending);
+    rc = staged_download(A, d_C, n_rows, k, A->stream_down, sink, ctx);
     SPMM_CUDA(cudaStreamSynchronize(A->stream_down));
     return rc;
+}
+
+int spmm_fetch_c_rows(spmm_csr_t A, const double *d_C, int n_rows, int k, double *const *C_rows)
+{
+    SPMM_REQUIRE(C_rows != nullptr || n_rows == 0 || k == 0, "C_rows is NULL");
+    HostRowsOut c;
+    c.rows = C_rows;
+    CopySink cs{c, k};
+    return spmm_fetch_c_sink(A, d_C, n_rows, k, copy_sink, &cs);
 }
 
 int spmm_upload_dense(spmm_csr_t A, const double *src, long long n_rows, int k, double *d_dst, void *stream)
@@ -536,20 +545,22 @@ int spmm_upload_dense(spmm_csr_t A, const double *src, long long n_rows, int k, 
     SPMM_REQUIRE(src != nullptr && d_dst != nullptr, "src / d_dst is NULL");
     SPMM_CUDA(cudaSetDevice(A->device));
     std::lock_guard<std::mutex> guard(A->host_mu);
-    HostRows b;
-    b.flat = src;
-    b.ld = k;
-    const bool direct = is_pinned(src);
-    if (!direct)
+    if (is_pinned(src))
+        SPMM_CUDA(cudaMemcpyAsync(d_dst, src, sizeof(double) * (size_t)n_rows * (size_t)k, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    else
     {
-        const int rc = ensure_pinned(&A->h_B, &A->h_B_elems, (size_t)n_rows * (size_t)k);
+        int rc = ensure_streams(A);
+        if (!rc)
+            rc = ensure_ring(A);
+        HostRows b;
+        b.flat = src;
+        b.ld = k;
+        if (!rc)
+            rc = staged_upload(A, b, d_dst, 0, (int)n_rows, k, (cudaStream_t)stream);
         if (rc)
             return rc;
     }
-    const int rc = upload_rows(b, direct, A->h_B, d_dst, 0, (int)n_rows, k, 0, k, (cudaStream_t)stream);
-    if (rc)
-        return rc;
-    SPMM_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); // the staging mirror is free again on return
+    SPMM_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); // the staging ring is free again on return
     return SPMM_OK;
 }
 
@@ -562,21 +573,21 @@ int spmm_download_dense(spmm_csr_t A, const double *d_src, long long n_rows, int
     SPMM_REQUIRE(d_src != nullptr && dst != nullptr, "d_src / dst is NULL");
     SPMM_CUDA(cudaSetDevice(A->device));
     std::lock_guard<std::mutex> guard(A->host_mu);
-    HostRowsOut c;
-    c.flat = dst;
-    c.ld = k;
-    const bool direct = is_pinned(dst);
-    if (!direct)
+    int rc = SPMM_OK;
+    if (is_pinned(dst))
+        SPMM_CUDA(cudaMemcpyAsync(dst, d_src, sizeof(double) * (size_t)n_rows * (size_t)k, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    else
     {
-        const int rc = ensure_pinned(&A->h_C, &A->h_C_elems, (size_t)n_rows * (size_t)k);
-        if (rc)
-            return rc;
+        rc = ensure_streams(A);
+        if (!rc)
+            rc = ensure_ring(A);
+        HostRowsOut c;
+        c.flat = dst;
+        c.ld = k;
+        CopySink cs{c, k};
+        if (!rc)
+            rc = staged_download(A, d_src, (int)n_rows, k, (cudaStream_t)stream, copy_sink, &cs);
     }
-    std::vector<Pending> pending;
-    size_t ev = 0;
-    int rc = download_rows(A, c, direct, A->h_C, d_src, (int)n_rows, k, 0, k, (cudaStream_t)stream, &pending, &ev);
-    if (!rc && !direct)
-        rc = unpack_pending(c, A->h_C, k, pending);
     SPMM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return rc;
 }

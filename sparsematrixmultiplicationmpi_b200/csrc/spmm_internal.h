@@ -70,6 +70,7 @@ struct Tuning
     int tiled_ksplit = 0;   // build: CTAs that share one chunk, each taking a group of k-tiles (0/1 none)
     int tiled_npw = 0;      // launch: producer warps (4, 8)
     int host_slabs = 0;     // host-buffer multiply: k-slabs in the PCIe pipeline (0 auto, 1 none)
+    int tiled_auto_after = 1; // AUTO builds the tile layout on the multiply after this many whole-matrix multiplies of a handle
     int tiled_pdl = 1;      // launch: programmatic dependent launch of the tiled kernel (0 off)
     int tiled_group = 0;    // build: tiles one far-band apart walked in turn, this many bands per group (0 auto = 2, 1 off)
     int tiled_stride = 0;   // build: far-band distance in rows (0 = detect from the matrix)
@@ -102,8 +103,7 @@ struct spmm_csr_s
     spmm::Schedule sched;
     // staging of the host-buffer entry points (spmm_host.cu): pinned mirrors of B and C, their device images, streams
     std::mutex host_mu; // one host-buffer call per handle at a time
-    double *h_B = nullptr, *h_C = nullptr;
-    size_t h_B_elems = 0, h_C_elems = 0;
+    double *h_ring = nullptr; // pinned staging ring (a few 2 MB chunks per direction)
     double *d_B = nullptr, *d_C = nullptr;
     size_t d_B_elems = 0, d_C_elems = 0;
     cudaStream_t stream = nullptr; // compute
@@ -112,6 +112,7 @@ struct spmm_csr_s
     // B-staged row tiles (spmm_tiled.cu), optional
     int tl_T = 0, tl_BR = 0, tl_tiles = 0, tl_NS = 0, tl_POOL = 0, tl_max_recs = 0, tl_max_blob = 0, tl_chunk = 0, tl_kt = 0, tl_depth = 0, tl_drains = 0, tl_ksplit = 0;
     long long tl_box_rows_loaded = 0, tl_single_rows = 0; // B rows staged per pass over the matrix
+    int auto_calls = 0;                                   // whole-matrix AUTO multiplies seen before the lazy build
     bool tl_tried = false;                                // AUTO already attempted the lazy build
     bool tl_auto = false;                                 // the layout was built by AUTO (it may rebuild it for another k)
     unsigned char *d_tblob = nullptr;
@@ -119,6 +120,7 @@ struct spmm_csr_s
     int *d_tsingles = nullptr;
     int *d_torder = nullptr;          // walking order of the tiles (nullptr: as they lie)
     int tl_stride = 0, tl_group = 0;  // detected far-band distance in rows, planes interleaved per super-group
+    int tl_gw = 0, tl_hdr_bytes = 0, tl_rowtab_off = 0; // gather-window layout (host-built): single B rows in an LRU window, per-tile row table
     // precomputed CTA cuts per (kind, grid size): kind 0 = rows of the CSR
     mutable std::map<long long, int *> bounds;
     // merge-path scratch (carry rows), grown on demand

@@ -650,7 +650,10 @@ struct TiledArgs
     double *C;
     long long ldb, ldc;
     int n_tiles, n_chunks /* shares: chunks x ksplit */, ksplit, tiles_per_chunk, T, BR, NS, POOL, kc, nkt, depth, prefetch;
-    unsigned hdr_bytes;   // header + unit table bytes of a blob
+    unsigned hdr_bytes;   // header + unit table (+ row table) bytes of a blob
+    unsigned rowtab_off;  // gather-window layouts: offset of the tile's row table (global row id of local row i) in the blob; 0 = none
+    int gw;               // gather-window layout: no boxes; every staged B row travels in a group of 4 (gather4) whose window slot is loads[].y
+    int sg_stride;        // ints per tile in the singles array
     unsigned blob_stride; // bytes reserved per blob buffer in smem
     unsigned slab_off;    // offset of the slab (window slots, then the singles pool) from the aligned smem base
 };
@@ -664,6 +667,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
                                                                          const __grid_constant__ CUtensorMap row_map)
 {
     constexpr int NL = KT / (2 * TL); // LDS.128 per lane and record
+    constexpr int NLC = NL < 4 ? NL : 4; // ... issued this many at a time
     static_assert(NL >= 1 && NL * 2 * TL == KT, "a team of TL lanes covers the k-tile with NL 16-byte accesses per lane");
     // (NL = 1, the 8-column k-tile for k <= 8: the two teams of a quarter-warp read 64-byte slab rows that share their banks
     // when the rows have the same parity — 1.5 wavefronts per quarter-warp on average instead of the 2 a half-empty 16-column
@@ -747,7 +751,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
             Meta m;
             m.d = a.tdesc[x.t];
             m.ld = a.loads[(size_t)x.t * a.NS + min(pw + NPW * lane, a.NS - 1)];
-            m.sg = reinterpret_cast<const int4 *>(a.singles + (size_t)x.t * a.POOL)[min(pw + NPW * lane, a.POOL / 4 - 1)];
+            m.sg = reinterpret_cast<const int4 *>(a.singles + (size_t)x.t * a.sg_stride)[min(pw + NPW * lane, a.sg_stride / 4 - 1)];
             return m;
         };
         long long p_wait = 0, p_issue = 0, p_sgl = 0, p_items = 0, p_t0 = TCLK();
@@ -817,11 +821,20 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
             const unsigned pool = s_slab + (unsigned)(a.NS * a.BR) * (KT * 8);
             for (int g = pw + NPW * lane; !T_NO_STAGE && g * 4 < n_singles; g += NPW * 32)
             {
-                const int4 rows = g == pw + NPW * lane
-                                      ? m.sg
-                                      : reinterpret_cast<const int4 *>(a.singles + (size_t)cur.t * a.POOL)[g]; // > 512 singles
-                const int pr = (m.d.pool_start + g * 4) % a.POOL;
-                tma_gather4(pool + (unsigned)pr * (KT * 8), &row_map, k0, rows, bar);
+                const bool mine = g == pw + NPW * lane;
+                const int4 rows = mine ? m.sg
+                                       : reinterpret_cast<const int4 *>(a.singles + (size_t)cur.t * a.sg_stride)[g]; // > 512 singles
+                if (a.gw)
+                {
+                    // gather-window layout: the group lands in the window slot the builder chose (least recently used)
+                    const int slot = mine ? m.ld.y : a.loads[(size_t)cur.t * a.NS + g].y;
+                    tma_gather4(s_slab + (unsigned)slot * (4u * KT * 8u), &row_map, k0, rows, bar);
+                }
+                else
+                {
+                    const int pr = (m.d.pool_start + g * 4) % a.POOL;
+                    tma_gather4(pool + (unsigned)pr * (KT * 8), &row_map, k0, rows, bar);
+                }
             }
             work_next(cur);
             ++w;
@@ -889,7 +902,8 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
         const int n_units = hdr.y;
         const unsigned units = blob + 16;
         const unsigned vals_s = blob + a.hdr_bytes, ids_s = blob + (unsigned)hdr.w;
-        double *__restrict__ Ck = a.C + (long long)hdr.z * a.T * a.ldc + k0; // hdr.z: the tile at this place of the walking order
+        double *__restrict__ Ck = a.C + (a.rowtab_off ? 0ll : (long long)hdr.z * a.T * a.ldc) + k0; // hdr.z: the tile at this place of the walking order
+        const unsigned rowtab = blob + a.rowtab_off; // gather-window layouts: the tile's rows are named one by one
 
         // units round-robin over the warps, rotated by the item so the remainder moves around
         for (int u = (warp + w) % NCW; !T_NO_COMPUTE && u < n_units; u += NCW)
@@ -897,6 +911,13 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
             const uint2 e = lds64u(units + (u * UW + tw) * 8);
             const int begin = e.x & 0x1FFF, len = (e.x >> 13) & 0x3FF, row = (e.x >> 23) & 0xFF;
             const bool split = (e.x >> 31) != 0;
+            long long crow = row; // row of C (relative to Ck)
+            if (a.rowtab_off && row != (int)UE_PAD_ROW)
+            {
+                int gr;
+                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(gr) : "r"(rowtab + (unsigned)row * 4u));
+                crow = gr;
+            }
             const int maxlen = __reduce_max_sync(0xFFFFFFFFu, len);
             double2 acc[NL];
 #pragma unroll
@@ -928,23 +949,29 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
 #pragma unroll
                     for (int q = 0; q < U; ++q)
                         v[q] = lds64d(vbase + (i + q) * 8);
-                    double2 b[U][NL];
+                    // (a k-tile of 64 columns = 8 accesses per lane and record: taken four at a time so that U records in flight
+                    // stay within the register file)
 #pragma unroll
-                    for (int q = 0; q < U; ++q)
+                    for (int xc = 0; xc < NL; xc += NLC)
                     {
-                        const unsigned a0 = b0 + id[q] * (KT * 8), a1 = a0 ^ 64u;
+                        double2 b[U][NLC];
 #pragma unroll
-                        for (int x = 0; x < NL; ++x)
-                            b[q][x] = lds128d(((x & 1) ? a1 : a0) + (x >> 1) * 128);
-                    }
-#pragma unroll
-                    for (int q = 0; q < U; ++q)
-#pragma unroll
-                        for (int x = 0; x < NL; ++x)
+                        for (int q = 0; q < U; ++q)
                         {
-                            acc[x].x = fma(v[q], b[q][x].x, acc[x].x);
-                            acc[x].y = fma(v[q], b[q][x].y, acc[x].y);
+                            const unsigned a0 = b0 + id[q] * (KT * 8), a1 = a0 ^ 64u;
+#pragma unroll
+                            for (int x = 0; x < NLC; ++x)
+                                b[q][x] = lds128d((((xc + x) & 1) ? a1 : a0) + ((xc + x) >> 1) * 128);
                         }
+#pragma unroll
+                        for (int q = 0; q < U; ++q)
+#pragma unroll
+                            for (int x = 0; x < NLC; ++x)
+                            {
+                                acc[xc + x].x = fma(v[q], b[q][x].x, acc[xc + x].x);
+                                acc[xc + x].y = fma(v[q], b[q][x].y, acc[xc + x].y);
+                            }
+                    }
                 }
             }
             for (; i < maxlen; i += U)
@@ -970,24 +997,28 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
                     if (i + q < len)
                         v[q] = lds64d(vbase + (i + q) * 8);
                 }
-                double2 b[U][NL];
 #pragma unroll
-                for (int q = 0; q < U; ++q)
-#pragma unroll
-                    for (int x = 0; x < NL; ++x)
-                    {
-                        b[q][x] = make_double2(0.0, 0.0);
-                        if (i + q < len)
-                            b[q][x] = lds128d(s_slab + id[q] * (KT * 8) + colo[x] * 8);
-                    }
-#pragma unroll
-                for (int q = 0; q < U; ++q)
+                for (int xc = 0; xc < NL; xc += NLC)
                 {
+                    double2 b[U][NLC];
 #pragma unroll
-                    for (int x = 0; x < NL; ++x)
+                    for (int q = 0; q < U; ++q)
+#pragma unroll
+                        for (int x = 0; x < NLC; ++x)
+                        {
+                            b[q][x] = make_double2(0.0, 0.0);
+                            if (i + q < len)
+                                b[q][x] = lds128d(s_slab + id[q] * (KT * 8) + colo[xc + x] * 8);
+                        }
+#pragma unroll
+                    for (int q = 0; q < U; ++q)
                     {
-                        acc[x].x = fma(v[q], b[q][x].x, acc[x].x);
-                        acc[x].y = fma(v[q], b[q][x].y, acc[x].y);
+#pragma unroll
+                        for (int x = 0; x < NLC; ++x)
+                        {
+                            acc[xc + x].x = fma(v[q], b[q][x].x, acc[xc + x].x);
+                            acc[xc + x].y = fma(v[q], b[q][x].y, acc[xc + x].y);
+                        }
                     }
                 }
             }
@@ -1009,7 +1040,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
                     }
                 if (tw == 0 && row != (int)UE_PAD_ROW)
                 {
-                    double *cr = Ck + (long long)row * a.ldc;
+                    double *cr = Ck + crow * a.ldc;
 #pragma unroll
                     for (int x = 0; x < NL; ++x)
                         if (k0 + (x * TL + l) * 2 < a.kc)
@@ -1022,7 +1053,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
             }
             else if (row != (int)UE_PAD_ROW)
             {
-                double *cr = Ck + (long long)row * a.ldc;
+                double *cr = Ck + crow * a.ldc;
 #pragma unroll
                 for (int x = 0; x < NL; ++x)
                     if (k0 + colo[x] < a.kc)
@@ -1173,7 +1204,10 @@ int launch_tiled_t(const spmm_csr_s *A, const double *d_B, long long ldb, double
     a.nkt = (kc + KT - 1) / KT;
     a.depth = A->tl_depth;
     a.prefetch = tuning().tiled_prefetch >= 0 ? tuning().tiled_prefetch : 0;
-    a.hdr_bytes = hdr_bytes_of(A->tl_T);
+    a.hdr_bytes = A->tl_hdr_bytes ? (unsigned)A->tl_hdr_bytes : hdr_bytes_of(A->tl_T);
+    a.rowtab_off = (unsigned)A->tl_rowtab_off;
+    a.gw = A->tl_gw;
+    a.sg_stride = A->tl_gw ? A->tl_NS * 4 : A->tl_POOL;
     a.blob_stride = (unsigned)m.blob_stride;
     a.slab_off = (unsigned)m.slab_off;
     const int grid = std::max(1, std::min(a.n_chunks, device_props(A->device).sm_count));
@@ -1378,6 +1412,7 @@ void free_tiles(spmm_csr_s *A)
     A->d_tsingles = nullptr;
     A->tl_T = A->tl_BR = A->tl_tiles = A->tl_NS = A->tl_POOL = A->tl_max_recs = A->tl_max_blob = A->tl_chunk = A->tl_kt = A->tl_depth = A->tl_ksplit = 0;
     A->tl_box_rows_loaded = A->tl_single_rows = 0;
+    A->tl_gw = A->tl_hdr_bytes = A->tl_rowtab_off = 0;
 }
 
 bool tiled_shape_ok(const spmm_csr_s *A, const double *d_B, long long ldb, const double *d_C, long long ldc, int kc)
@@ -1393,7 +1428,7 @@ int launch_tiled(const spmm_csr_s *A, const double *d_B, long long ldb, double *
     const Tuning &t = tuning();
     note_kernel("spmm_tiled_kernel");
     const int kt = t.tiled_kt > 0 ? t.tiled_kt : A->tl_kt;
-    const int ncw = t.tiled_ncw > 0 ? t.tiled_ncw : 16;
+    const int ncw = t.tiled_ncw > 0 ? t.tiled_ncw : (kt == 64 ? 8 : 16);
     const int u = t.tiled_unroll > 0 ? t.tiled_unroll : 4;
     const int npw = t.tiled_npw == 8 ? 8 : 4;
     if (kt == 8)
@@ -1411,7 +1446,21 @@ int launch_tiled(const spmm_csr_s *A, const double *d_B, long long ldb, double *
         return launch_tiled_ncw<16>(A, ncw, u, npw, d_B, ldb, d_C, ldc, kc, stream, x);
     if (kt == 32)
         return launch_tiled_ncw<32>(A, ncw, u, npw, d_B, ldb, d_C, ldc, kc, stream, x);
-    set_error("tiled kernel: k-tile must be 8, 16 or 32");
+    if (kt == 64)
+    {
+        // 64-column k-tile (gather-window layouts): 16 accumulators per lane, fewer consumer warps within the register file
+        if ((ncw == 8 || ncw == 0) && u == 4 && npw == 4)
+            return launch_tiled_t<64, 8, 4, 4>(A, d_B, ldb, d_C, ldc, kc, stream, x);
+        if (ncw == 12 && u == 4 && npw == 4)
+            return launch_tiled_t<64, 12, 4, 4>(A, d_B, ldb, d_C, ldc, kc, stream, x);
+        if (ncw == 8 && u == 4 && npw == 8)
+            return launch_tiled_t<64, 8, 4, 8>(A, d_B, ldb, d_C, ldc, kc, stream, x);
+        if (ncw == 4 && u == 4 && npw == 4)
+            return launch_tiled_t<64, 4, 4, 4>(A, d_B, ldb, d_C, ldc, kc, stream, x);
+        set_error("tiled kernel: the 64-column k-tile goes with 4, 8 or 12 consumer warps, unroll 4");
+        return SPMM_ERR_INVALID;
+    }
+    set_error("tiled kernel: k-tile must be 8, 16, 32 or 64");
     return SPMM_ERR_INVALID;
 }
 

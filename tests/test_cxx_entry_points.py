@@ -60,7 +60,7 @@ def entry_lib():
     lib = C.CDLL(os.path.join(PKG, "libspmm_entry.so"))
     lib.spmm_entry_run.restype = C.c_int
     lib.spmm_entry_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
-                                   C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                   C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                    C.c_char_p, C.c_int]
     return lib
 
@@ -74,7 +74,7 @@ def entry_run(strategy, P, rp, ci, va, n_cols, B, k, steps=0):
     first, mean = C.c_double(), C.c_double()
     err = C.create_string_buffer(512)
     rc = lib.spmm_entry_run(strategy, P, n, n_cols, len(va), rp.ctypes.data, ci.ctypes.data, va.ctypes.data, k,
-                            B.ctypes.data, out.ctypes.data, steps, C.byref(first), C.byref(mean), err, 512)
+                            B.ctypes.data, out.ctypes.data, 1 if steps else 0, steps, C.byref(first), C.byref(mean), err, 512)
     if rc:
         raise RuntimeError(err.value.decode() or f"spmm_entry_run status {rc}")
     return out, first.value, mean.value
