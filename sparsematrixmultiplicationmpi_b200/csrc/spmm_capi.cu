@@ -260,6 +260,7 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "tiled.group") t.tiled_group = value;
     else if (k == "tiled.pdl") t.tiled_pdl = value;
     else if (k == "tiled.auto_after") t.tiled_auto_after = value;
+    else if (k == "tiled.gw") t.tiled_gw = value;
     else if (k == "tiled.stride") t.tiled_stride = value;
     else if (k == "stream") t.stream = value;
     else if (k == "stream.tile") t.stream_tile = value;
@@ -369,8 +370,6 @@ int spmm_csr_destroy(spmm_csr_t A)
     cudaFree(A->d_C);
     cudaFree(A->d_carry);
     cudaFree(A->d_carry_row);
-    if (A->h_ring)
-        cudaFreeHost(A->h_ring);
     if (A->stream)
         cudaStreamDestroy(A->stream);
     if (A->stream_up)

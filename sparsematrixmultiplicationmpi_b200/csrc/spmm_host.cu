@@ -135,6 +135,11 @@ Pool &pool()
     return p;
 }
 
+} // namespace
+void host_parallel_for(int n, const std::function<void(int)> &fn) { pool().parallel_for(n, fn); }
+namespace
+{
+
 // A dense host operand: either N row pointers (the memory shape of a FatVector) or one flat row-major block.
 struct HostRows
 {
@@ -164,8 +169,9 @@ bool is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
-constexpr size_t CHUNK_BYTES = 2u << 20; // pipeline chunk: about 2 MB of rows
-constexpr int RING_SLOTS = 6;            // chunks in flight per direction (pinned staging ring: 2 x 6 x 2 MB per handle)
+constexpr size_t CHUNK_BYTES = 1u << 20; // pipeline chunk: about 1 MB of rows, packed / unpacked by one host thread
+constexpr int RING_WORKERS = 8;          // host threads that pack / unpack side by side, two ring slots each
+constexpr int RING_SLOTS = 2 * RING_WORKERS;
 
 int ensure_device(double **buf, size_t *have, size_t want)
 {
@@ -188,7 +194,7 @@ int ensure_streams(spmm_csr_t A)
         SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_up, cudaStreamNonBlocking));
         SPMM_CUDA(cudaStreamCreateWithFlags(&A->stream_down, cudaStreamNonBlocking));
     }
-    while (A->events.size() < 2 * RING_SLOTS + 16)
+    while (A->events.size() < 16)
     {
         cudaEvent_t e;
         SPMM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -197,77 +203,133 @@ int ensure_streams(spmm_csr_t A)
     return SPMM_OK;
 }
 
-// Pinned staging ring of the handle: RING_SLOTS chunks per direction. A small ring instead of full mirrors of B and C keeps
-// the first call on a new matrix cheap (page-locking 124 MB costs tens of milliseconds; the reference calls each function once).
-int ensure_ring(spmm_csr_t A)
+// Pinned staging rings: RING_SLOTS chunks per direction, with one event per slot. A small ring instead of full mirrors of B
+// and C keeps the first call on a new matrix cheap (page-locking 124 MB costs tens of milliseconds; the reference calls each
+// function once per run), and the rings outlive the handles: a ring is borrowed for the duration of one host-buffer call and
+// goes back to its device's free list, so main()'s four functions (four shards per rank) page-lock once.
+struct Ring
 {
-    if (A->h_ring)
-        return SPMM_OK;
-    SPMM_CUDA(cudaHostAlloc((void **)&A->h_ring, 2 * RING_SLOTS * CHUNK_BYTES, cudaHostAllocDefault));
+    int device = 0;
+    double *buf = nullptr;
+    cudaEvent_t ev[2 * RING_SLOTS] = {};
+    double *slot(int dir, int i) const { return buf + ((size_t)(dir * RING_SLOTS + i) * CHUNK_BYTES) / sizeof(double); }
+    cudaEvent_t event(int dir, int i) const { return ev[dir * RING_SLOTS + i]; }
+};
+std::mutex g_ring_mu;
+std::vector<Ring *> g_rings_free;
+
+int borrow_ring(int device, Ring **out)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_ring_mu);
+        for (size_t i = 0; i < g_rings_free.size(); ++i)
+            if (g_rings_free[i]->device == device)
+            {
+                *out = g_rings_free[i];
+                g_rings_free.erase(g_rings_free.begin() + (long)i);
+                return SPMM_OK;
+            }
+    }
+    Ring *r = new Ring();
+    r->device = device;
+    cudaError_t e = cudaHostAlloc((void **)&r->buf, 2 * RING_SLOTS * CHUNK_BYTES, cudaHostAllocDefault);
+    for (int i = 0; e == cudaSuccess && i < 2 * RING_SLOTS; ++i)
+        e = cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming);
+    if (e != cudaSuccess)
+    {
+        if (r->buf)
+            cudaFreeHost(r->buf);
+        delete r;
+        return cuda_fail(e, "pinned staging ring", __FILE__, __LINE__);
+    }
+    *out = r;
     return SPMM_OK;
 }
-double *ring_slot(spmm_csr_t A, int dir, int slot) { return A->h_ring + ((size_t)(dir * RING_SLOTS + slot) * CHUNK_BYTES) / sizeof(double); }
-cudaEvent_t ring_event(spmm_csr_t A, int dir, int slot) { return A->events[16 + dir * RING_SLOTS + slot]; }
+void return_ring(Ring *r)
+{
+    if (!r)
+        return;
+    std::lock_guard<std::mutex> lk(g_ring_mu);
+    g_rings_free.push_back(r);
+}
+struct RingLease
+{
+    Ring *r = nullptr;
+    ~RingLease() { return_ring(r); }
+};
 
 int rows_per_chunk(int k) { return (int)std::max<size_t>(1, CHUNK_BYTES / (sizeof(double) * (size_t)std::max(k, 1))); }
 
-// Rows [r0, r1) of `src` (all k columns) -> the device image d (row r at d + r*k), enqueued on `s`: packed chunk by chunk into
-// the ring by the pool while the copy engine moves the chunks already packed (serialize(), utils.cpp:216-228, pipelined).
-int staged_upload(spmm_csr_t A, const HostRows &src, double *d, int r0, int r1, int k, cudaStream_t s)
+// Rows [r0, r1) of `src` (all k columns) -> the device image d (row r at d + r*k), enqueued on `s`. RING_WORKERS host threads
+// each take every RING_WORKERS-th chunk: pack it into one of their two ring slots (serialize(), utils.cpp:216-228), hand it
+// to the copy engine, go on packing the next while it travels.
+int staged_upload(const Ring &ring, int device, const HostRows &src, double *d, int r0, int r1, int k, cudaStream_t s)
 {
     if (r1 <= r0 || k <= 0)
         return SPMM_OK;
-    const int rpc = rows_per_chunk(k);
+    const int rpc = rows_per_chunk(k), n_chunks = (r1 - r0 + rpc - 1) / rpc;
     const size_t width = sizeof(double) * (size_t)k;
-    const int sub = std::max(8, rpc / (2 * pool().threads())); // rows per pool task
-    int used = 0;
-    for (int c0 = r0; c0 < r1; c0 += rpc, ++used)
-    {
-        const int c1 = std::min(r1, c0 + rpc), slot = used % RING_SLOTS;
-        if (used >= RING_SLOTS)
-            SPMM_CUDA(cudaEventSynchronize(ring_event(A, 0, slot))); // the chunk that used this slot has left the host
-        double *stage = ring_slot(A, 0, slot);
-        pool().parallel_for((c1 - c0 + sub - 1) / sub, [&](int t) {
-            const int a = c0 + t * sub, b = std::min(c1, a + sub);
-            for (int r = a; r < b; ++r)
+    const int W = std::max(1, std::min({RING_WORKERS, pool().threads(), n_chunks}));
+    std::atomic<int> err{(int)cudaSuccess};
+    pool().parallel_for(W, [&](int w) {
+        cudaError_t e = cudaSetDevice(device);
+        for (int i = 0, c = w; c < n_chunks && e == cudaSuccess; c += W, ++i)
+        {
+            const int c0 = r0 + c * rpc, c1 = std::min(r1, c0 + rpc), slot = 2 * w + (i & 1);
+            if (i >= 2)
+                e = cudaEventSynchronize(ring.event(0, slot)); // the chunk that used this slot has left the host
+            double *stage = ring.slot(0, slot);
+            for (int r = c0; r < c1; ++r)
                 std::memcpy(stage + (size_t)(r - c0) * k, src.at(r), width);
-        });
-        SPMM_CUDA(cudaMemcpyAsync(d + (size_t)c0 * k, stage, width * (size_t)(c1 - c0), cudaMemcpyHostToDevice, s));
-        SPMM_CUDA(cudaEventRecord(ring_event(A, 0, slot), s));
-    }
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(d + (size_t)c0 * k, stage, width * (size_t)(c1 - c0), cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess)
+                e = cudaEventRecord(ring.event(0, slot), s);
+        }
+        if (e != cudaSuccess)
+            err = (int)e;
+    });
+    SPMM_CUDA((cudaError_t)err.load());
     return SPMM_OK;
 }
 
 // n rows x k at d_c -> sink(row_begin, row_end, rows, ctx) chunk by chunk as they arrive (`rows` = row_begin's first double,
-// leading dimension k); the sink runs on the pool threads over disjoint row ranges (deserialize(), utils.cpp:237-253).
+// leading dimension k); the sink runs on the host threads over disjoint row ranges (deserialize(), utils.cpp:237-253).
+// Worker w owns chunks w, w+W, ...: its first two downloads are enqueued up front, each further one as soon as the slot it
+// lands in has been handed to the sink.
 typedef void (*RowsSink)(int, int, const double *, void *);
-int staged_download(spmm_csr_t A, const double *d_c, int n, int k, cudaStream_t s, RowsSink sink, void *ctx)
+int staged_download(const Ring &ring, int device, const double *d_c, int n, int k, cudaStream_t s, RowsSink sink, void *ctx)
 {
     if (n <= 0 || k <= 0)
         return SPMM_OK;
-    const int rpc = rows_per_chunk(k);
+    const int rpc = rows_per_chunk(k), n_chunks = (n + rpc - 1) / rpc;
     const size_t width = sizeof(double) * (size_t)k;
-    const int n_chunks = (n + rpc - 1) / rpc;
-    const int sub = std::max(8, rpc / (2 * pool().threads()));
-    auto issue = [&](int c) -> cudaError_t {
-        const int c0 = c * rpc, c1 = std::min(n, c0 + rpc), slot = c % RING_SLOTS;
-        cudaError_t e = cudaMemcpyAsync(ring_slot(A, 1, slot), d_c + (size_t)c0 * k, width * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, s);
-        return e == cudaSuccess ? cudaEventRecord(ring_event(A, 1, slot), s) : e;
+    const int W = std::max(1, std::min({RING_WORKERS, pool().threads(), n_chunks}));
+    auto issue = [&](int c, int slot) -> cudaError_t {
+        const int c0 = c * rpc, c1 = std::min(n, c0 + rpc);
+        cudaError_t e = cudaMemcpyAsync(ring.slot(1, slot), d_c + (size_t)c0 * k, width * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, s);
+        return e == cudaSuccess ? cudaEventRecord(ring.event(1, slot), s) : e;
     };
-    for (int c = 0; c < std::min(n_chunks, RING_SLOTS); ++c)
-        SPMM_CUDA(issue(c));
-    for (int c = 0; c < n_chunks; ++c)
-    {
-        const int c0 = c * rpc, c1 = std::min(n, c0 + rpc), slot = c % RING_SLOTS;
-        SPMM_CUDA(cudaEventSynchronize(ring_event(A, 1, slot)));
-        const double *stage = ring_slot(A, 1, slot);
-        pool().parallel_for((c1 - c0 + sub - 1) / sub, [&](int t) {
-            const int a = c0 + t * sub, b = std::min(c1, a + sub);
-            sink(a, b, stage + (size_t)(a - c0) * k, ctx);
-        });
-        if (c + RING_SLOTS < n_chunks)
-            SPMM_CUDA(issue(c + RING_SLOTS));
-    }
+    // in chunk order, so that the first chunks arrive first
+    for (int c = 0; c < std::min(n_chunks, 2 * W); ++c)
+        SPMM_CUDA(issue(c, 2 * (c % W) + ((c / W) & 1)));
+    std::atomic<int> err{(int)cudaSuccess};
+    pool().parallel_for(W, [&](int w) {
+        cudaError_t e = cudaSetDevice(device);
+        for (int i = 0, c = w; c < n_chunks && e == cudaSuccess; c += W, ++i)
+        {
+            const int c0 = c * rpc, c1 = std::min(n, c0 + rpc), slot = 2 * w + (i & 1);
+            e = cudaEventSynchronize(ring.event(1, slot));
+            if (e != cudaSuccess)
+                break;
+            sink(c0, c1, ring.slot(1, slot), ctx);
+            if (c + 2 * W < n_chunks)
+                e = issue(c + 2 * W, slot);
+        }
+        if (e != cudaSuccess)
+            err = (int)e;
+    });
+    SPMM_CUDA((cudaError_t)err.load());
     return SPMM_OK;
 }
 
@@ -301,8 +363,9 @@ int host_multiply(spmm_csr_t A, const HostRows &B, int b0, int b1, int k, const 
     if (!rc)
         rc = ensure_device(&A->d_C, &A->d_C_elems, nc);
     const bool b_direct = !B.rows && is_pinned(B.flat), c_direct = !sink && !C.rows && is_pinned(C.flat);
+    RingLease lease;
     if (!rc && !(b_direct && c_direct))
-        rc = ensure_ring(A);
+        rc = borrow_ring(A->device, &lease.r);
     if (rc)
         return rc;
     if (!(b_direct && c_direct))
@@ -327,7 +390,7 @@ int host_multiply(spmm_csr_t A, const HostRows &B, int b0, int b1, int k, const 
         }
         else
         {
-            rc = staged_upload(A, B, A->d_B, b0, b1, k, A->stream_up);
+            rc = staged_upload(*lease.r, A->device, B, A->d_B, b0, b1, k, A->stream_up);
             if (rc)
                 return rc;
         }
@@ -349,7 +412,7 @@ int host_multiply(spmm_csr_t A, const HostRows &B, int b0, int b1, int k, const 
         else
         {
             CopySink cs{C, k};
-            rc = staged_download(A, A->d_C, c_rows, k, A->stream_down, sink ? sink : copy_sink, sink ? sink_ctx : &cs);
+            rc = staged_download(*lease.r, A->device, A->d_C, c_rows, k, A->stream_down, sink ? sink : copy_sink, sink ? sink_ctx : &cs);
             if (rc)
                 return rc;
         }
@@ -492,16 +555,21 @@ int spmm_stage_b_rows(spmm_csr_t A, const double *const *B_rows, int row_begin, 
     int rc = ensure_streams(A);
     if (!rc)
         rc = ensure_device(&A->d_B, &A->d_B_elems, nb);
+    RingLease lease;
     if (!rc && row_end > row_begin)
-        rc = ensure_ring(A);
+        rc = borrow_ring(A->device, &lease.r);
     if (rc)
         return rc;
     SPMM_REQUIRE(B_rows != nullptr || row_end == row_begin, "B_rows is NULL");
     HostRows b;
     b.rows = B_rows;
-    rc = staged_upload(A, b, A->d_B, row_begin, row_end, k, A->stream);
-    if (rc)
-        return rc;
+    if (row_end > row_begin)
+    {
+        rc = staged_upload(*lease.r, A->device, b, A->d_B, row_begin, row_end, k, A->stream);
+        if (rc)
+            return rc;
+        SPMM_CUDA(cudaStreamSynchronize(A->stream)); // the ring goes back to the free list: its chunks must have left the host
+    }
     *d_B = A->d_B;
     if (stream)
         *stream = (void *)A->stream;
@@ -517,12 +585,13 @@ int spmm_fetch_c_sink(spmm_csr_t A, const double *d_C, int n_rows, int k, spmm_r
     SPMM_REQUIRE(d_C != nullptr && sink != nullptr, "d_C / sink is NULL");
     SPMM_CUDA(cudaSetDevice(A->device));
     std::lock_guard<std::mutex> guard(A->host_mu);
+    RingLease lease;
     int rc = ensure_streams(A);
     if (!rc)
-        rc = ensure_ring(A);
+        rc = borrow_ring(A->device, &lease.r);
     if (rc)
         return rc;
-    rc = staged_download(A, d_C, n_rows, k, A->stream_down, sink, ctx);
+    rc = staged_download(*lease.r, A->device, d_C, n_rows, k, A->stream_down, sink, ctx);
     SPMM_CUDA(cudaStreamSynchronize(A->stream_down));
     return rc;
 }
@@ -549,18 +618,19 @@ int spmm_upload_dense(spmm_csr_t A, const double *src, long long n_rows, int k, 
         SPMM_CUDA(cudaMemcpyAsync(d_dst, src, sizeof(double) * (size_t)n_rows * (size_t)k, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     else
     {
-        int rc = ensure_streams(A);
-        if (!rc)
-            rc = ensure_ring(A);
+        RingLease lease;
+        int rc = borrow_ring(A->device, &lease.r);
         HostRows b;
         b.flat = src;
         b.ld = k;
         if (!rc)
-            rc = staged_upload(A, b, d_dst, 0, (int)n_rows, k, (cudaStream_t)stream);
+            rc = staged_upload(*lease.r, A->device, b, d_dst, 0, (int)n_rows, k, (cudaStream_t)stream);
         if (rc)
             return rc;
+        SPMM_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); // before the ring goes back to the free list
+        return SPMM_OK;
     }
-    SPMM_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); // the staging ring is free again on return
+    SPMM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return SPMM_OK;
 }
 
@@ -578,15 +648,18 @@ int spmm_download_dense(spmm_csr_t A, const double *d_src, long long n_rows, int
         SPMM_CUDA(cudaMemcpyAsync(dst, d_src, sizeof(double) * (size_t)n_rows * (size_t)k, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     else
     {
-        rc = ensure_streams(A);
-        if (!rc)
-            rc = ensure_ring(A);
+        RingLease lease;
+        rc = borrow_ring(A->device, &lease.r);
         HostRowsOut c;
         c.flat = dst;
         c.ld = k;
         CopySink cs{c, k};
         if (!rc)
-            rc = staged_download(A, d_src, (int)n_rows, k, (cudaStream_t)stream, copy_sink, &cs);
+            rc = staged_download(*lease.r, A->device, d_src, (int)n_rows, k, (cudaStream_t)stream, copy_sink, &cs);
+        const cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (!rc)
+            SPMM_CUDA(e);
+        return rc;
     }
     SPMM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return rc;

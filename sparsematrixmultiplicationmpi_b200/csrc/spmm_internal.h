@@ -70,6 +70,7 @@ struct Tuning
     int tiled_ksplit = 0;   // build: CTAs that share one chunk, each taking a group of k-tiles (0/1 none)
     int tiled_npw = 0;      // launch: producer warps (4, 8)
     int host_slabs = 0;     // host-buffer multiply: k-slabs in the PCIe pipeline (0 auto, 1 none)
+    int tiled_gw = 0;       // build: gather-window layout built on the host (0 off, 1 rows as they lie, 2 rows clustered by shared columns)
     int tiled_auto_after = 1; // AUTO builds the tile layout on the multiply after this many whole-matrix multiplies of a handle
     int tiled_pdl = 1;      // launch: programmatic dependent launch of the tiled kernel (0 off)
     int tiled_group = 0;    // build: tiles one far-band apart walked in turn, this many bands per group (0 auto = 2, 1 off)
@@ -88,6 +89,8 @@ struct DeviceProps
     long long l2_bytes = 0;
 };
 const DeviceProps &device_props(int device);
+// fn(i) for i in [0, n) on the library's host threads, the caller taking part (spmm_host.cu)
+void host_parallel_for(int n, const std::function<void(int)> &fn);
 
 } // namespace spmm
 
@@ -103,7 +106,6 @@ struct spmm_csr_s
     spmm::Schedule sched;
     // staging of the host-buffer entry points (spmm_host.cu): pinned mirrors of B and C, their device images, streams
     std::mutex host_mu; // one host-buffer call per handle at a time
-    double *h_ring = nullptr; // pinned staging ring (a few 2 MB chunks per direction)
     double *d_B = nullptr, *d_C = nullptr;
     size_t d_B_elems = 0, d_C_elems = 0;
     cudaStream_t stream = nullptr; // compute

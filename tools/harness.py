@@ -166,8 +166,9 @@ def cfg2(args, emit, dev):
                 pool = f[6] if len(f) > 6 else 0
                 ksplit = f[7] if len(f) > 7 else 0
                 group = f[8] if len(f) > 8 else 0
+                gw = f[9] if len(f) > 9 else 0  # gather-window layout built on the host: 1 rows as they lie, 2 clustered
 
-                def make(s, T=T, BR=BR, kt=kt, thr=thr, depth=depth, ns_cap=ns_cap, pool=pool, ksplit=ksplit, group=group):
+                def make(s, T=T, BR=BR, kt=kt, thr=thr, depth=depth, ns_cap=ns_cap, pool=pool, ksplit=ksplit, group=group, gw=gw):
                     A = spmm.DeviceCSR.from_host(host, dev.index)
                     _cabi.tune("reset", 0)
                     _cabi.tune("tiled.kt", kt)
@@ -177,6 +178,7 @@ def cfg2(args, emit, dev):
                     _cabi.tune("tiled.pool", pool)
                     _cabi.tune("tiled.ksplit", ksplit)
                     _cabi.tune("tiled.group", group)
+                    _cabi.tune("tiled.gw", gw)
                     try:
                         A.build_tiles(T, BR)
                     finally:
@@ -198,6 +200,8 @@ def cfg2(args, emit, dev):
                            for ncw, u in ((8, 4), (8, 8), (12, 4), (12, 8), (16, 4), (16, 8), (20, 4), (24, 4))]
                     vs += [(f"{base} ncw={ncw} u=4 npw=8", "tiled", {"tiled.ncw": ncw, "tiled.unroll": 4, "tiled.npw": 8})
                            for ncw in (12, 16)]
+                if kt:
+                    vs = [(lab, kern, dict(tune, **{"tiled.kt": kt})) for lab, kern, tune in vs]  # launch with the k-tile the layout was cut for
                 run_variants("cfg2", sets, k, vs, args.iters, emit, host.nnz, n, {"tiles": info})
                 for A, _, _ in sets:
                     A.close()
