@@ -260,7 +260,6 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "tiled.group") t.tiled_group = value;
     else if (k == "tiled.pdl") t.tiled_pdl = value;
     else if (k == "tiled.auto_after") t.tiled_auto_after = value;
-    else if (k == "tiled.gw") t.tiled_gw = value;
     else if (k == "tiled.stride") t.tiled_stride = value;
     else if (k == "stream") t.stream = value;
     else if (k == "stream.tile") t.stream_tile = value;

@@ -170,8 +170,18 @@ bool is_pinned(const void *p)
 }
 
 constexpr size_t CHUNK_BYTES = 1u << 20; // pipeline chunk: about 1 MB of rows, packed / unpacked by one host thread
-constexpr int RING_WORKERS = 8;          // host threads that pack / unpack side by side, two ring slots each
-constexpr int RING_SLOTS = 2 * RING_WORKERS;
+constexpr int RING_WORKERS_MAX = 16;     // host threads that pack / unpack side by side, two ring slots each
+constexpr int RING_SLOTS = 2 * RING_WORKERS_MAX;
+int ring_workers()
+{
+    static const int w = [] {
+        int v = 8; // measured on the B200 host (16 cores): see DESIGN.md section 6
+        if (const char *e = getenv("SPMM_RING_WORKERS"))
+            v = atoi(e);
+        return std::max(1, std::min(v, RING_WORKERS_MAX));
+    }();
+    return w;
+}
 
 int ensure_device(double **buf, size_t *have, size_t want)
 {
@@ -212,7 +222,7 @@ struct Ring
     int device = 0;
     double *buf = nullptr;
     cudaEvent_t ev[2 * RING_SLOTS] = {};
-    double *slot(int dir, int i) const { return buf + ((size_t)(dir * RING_SLOTS + i) * CHUNK_BYTES) / sizeof(double); }
+    double *slot(int dir, int i) const { return buf + ((size_t)(dir * 2 * ring_workers() + i) * CHUNK_BYTES) / sizeof(double); }
     cudaEvent_t event(int dir, int i) const { return ev[dir * RING_SLOTS + i]; }
 };
 std::mutex g_ring_mu;
@@ -232,7 +242,7 @@ int borrow_ring(int device, Ring **out)
     }
     Ring *r = new Ring();
     r->device = device;
-    cudaError_t e = cudaHostAlloc((void **)&r->buf, 2 * RING_SLOTS * CHUNK_BYTES, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc((void **)&r->buf, (size_t)4 * ring_workers() * CHUNK_BYTES, cudaHostAllocDefault); // 2 directions x 2 slots per worker
     for (int i = 0; e == cudaSuccess && i < 2 * RING_SLOTS; ++i)
         e = cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming);
     if (e != cudaSuccess)
@@ -269,7 +279,7 @@ int staged_upload(const Ring &ring, int device, const HostRows &src, double *d, 
         return SPMM_OK;
     const int rpc = rows_per_chunk(k), n_chunks = (r1 - r0 + rpc - 1) / rpc;
     const size_t width = sizeof(double) * (size_t)k;
-    const int W = std::max(1, std::min({RING_WORKERS, pool().threads(), n_chunks}));
+    const int W = std::max(1, std::min({ring_workers(), pool().threads(), n_chunks}));
     std::atomic<int> err{(int)cudaSuccess};
     pool().parallel_for(W, [&](int w) {
         cudaError_t e = cudaSetDevice(device);
@@ -304,7 +314,7 @@ int staged_download(const Ring &ring, int device, const double *d_c, int n, int 
         return SPMM_OK;
     const int rpc = rows_per_chunk(k), n_chunks = (n + rpc - 1) / rpc;
     const size_t width = sizeof(double) * (size_t)k;
-    const int W = std::max(1, std::min({RING_WORKERS, pool().threads(), n_chunks}));
+    const int W = std::max(1, std::min({ring_workers(), pool().threads(), n_chunks}));
     auto issue = [&](int c, int slot) -> cudaError_t {
         const int c0 = c * rpc, c1 = std::min(n, c0 + rpc);
         cudaError_t e = cudaMemcpyAsync(ring.slot(1, slot), d_c + (size_t)c0 * k, width * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, s);

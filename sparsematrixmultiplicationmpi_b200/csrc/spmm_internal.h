@@ -70,7 +70,6 @@ struct Tuning
     int tiled_ksplit = 0;   // build: CTAs that share one chunk, each taking a group of k-tiles (0/1 none)
     int tiled_npw = 0;      // launch: producer warps (4, 8)
     int host_slabs = 0;     // host-buffer multiply: k-slabs in the PCIe pipeline (0 auto, 1 none)
-    int tiled_gw = 0;       // build: gather-window layout built on the host (0 off, 1 rows as they lie, 2 rows clustered by shared columns)
     int tiled_auto_after = 1; // AUTO builds the tile layout on the multiply after this many whole-matrix multiplies of a handle
     int tiled_pdl = 1;      // launch: programmatic dependent launch of the tiled kernel (0 off)
     int tiled_group = 0;    // build: tiles one far-band apart walked in turn, this many bands per group (0 auto = 2, 1 off)
@@ -122,7 +121,6 @@ struct spmm_csr_s
     int *d_tsingles = nullptr;
     int *d_torder = nullptr;          // walking order of the tiles (nullptr: as they lie)
     int tl_stride = 0, tl_group = 0;  // detected far-band distance in rows, planes interleaved per super-group
-    int tl_gw = 0, tl_hdr_bytes = 0, tl_rowtab_off = 0; // gather-window layout (host-built): single B rows in an LRU window, per-tile row table
     // precomputed CTA cuts per (kind, grid size): kind 0 = rows of the CSR
     mutable std::map<long long, int *> bounds;
     // merge-path scratch (carry rows), grown on demand

@@ -39,7 +39,6 @@
 
 #include <cstdio>
 #include <cstdlib>
-#include <atomic>
 #include <cstring>
 #include <vector>
 
@@ -651,10 +650,7 @@ struct TiledArgs
     double *C;
     long long ldb, ldc;
     int n_tiles, n_chunks /* shares: chunks x ksplit */, ksplit, tiles_per_chunk, T, BR, NS, POOL, kc, nkt, depth, prefetch;
-    unsigned hdr_bytes;   // header + unit table (+ row table) bytes of a blob
-    unsigned rowtab_off;  // gather-window layouts: offset of the tile's row table (global row id of local row i) in the blob; 0 = none
-    int gw;               // gather-window layout: no boxes; every staged B row travels in a group of 4 (gather4) whose window slot is loads[].y
-    int sg_stride;        // ints per tile in the singles array
+    unsigned hdr_bytes;   // header + unit table bytes of a blob
     unsigned blob_stride; // bytes reserved per blob buffer in smem
     unsigned slab_off;    // offset of the slab (window slots, then the singles pool) from the aligned smem base
 };
@@ -668,7 +664,6 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
                                                                          const __grid_constant__ CUtensorMap row_map)
 {
     constexpr int NL = KT / (2 * TL); // LDS.128 per lane and record
-    constexpr int NLC = NL < 4 ? NL : 4; // ... issued this many at a time
     static_assert(NL >= 1 && NL * 2 * TL == KT, "a team of TL lanes covers the k-tile with NL 16-byte accesses per lane");
     // (NL = 1, the 8-column k-tile for k <= 8: the two teams of a quarter-warp read 64-byte slab rows that share their banks
     // when the rows have the same parity — 1.5 wavefronts per quarter-warp on average instead of the 2 a half-empty 16-column
@@ -752,7 +747,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
             Meta m;
             m.d = a.tdesc[x.t];
             m.ld = a.loads[(size_t)x.t * a.NS + min(pw + NPW * lane, a.NS - 1)];
-            m.sg = reinterpret_cast<const int4 *>(a.singles + (size_t)x.t * a.sg_stride)[min(pw + NPW * lane, a.sg_stride / 4 - 1)];
+            m.sg = reinterpret_cast<const int4 *>(a.singles + (size_t)x.t * a.POOL)[min(pw + NPW * lane, a.POOL / 4 - 1)];
             return m;
         };
         long long p_wait = 0, p_issue = 0, p_sgl = 0, p_items = 0, p_t0 = TCLK();
@@ -822,20 +817,11 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
             const unsigned pool = s_slab + (unsigned)(a.NS * a.BR) * (KT * 8);
             for (int g = pw + NPW * lane; !T_NO_STAGE && g * 4 < n_singles; g += NPW * 32)
             {
-                const bool mine = g == pw + NPW * lane;
-                const int4 rows = mine ? m.sg
-                                       : reinterpret_cast<const int4 *>(a.singles + (size_t)cur.t * a.sg_stride)[g]; // > 512 singles
-                if (a.gw)
-                {
-                    // gather-window layout: the group lands in the window slot the builder chose (least recently used)
-                    const int slot = mine ? m.ld.y : a.loads[(size_t)cur.t * a.NS + g].y;
-                    tma_gather4(s_slab + (unsigned)slot * (4u * KT * 8u), &row_map, k0, rows, bar);
-                }
-                else
-                {
-                    const int pr = (m.d.pool_start + g * 4) % a.POOL;
-                    tma_gather4(pool + (unsigned)pr * (KT * 8), &row_map, k0, rows, bar);
-                }
+                const int4 rows = g == pw + NPW * lane
+                                      ? m.sg
+                                      : reinterpret_cast<const int4 *>(a.singles + (size_t)cur.t * a.POOL)[g]; // > 512 singles
+                const int pr = (m.d.pool_start + g * 4) % a.POOL;
+                tma_gather4(pool + (unsigned)pr * (KT * 8), &row_map, k0, rows, bar);
             }
             work_next(cur);
             ++w;
@@ -903,8 +889,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
         const int n_units = hdr.y;
         const unsigned units = blob + 16;
         const unsigned vals_s = blob + a.hdr_bytes, ids_s = blob + (unsigned)hdr.w;
-        double *__restrict__ Ck = a.C + (a.rowtab_off ? 0ll : (long long)hdr.z * a.T * a.ldc) + k0; // hdr.z: the tile at this place of the walking order
-        const unsigned rowtab = blob + a.rowtab_off; // gather-window layouts: the tile's rows are named one by one
+        double *__restrict__ Ck = a.C + (long long)hdr.z * a.T * a.ldc + k0; // hdr.z: the tile at this place of the walking order
 
         // units round-robin over the warps, rotated by the item so the remainder moves around
         for (int u = (warp + w) % NCW; !T_NO_COMPUTE && u < n_units; u += NCW)
@@ -912,13 +897,6 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
             const uint2 e = lds64u(units + (u * UW + tw) * 8);
             const int begin = e.x & 0x1FFF, len = (e.x >> 13) & 0x3FF, row = (e.x >> 23) & 0xFF;
             const bool split = (e.x >> 31) != 0;
-            long long crow = row; // row of C (relative to Ck)
-            if (a.rowtab_off && row != (int)UE_PAD_ROW)
-            {
-                int gr;
-                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(gr) : "r"(rowtab + (unsigned)row * 4u));
-                crow = gr;
-            }
             const int maxlen = __reduce_max_sync(0xFFFFFFFFu, len);
             double2 acc[NL];
 #pragma unroll
@@ -950,29 +928,23 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
 #pragma unroll
                     for (int q = 0; q < U; ++q)
                         v[q] = lds64d(vbase + (i + q) * 8);
-                    // (a k-tile of 64 columns = 8 accesses per lane and record: taken four at a time so that U records in flight
-                    // stay within the register file)
+                    double2 b[U][NL];
 #pragma unroll
-                    for (int xc = 0; xc < NL; xc += NLC)
+                    for (int q = 0; q < U; ++q)
                     {
-                        double2 b[U][NLC];
+                        const unsigned a0 = b0 + id[q] * (KT * 8), a1 = a0 ^ 64u;
 #pragma unroll
-                        for (int q = 0; q < U; ++q)
-                        {
-                            const unsigned a0 = b0 + id[q] * (KT * 8), a1 = a0 ^ 64u;
-#pragma unroll
-                            for (int x = 0; x < NLC; ++x)
-                                b[q][x] = lds128d((((xc + x) & 1) ? a1 : a0) + ((xc + x) >> 1) * 128);
-                        }
-#pragma unroll
-                        for (int q = 0; q < U; ++q)
-#pragma unroll
-                            for (int x = 0; x < NLC; ++x)
-                            {
-                                acc[xc + x].x = fma(v[q], b[q][x].x, acc[xc + x].x);
-                                acc[xc + x].y = fma(v[q], b[q][x].y, acc[xc + x].y);
-                            }
+                        for (int x = 0; x < NL; ++x)
+                            b[q][x] = lds128d(((x & 1) ? a1 : a0) + (x >> 1) * 128);
                     }
+#pragma unroll
+                    for (int q = 0; q < U; ++q)
+#pragma unroll
+                        for (int x = 0; x < NL; ++x)
+                        {
+                            acc[x].x = fma(v[q], b[q][x].x, acc[x].x);
+                            acc[x].y = fma(v[q], b[q][x].y, acc[x].y);
+                        }
                 }
             }
             for (; i < maxlen; i += U)
@@ -998,28 +970,24 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
                     if (i + q < len)
                         v[q] = lds64d(vbase + (i + q) * 8);
                 }
+                double2 b[U][NL];
 #pragma unroll
-                for (int xc = 0; xc < NL; xc += NLC)
-                {
-                    double2 b[U][NLC];
+                for (int q = 0; q < U; ++q)
 #pragma unroll
-                    for (int q = 0; q < U; ++q)
-#pragma unroll
-                        for (int x = 0; x < NLC; ++x)
-                        {
-                            b[q][x] = make_double2(0.0, 0.0);
-                            if (i + q < len)
-                                b[q][x] = lds128d(s_slab + id[q] * (KT * 8) + colo[xc + x] * 8);
-                        }
-#pragma unroll
-                    for (int q = 0; q < U; ++q)
+                    for (int x = 0; x < NL; ++x)
                     {
+                        b[q][x] = make_double2(0.0, 0.0);
+                        if (i + q < len)
+                            b[q][x] = lds128d(s_slab + id[q] * (KT * 8) + colo[x] * 8);
+                    }
 #pragma unroll
-                        for (int x = 0; x < NLC; ++x)
-                        {
-                            acc[xc + x].x = fma(v[q], b[q][x].x, acc[xc + x].x);
-                            acc[xc + x].y = fma(v[q], b[q][x].y, acc[xc + x].y);
-                        }
+                for (int q = 0; q < U; ++q)
+                {
+#pragma unroll
+                    for (int x = 0; x < NL; ++x)
+                    {
+                        acc[x].x = fma(v[q], b[q][x].x, acc[x].x);
+                        acc[x].y = fma(v[q], b[q][x].y, acc[x].y);
                     }
                 }
             }
@@ -1041,7 +1009,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
                     }
                 if (tw == 0 && row != (int)UE_PAD_ROW)
                 {
-                    double *cr = Ck + crow * a.ldc;
+                    double *cr = Ck + (long long)row * a.ldc;
 #pragma unroll
                     for (int x = 0; x < NL; ++x)
                         if (k0 + (x * TL + l) * 2 < a.kc)
@@ -1054,7 +1022,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) spmm_tiled_kernel(const T
             }
             else if (row != (int)UE_PAD_ROW)
             {
-                double *cr = Ck + crow * a.ldc;
+                double *cr = Ck + (long long)row * a.ldc;
 #pragma unroll
                 for (int x = 0; x < NL; ++x)
                     if (k0 + colo[x] < a.kc)
@@ -1205,10 +1173,7 @@ int launch_tiled_t(const spmm_csr_s *A, const double *d_B, long long ldb, double
     a.nkt = (kc + KT - 1) / KT;
     a.depth = A->tl_depth;
     a.prefetch = tuning().tiled_prefetch >= 0 ? tuning().tiled_prefetch : 0;
-    a.hdr_bytes = A->tl_hdr_bytes ? (unsigned)A->tl_hdr_bytes : hdr_bytes_of(A->tl_T);
-    a.rowtab_off = (unsigned)A->tl_rowtab_off;
-    a.gw = A->tl_gw;
-    a.sg_stride = A->tl_gw ? A->tl_NS * 4 : A->tl_POOL;
+    a.hdr_bytes = hdr_bytes_of(A->tl_T);
     a.blob_stride = (unsigned)m.blob_stride;
     a.slab_off = (unsigned)m.slab_off;
     const int grid = std::max(1, std::min(a.n_chunks, device_props(A->device).sm_count));
@@ -1413,7 +1378,6 @@ void free_tiles(spmm_csr_s *A)
     A->d_tsingles = nullptr;
     A->tl_T = A->tl_BR = A->tl_tiles = A->tl_NS = A->tl_POOL = A->tl_max_recs = A->tl_max_blob = A->tl_chunk = A->tl_kt = A->tl_depth = A->tl_ksplit = 0;
     A->tl_box_rows_loaded = A->tl_single_rows = 0;
-    A->tl_gw = A->tl_hdr_bytes = A->tl_rowtab_off = 0;
 }
 
 bool tiled_shape_ok(const spmm_csr_s *A, const double *d_B, long long ldb, const double *d_C, long long ldc, int kc)
@@ -1429,7 +1393,7 @@ int launch_tiled(const spmm_csr_s *A, const double *d_B, long long ldb, double *
     const Tuning &t = tuning();
     note_kernel("spmm_tiled_kernel");
     const int kt = t.tiled_kt > 0 ? t.tiled_kt : A->tl_kt;
-    const int ncw = t.tiled_ncw > 0 ? t.tiled_ncw : (kt == 64 ? 8 : 16);
+    const int ncw = t.tiled_ncw > 0 ? t.tiled_ncw : 16;
     const int u = t.tiled_unroll > 0 ? t.tiled_unroll : 4;
     const int npw = t.tiled_npw == 8 ? 8 : 4;
     if (kt == 8)
@@ -1447,453 +1411,10 @@ int launch_tiled(const spmm_csr_s *A, const double *d_B, long long ldb, double *
         return launch_tiled_ncw<16>(A, ncw, u, npw, d_B, ldb, d_C, ldc, kc, stream, x);
     if (kt == 32)
         return launch_tiled_ncw<32>(A, ncw, u, npw, d_B, ldb, d_C, ldc, kc, stream, x);
-    if (kt == 64)
-    {
-        // 64-column k-tile (gather-window layouts): 16 accumulators per lane, fewer consumer warps within the register file
-        if ((ncw == 8 || ncw == 0) && u == 4 && npw == 4)
-            return launch_tiled_t<64, 8, 4, 4>(A, d_B, ldb, d_C, ldc, kc, stream, x);
-        if (ncw == 12 && u == 4 && npw == 4)
-            return launch_tiled_t<64, 12, 4, 4>(A, d_B, ldb, d_C, ldc, kc, stream, x);
-        if (ncw == 8 && u == 4 && npw == 8)
-            return launch_tiled_t<64, 8, 4, 8>(A, d_B, ldb, d_C, ldc, kc, stream, x);
-        if (ncw == 4 && u == 4 && npw == 4)
-            return launch_tiled_t<64, 4, 4, 4>(A, d_B, ldb, d_C, ldc, kc, stream, x);
-        set_error("tiled kernel: the 64-column k-tile goes with 4, 8 or 12 consumer warps, unroll 4");
-        return SPMM_ERR_INVALID;
-    }
-    set_error("tiled kernel: k-tile must be 8, 16, 32 or 64");
+    set_error("tiled kernel: k-tile must be 8, 16 or 32");
     return SPMM_ERR_INVALID;
 }
 
-} // namespace spmm
-
-
-// ---- gather-window layout, built on the host --------------------------------------------------------------------------
-// The same blobs, units and kernel as above, but the window holds single B rows: every row a tile reads and the window
-// lacks travels in a group of four (one cp.async.bulk.tensor gather4) into the least recently used 4-row slot that no tile
-// in flight reads. No boxes of consecutive rows, so a tile may be ANY set of T rows (its row ids sit in the blob) — rows
-// that share columns can be walked together wherever they lie in the matrix — and the k-tile may be as wide as k (64
-// columns: values and ids are staged and read once instead of once per 16 columns).
-// Built by the host threads from a copy of the CSR arrays: one pass over the tiles for sizes, one replay per chunk.
-namespace spmm
-{
-namespace
-{
-struct TileLayout
-{
-    int n = 0, nr = 0, n_units = 0, nval = 0, nid = 0;
-    bool fail = false;
-    std::vector<uint2> units; // n_units * UW entries
-    std::vector<int> voff, ioff;
-};
-
-// mirrors the unit / stream layout of tile_build_kernel (rows ranked by length, long rows split in 8 segments, rows of a unit
-// start on distinct 8-byte bank pairs)
-void layout_tile(const int *len, int nr, TileLayout &L)
-{
-    L.nr = nr;
-    std::vector<int> split, normal;
-    for (int r = 0; r < nr; ++r)
-        if (len[r] >= TB_SPLIT && (int)split.size() < TB_SPLITCAP)
-            split.push_back(r);
-        else
-            normal.push_back(r);
-    std::stable_sort(normal.begin(), normal.end(), [&](int a, int b) { return len[a] > len[b]; });
-    const int n_split = (int)split.size(), n_normal_units = ((int)normal.size() + UW - 1) / UW;
-    L.n_units = n_normal_units + n_split;
-    L.units.assign((size_t)L.n_units * UW, make_uint2(UE_PAD_ROW << 23, 0u));
-    L.voff.assign(nr, 0);
-    L.ioff.assign(nr, 0);
-    for (size_t rank = 0; rank < normal.size(); ++rank)
-    {
-        const int r = normal[rank];
-        if (len[r] > 0x3FF)
-            L.fail = true; // more than TB_SPLITCAP very long rows in one tile
-        L.units[rank] = make_uint2(((unsigned)(len[r] & 0x3FF) << 13) | ((unsigned)r << 23), 0u);
-    }
-    for (int sr = 0; sr < n_split; ++sr)
-    {
-        const int r = split[sr], l = len[r];
-        const int seg = (((l + UW - 1) / UW) + 3) & ~3;
-        for (int j = 0; j < UW; ++j)
-        {
-            const int b = std::min(j * seg, l), e = std::min(b + seg, l);
-            L.units[(size_t)(n_normal_units + sr) * UW + j] =
-                make_uint2((unsigned)b | ((unsigned)(e - b) << 13) | ((unsigned)r << 23) | 0x80000000u, (unsigned)b);
-        }
-    }
-    std::vector<int> usz_v(L.n_units), usz_i(L.n_units);
-    for (int u = 0; u < L.n_units; ++u)
-    {
-        int pos = 0, ipos = 0;
-        if (u >= n_normal_units)
-        {
-            const int r = split[u - n_normal_units];
-            pos = len[r];
-            ipos = (len[r] + 3) >> 2;
-        }
-        else
-        {
-            unsigned used_v = 0, used_i = 0;
-            for (int j = 0; j < UW; ++j)
-            {
-                uint2 &w = L.units[(size_t)u * UW + j];
-                const int r = (int)((w.x >> 23) & 0xFF);
-                if (r == (int)UE_PAD_ROW)
-                    continue;
-                const int l = len[r];
-                if (l > 0)
-                {
-                    while ((used_v >> (pos & 15)) & 1u)
-                        ++pos;
-                    used_v |= 1u << (pos & 15);
-                    while ((used_i >> (ipos & 15)) & 1u)
-                        ++ipos;
-                    used_i |= 1u << (ipos & 15);
-                }
-                w.x = (w.x & ~0x1FFFu) | (unsigned)pos;
-                w.y = (unsigned)(ipos * 4);
-                L.voff[r] = pos;
-                L.ioff[r] = ipos * 4;
-                pos += l;
-                ipos += (l + 3) >> 2;
-            }
-        }
-        usz_v[u] = pos;
-        usz_i[u] = ipos;
-    }
-    int bv = 0, bi = 0;
-    for (int u = 0; u < L.n_units; ++u)
-    {
-        for (int j = 0; j < UW; ++j)
-        {
-            uint2 &w = L.units[(size_t)u * UW + j];
-            const int r = (int)((w.x >> 23) & 0xFF);
-            if (r == (int)UE_PAD_ROW)
-                continue;
-            w.x = (w.x & ~0x1FFFu) | (unsigned)((int)(w.x & 0x1FFF) + bv);
-            w.y += (unsigned)(bi * 4);
-            if (u < n_normal_units || j == 0)
-            {
-                L.voff[r] += bv;
-                L.ioff[r] += bi * 4;
-            }
-        }
-        bv += usz_v[u];
-        bi += usz_i[u];
-    }
-    L.nval = bv;
-    L.nid = bi * 4;
-    if (L.nval > 0x1FFF)
-        L.fail = true; // the begin field of a unit entry holds 13 bits
-}
-
-// Tiles of T rows that share columns, for matrices whose pattern is (close to) symmetric: a tile grows from a seed row by
-// always taking the unassigned row with the most columns already in the tile; the scores of the frontier are halved when
-// a tile is closed, so the next tile starts beside the last ones (rows of B still in the window). Rows of a tile need not
-// be consecutive: natural orderings of 3-D meshes put a row's neighbours a whole grid plane apart.
-void cluster_rows(const std::vector<int> &rp, const std::vector<int> &ci, int n_rows, int n_cols, int T, std::vector<int> &perm)
-{
-    perm.clear();
-    perm.reserve(n_rows);
-    std::vector<float> score(n_rows, 0.f);
-    std::vector<char> assigned(n_rows, 0);
-    std::vector<int> in_tile(n_cols, -1), active;
-    std::vector<std::pair<float, int>> heap;
-    auto push = [&](int r) {
-        heap.emplace_back(score[r], -r); // ties: the lower row id first
-        std::push_heap(heap.begin(), heap.end());
-    };
-    int next_seed = 0, tile = 0;
-    while ((int)perm.size() < n_rows)
-    {
-        for (int cnt = 0; cnt < T && (int)perm.size() < n_rows; ++cnt)
-        {
-            int r = -1;
-            while (!heap.empty())
-            {
-                std::pop_heap(heap.begin(), heap.end());
-                const std::pair<float, int> top = heap.back();
-                heap.pop_back();
-                if (!assigned[-top.second] && top.first == score[-top.second])
-                {
-                    r = -top.second;
-                    break;
-                }
-            }
-            if (r < 0)
-            {
-                while (next_seed < n_rows && assigned[next_seed])
-                    ++next_seed;
-                r = next_seed;
-            }
-            assigned[r] = 1;
-            perm.push_back(r);
-            for (int e = rp[r]; e < rp[r + 1]; ++e)
-            {
-                const int c = ci[e];
-                if (in_tile[c] == tile)
-                    continue;
-                in_tile[c] = tile;
-                if (c >= n_rows)
-                    continue;
-                // rows that name column c: for a symmetric pattern, the columns of row c
-                for (int e2 = rp[c]; e2 < rp[c + 1]; ++e2)
-                {
-                    const int r2 = ci[e2];
-                    if (r2 < n_rows && !assigned[r2])
-                    {
-                        if (score[r2] == 0.f)
-                            active.push_back(r2);
-                        score[r2] += 1.f;
-                        push(r2);
-                    }
-                }
-            }
-        }
-        ++tile;
-        heap.clear();
-        size_t keep = 0;
-        for (int r : active)
-            if (!assigned[r])
-            {
-                score[r] *= 0.5f;
-                if (score[r] >= 0.25f)
-                {
-                    active[keep++] = r;
-                    heap.emplace_back(score[r], -r);
-                }
-                else
-                    score[r] = 0.f;
-            }
-        active.resize(keep);
-        std::make_heap(heap.begin(), heap.end());
-    }
-}
-} // namespace
-
-int build_tiles_gw(spmm_csr_s *A, int T, int kt, int ksplit, int cluster, int depth)
-{
-    const int n_rows = A->n_rows, n_cols = A->n_cols;
-    const long long nnz = A->nnz;
-    std::vector<int> rp((size_t)n_rows + 1), ci((size_t)nnz);
-    std::vector<double> va((size_t)nnz);
-    SPMM_CUDA(cudaMemcpy(rp.data(), A->d_rowptr, sizeof(int) * rp.size(), cudaMemcpyDeviceToHost));
-    SPMM_CUDA(cudaMemcpy(ci.data(), A->d_colidx, sizeof(int) * ci.size(), cudaMemcpyDeviceToHost));
-    SPMM_CUDA(cudaMemcpy(va.data(), A->d_vals, sizeof(double) * va.size(), cudaMemcpyDeviceToHost));
-
-    std::vector<int> perm;
-    if (cluster && n_rows == n_cols)
-        cluster_rows(rp, ci, n_rows, n_cols, T, perm);
-    else
-    {
-        perm.resize(n_rows);
-        for (int i = 0; i < n_rows; ++i)
-            perm[i] = i;
-    }
-    const int n_tiles = (n_rows + T - 1) / T;
-    const int ucap = units_cap(T);
-    const int rowtab_off = 16 + 64 * ucap;
-    const int hdr_bytes = rowtab_off + ((4 * T + 15) & ~15);
-
-    // pass 1: unit layout and blob size of every tile
-    std::vector<TileLayout> lay((size_t)n_tiles);
-    std::vector<unsigned> bytes((size_t)n_tiles);
-    std::atomic<int> failed{0};
-    host_parallel_for((n_tiles + 31) / 32, [&](int blk) {
-        std::vector<int> len(T);
-        for (int t = blk * 32; t < std::min(n_tiles, blk * 32 + 32); ++t)
-        {
-            const int r0 = t * T, nr = std::min(n_rows, r0 + T) - r0;
-            int n = 0;
-            for (int i = 0; i < nr; ++i)
-            {
-                len[i] = rp[perm[r0 + i] + 1] - rp[perm[r0 + i]];
-                n += len[i];
-            }
-            layout_tile(len.data(), nr, lay[t]);
-            lay[t].n = n;
-            if (lay[t].fail)
-                failed = 1;
-            bytes[t] = (unsigned)hdr_bytes + (((unsigned)lay[t].nval * 8u + 15u) & ~15u) + (((unsigned)lay[t].nid * 2u + 15u) & ~15u);
-        }
-    });
-    if (failed)
-    {
-        set_error("gather-window layout: a tile holds more than 8 very long rows or more than 8191 value slots");
-        return SPMM_ERR_UNSUPPORTED;
-    }
-    std::vector<unsigned long long> off((size_t)n_tiles + 1, 0);
-    unsigned max_blob = 0;
-    for (int t = 0; t < n_tiles; ++t)
-    {
-        off[t + 1] = off[t] + bytes[t];
-        max_blob = std::max(max_blob, bytes[t]);
-    }
-    SPMM_REQUIRE((off[n_tiles] >> 4) < (1ull << 32), "matrix too large for the tile layout");
-
-    const int sms = device_props(A->device).sm_count;
-    const int per_sm = std::max(1, (int)((n_tiles + (long long)sms * 48 - 1) / ((long long)sms * 48)));
-    const int n_chunks_want = std::max(1, sms * per_sm / std::max(1, ksplit));
-    const int tiles_per_chunk = tuning().tiled_chunk > 0 ? tuning().tiled_chunk : std::max(1, (n_tiles + n_chunks_want - 1) / n_chunks_want);
-    const int n_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
-    const TiledSmem fixed = tiled_smem(kt, depth, T, 4, 0, 0, (int)max_blob);
-    const size_t slot_bytes = (size_t)4 * kt * 8;
-    if (fixed.total + 16 * slot_bytes > (size_t)SMEM_CAP)
-    {
-        set_error("gather-window layout: the blobs of this tile height leave no room for a window");
-        return SPMM_ERR_UNSUPPORTED;
-    }
-    int NS = (int)std::min<size_t>(4096, ((size_t)SMEM_CAP - fixed.total) / slot_bytes);
-    if (tuning().tiled_ns > 0)
-        NS = std::min(NS, tuning().tiled_ns);
-
-    std::vector<unsigned char> blob((size_t)off[n_tiles] + 64, 0);
-    std::vector<TileDesc> tdesc((size_t)n_tiles);
-    std::vector<int2> loads((size_t)n_tiles * NS, make_int2(0, 0));
-    std::vector<int> singles((size_t)n_tiles * NS * 4, 0);
-    std::atomic<long long> total_groups{0};
-    std::atomic<int> drains{0};
-    failed = 0;
-
-    host_parallel_for(n_chunks, [&](int chunk) {
-        std::vector<int> where((size_t)n_cols, -1); // column -> slab row (slot*4 + j) while it is in the window
-        std::vector<int> slot_stamp(NS, -1000000), slot_cols((size_t)NS * 4, -1), cols, miss;
-        int last_fence = 0;
-        const int t_begin = chunk * tiles_per_chunk, t_end = std::min(n_tiles, t_begin + tiles_per_chunk);
-        for (int t = t_begin; t < t_end && !failed; ++t)
-        {
-            const int lt = t - t_begin, r0 = t * T, nr = lay[t].nr;
-            cols.clear();
-            for (int i = 0; i < nr; ++i)
-                for (int e = rp[perm[r0 + i]]; e < rp[perm[r0 + i] + 1]; ++e)
-                    cols.push_back(ci[e]);
-            std::sort(cols.begin(), cols.end());
-            cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
-            miss.clear();
-            for (int c : cols)
-                if (where[c] >= 0)
-                    slot_stamp[where[c] >> 2] = lt;
-                else
-                    miss.push_back(c);
-            const int groups = ((int)miss.size() + 3) / 4;
-            int eligible = 0;
-            for (int s = 0; s < NS; ++s)
-                eligible += slot_stamp[s] <= lt - depth ? 1 : 0;
-            const bool drain = groups > eligible;
-            if (drain)
-            {
-                last_fence = lt;
-                ++drains;
-            }
-            const int limit = drain ? lt - 1 : lt - depth; // a slot may be overwritten if nothing later than `limit` reads it
-            for (int g = 0; g < groups; ++g)
-            {
-                int best = -1, best_stamp = limit + 1;
-                for (int s = 0; s < NS; ++s)
-                    if (slot_stamp[s] < best_stamp)
-                    {
-                        best = s;
-                        best_stamp = slot_stamp[s];
-                    }
-                if (best < 0)
-                {
-                    failed = 1; // the tile alone needs more rows than the window holds
-                    break;
-                }
-                for (int j = 0; j < 4; ++j)
-                    if (slot_cols[(size_t)best * 4 + j] >= 0)
-                        where[slot_cols[(size_t)best * 4 + j]] = -1;
-                for (int j = 0; j < 4; ++j)
-                {
-                    const int idx = g * 4 + j;
-                    const int c = idx < (int)miss.size() ? miss[idx] : -1;
-                    slot_cols[(size_t)best * 4 + j] = c;
-                    if (c >= 0)
-                        where[c] = best * 4 + j;
-                    singles[((size_t)t * NS + g) * 4 + j] = c >= 0 ? c : miss[(size_t)g * 4]; // padding: a row of the group again
-                }
-                slot_stamp[best] = lt;
-                loads[(size_t)t * NS + g] = make_int2(0, best);
-            }
-            if (failed)
-                break;
-            total_groups += groups;
-            // blob
-            const TileLayout &L = lay[t];
-            unsigned char *mine = blob.data() + off[t];
-            const unsigned val_bytes = ((unsigned)L.nval * 8u + 15u) & ~15u;
-            *reinterpret_cast<int4 *>(mine) = make_int4(L.n, L.n_units, t, (int)((unsigned)hdr_bytes + val_bytes));
-            uint2 *units_out = reinterpret_cast<uint2 *>(mine + 16);
-            for (int i = 0; i < ucap * UW; ++i)
-                units_out[i] = i < L.n_units * UW ? L.units[i] : make_uint2(UE_PAD_ROW << 23, 0u);
-            int *rowtab = reinterpret_cast<int *>(mine + rowtab_off);
-            for (int i = 0; i < nr; ++i)
-                rowtab[i] = perm[r0 + i];
-            double *val_out = reinterpret_cast<double *>(mine + hdr_bytes);
-            unsigned short *id_out = reinterpret_cast<unsigned short *>(mine + hdr_bytes + val_bytes);
-            for (int i = 0; i < nr; ++i)
-            {
-                const int row = perm[r0 + i];
-                for (int e = rp[row], j = 0; e < rp[row + 1]; ++e, ++j)
-                {
-                    val_out[L.voff[i] + j] = va[e];
-                    id_out[L.ioff[i] + j] = (unsigned short)where[ci[e]];
-                }
-            }
-            TileDesc d;
-            d.off16 = (unsigned)(off[t] >> 4);
-            d.bytes = bytes[t];
-            const int fence = std::min(lt - last_fence, 7);
-            d.counts = 0u | ((unsigned)(groups * 4) << 16) | ((unsigned)fence << 29);
-            d.pool_start = 0;
-            tdesc[t] = d;
-        }
-    });
-    if (failed)
-    {
-        set_error("gather-window layout: a tile reads more B rows than the window holds (smaller tiles or a narrower k-tile needed)");
-        return SPMM_ERR_UNSUPPORTED;
-    }
-    if (NS * 4 > 65535)
-    {
-        set_error("gather-window layout: window larger than 16-bit slab row ids");
-        return SPMM_ERR_UNSUPPORTED;
-    }
-
-    SPMM_CUDA(cudaMalloc(&A->d_tblob, blob.size() + 16));
-    SPMM_CUDA(cudaMalloc(&A->d_tdesc, sizeof(TileDesc) * tdesc.size()));
-    SPMM_CUDA(cudaMalloc(&A->d_tloads, sizeof(int2) * loads.size()));
-    SPMM_CUDA(cudaMalloc(&A->d_tsingles, sizeof(int) * singles.size()));
-    SPMM_CUDA(cudaMemcpy(A->d_tblob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
-    SPMM_CUDA(cudaMemcpy(A->d_tdesc, tdesc.data(), sizeof(TileDesc) * tdesc.size(), cudaMemcpyHostToDevice));
-    SPMM_CUDA(cudaMemcpy(A->d_tloads, loads.data(), sizeof(int2) * loads.size(), cudaMemcpyHostToDevice));
-    SPMM_CUDA(cudaMemcpy(A->d_tsingles, singles.data(), sizeof(int) * singles.size(), cudaMemcpyHostToDevice));
-    A->tl_T = T;
-    A->tl_BR = 4;
-    A->tl_tiles = n_tiles;
-    A->tl_NS = NS;
-    A->tl_POOL = 0;
-    A->tl_max_recs = 0;
-    for (int t = 0; t < n_tiles; ++t)
-        A->tl_max_recs = std::max(A->tl_max_recs, lay[t].n);
-    A->tl_max_blob = (int)max_blob;
-    A->tl_chunk = tiles_per_chunk;
-    A->tl_kt = kt;
-    A->tl_depth = depth;
-    A->tl_ksplit = ksplit;
-    A->tl_drains = drains;
-    A->tl_box_rows_loaded = 0;
-    A->tl_single_rows = total_groups * 4;
-    A->tl_gw = 1 + (cluster ? 1 : 0);
-    A->tl_hdr_bytes = hdr_bytes;
-    A->tl_rowtab_off = rowtab_off;
-    if (getenv("SPMM_TILED_DEBUG"))
-        fprintf(stderr, "[tiled build gw] T=%d kt=%d NS=%d (%d rows) chunk=%d cluster=%d: staged rows %lld (%.2f per matrix row), drains %d, max blob %u\n",
-                T, kt, NS, NS * 4, tiles_per_chunk, cluster, (long long)total_groups * 4, (double)total_groups * 4 / std::max(1, n_rows),
-                (int)drains, max_blob);
-    return SPMM_OK;
-}
 } // namespace spmm
 
 namespace spmm
@@ -1923,13 +1444,6 @@ int build_tiles(spmm_csr_t A, int rows_per_tile, int box_rows, int kt_want, int 
     // (64-byte window rows leave room for a third work item in flight: measured 20.6 against 22.7 us at k=8, T=96)
     const int depth = (tn.tiled_depth >= 2 && tn.tiled_depth <= TB_DMAX) ? tn.tiled_depth : (kt_for_depth == 8 ? 3 : 2);
     const int ksplit = std::max(1, std::min(8, ksplit_want > 0 ? ksplit_want : tn.tiled_ksplit)); // CTAs per chunk
-    if (tn.tiled_gw > 0)
-    {
-        // gather-window layout (host-built): 1 = rows as they lie, 2 = rows clustered by shared columns
-        const int T = rows_per_tile > 0 ? rows_per_tile : 64;
-        const int gkt = tn.tiled_kt > 0 ? tn.tiled_kt : kt;
-        return build_tiles_gw(A, T, gkt, gkt >= 64 ? 1 : ksplit, tn.tiled_gw == 2, depth);
-    }
 
     BuildParams p = {};
     p.n_rows = A->n_rows;

@@ -520,36 +520,6 @@ def test_tiled_kernel_8_column_k_tile(oracle, shape, k, ncw):
     assert_close_rel(got, ref, tol=REL_TOL)
 
 
-@pytest.mark.parametrize("shape", list(TILED_SHAPES))
-@pytest.mark.parametrize("gw,kt,T,k", [(1, 16, 64, 16), (1, 32, 32, 32), (2, 64, 32, 64), (2, 64, 64, 64), (1, 64, 8, 64), (2, 32, 64, 48),
-                                       (2, 16, 80, 6), (2, 64, 64, 100), (2, 64, 16, 130)])
-def test_gather_window_layout_vs_oracle(oracle, shape, gw, kt, T, k):
-    """Tile layout built on the host (spmm_tiled.cu: build_tiles_gw): single B rows in an LRU window fed by gather4, tiles of
-    arbitrary rows (gw=2: rows clustered by shared columns, C rows named by the tile's row table), k-tiles up to 64 columns."""
-    n, mean, hb, planes, long_row, ee = TILED_SHAPES[shape]
-    rp, ci, va = banded_csr(41, n, mean, hb, planes, long_row, ee)
-    B = np.random.default_rng(k).integers(1, 101, (n, k)).astype(np.float64)
-    try:
-        got, info = tiled_multiply(spmm.SparseMatrix(va, ci, rp, n, n), B, k, T, 0, {"tiled.gw": gw, "tiled.kt": kt})
-    except _cabi.SpmmError as e:
-        assert e.status == _cabi.SPMM_ERR_UNSUPPORTED  # a tile alone reads more B rows than this window holds
-        return
-    assert info["rows_per_tile"] == T and info["reuse"] > 0
-    assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
-
-
-def test_gather_window_layout_cop20k_shape_vs_oracle(oracle):
-    n, nc, r, c, v, sym = gen.cop20k_A_shaped()
-    with spmm.DeviceCSR.from_coo_host(n, nc, r, c, v, sym, device=0) as A0:
-        host = A0.download()
-    k = 64
-    B = np.random.default_rng(k).integers(1, 101, (n, k)).astype(np.float64)
-    ref = oracle.spmm(host.rowPtr, host.colIndices, host.values, B, k)
-    for gw, kt, T in ((2, 64, 64), (1, 32, 64)):
-        got, info = tiled_multiply(host, B, k, T, 0, {"tiled.gw": gw, "tiled.kt": kt})
-        assert_close_rel(got, ref, tol=REL_TOL)
-
-
 @pytest.mark.parametrize("group", [1, 2, 3, 4, 6])
 @pytest.mark.parametrize("k", [16, 64])
 def test_tiled_walking_order_of_far_band_matrices(oracle, group, k):

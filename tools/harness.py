@@ -166,9 +166,8 @@ def cfg2(args, emit, dev):
                 pool = f[6] if len(f) > 6 else 0
                 ksplit = f[7] if len(f) > 7 else 0
                 group = f[8] if len(f) > 8 else 0
-                gw = f[9] if len(f) > 9 else 0  # gather-window layout built on the host: 1 rows as they lie, 2 clustered
 
-                def make(s, T=T, BR=BR, kt=kt, thr=thr, depth=depth, ns_cap=ns_cap, pool=pool, ksplit=ksplit, group=group, gw=gw):
+                def make(s, T=T, BR=BR, kt=kt, thr=thr, depth=depth, ns_cap=ns_cap, pool=pool, ksplit=ksplit, group=group):
                     A = spmm.DeviceCSR.from_host(host, dev.index)
                     _cabi.tune("reset", 0)
                     _cabi.tune("tiled.kt", kt)
@@ -178,7 +177,6 @@ def cfg2(args, emit, dev):
                     _cabi.tune("tiled.pool", pool)
                     _cabi.tune("tiled.ksplit", ksplit)
                     _cabi.tune("tiled.group", group)
-                    _cabi.tune("tiled.gw", gw)
                     try:
                         A.build_tiles(T, BR)
                     finally:
