@@ -231,6 +231,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("SPMM_DEVICE_BASE", str(local_rank))  # the C++ entry points of this process drive this rank's GPU
     # host threads of the pack / unpack pool: the ranks of one box share its cores
     os.environ.setdefault("SPMM_HOST_THREADS", str(max(2, min(16, (os.cpu_count() or 8) // max(1, world)))))
     metric = "SpMM GFLOP/s and HBM GB/s (% roofline) at 1/2/4/8 B200 vs ref CPU MPI"

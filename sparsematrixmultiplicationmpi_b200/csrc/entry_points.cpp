@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -68,13 +69,17 @@ void ok(int status)
         throw std::runtime_error(std::string("spmm_b200: ") + spmm_last_error());
 }
 
+// Rank r drives GPU (base + r) mod device count; base = SPMM_DEVICE_BASE (default 0) lets several single-rank processes
+// of one box (e.g. one per GPU under a launcher that sets LOCAL_RANK) take different devices.
 int device_for_rank(int rank)
 {
     int count = 0;
     ok(spmm_device_count(&count));
     if (count < 1)
         throw std::runtime_error("spmm_b200: no CUDA device (no CPU fallback)");
-    return rank % count;
+    const char *e = std::getenv("SPMM_DEVICE_BASE");
+    const int base = e ? std::atoi(e) : 0;
+    return ((base + rank) % count + count) % count;
 }
 
 void validate(const SparseMatrix &m, const FatVector &v, int k)

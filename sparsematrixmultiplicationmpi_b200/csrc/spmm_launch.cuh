@@ -12,6 +12,7 @@
 // All of these can be overridden through spmm_tune_set() for measurement.
 #pragma once
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <unordered_map>
 
@@ -34,10 +35,13 @@ template <typename K>
 int kernel_info(K kern, int *ctas_per_sm, int threads = THREADS)
 {
     static std::mutex mu;
-    static std::unordered_map<const void *, KernelInfo> cache;
+    static std::map<std::pair<const void *, int>, KernelInfo> cache; // function attributes and occupancy are per device
+    int dev = 0;
+    SPMM_CUDA(cudaGetDevice(&dev));
     const void *fn = (const void *)kern;
+    const std::pair<const void *, int> key(fn, dev);
     std::lock_guard<std::mutex> lk(mu);
-    auto it = cache.find(fn);
+    auto it = cache.find(key);
     if (it == cache.end())
     {
         SPMM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
@@ -45,7 +49,7 @@ int kernel_info(K kern, int *ctas_per_sm, int threads = THREADS)
         SPMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, kern, threads, 0));
         if (ki.ctas_per_sm < 1)
             ki.ctas_per_sm = 1;
-        it = cache.emplace(fn, ki).first;
+        it = cache.emplace(key, ki).first;
     }
     *ctas_per_sm = it->second.ctas_per_sm;
     return SPMM_OK;

@@ -97,13 +97,14 @@ int launch_stream_t(const spmm_csr_s *A, const double *d_B, long long ldb, doubl
     auto kern = spmm_stream_kernel<K>;
     const size_t smem = (size_t)cap * K * sizeof(double);
     static std::mutex mu;
-    static size_t configured = 0;
+    static std::map<int, size_t> configured; // per device
     {
         std::lock_guard<std::mutex> lk(mu);
-        if (smem > configured && smem > 48 * 1024)
+        size_t &have = configured[A->device];
+        if (smem > have && smem > 48 * 1024)
         {
             SPMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
+            have = smem;
         }
     }
     kern<<<n_tiles, ST_TPB, smem, stream>>>(A->d_rowptr, A->d_colidx, A->d_vals, d_B, ldb, d_C, ldc, cuts, cap);

@@ -1135,10 +1135,10 @@ int launch_tiled_t(const spmm_csr_s *A, const double *d_B, long long ldb, double
         return SPMM_ERR_UNSUPPORTED;
     }
     static std::mutex mu;
-    static std::unordered_map<const void *, int> configured;
+    static std::map<std::pair<const void *, int>, int> configured; // function attributes are per device
     {
         std::lock_guard<std::mutex> lk(mu);
-        int &have = configured[(const void *)kern];
+        int &have = configured[{(const void *)kern, A->device}];
         if (!have)
         {
             SPMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
