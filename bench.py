@@ -469,12 +469,13 @@ def north_star_extras(spmm, torch, dist, dev, rank, world, timed, barrier):
     s0, e0 = spmm.partition_rows(n, world, rank)
     A = spmm.DeviceCSR.banded(n, npr, hb, seed=7, device=dev.index, row_begin=s0, row_end=e0)
     plan = spmm.RowWise(eng, n, k, A)
-    B_own = torch.randint(1, 101, (e0 - s0, k), device=dev).double()  # B sharded by rows like C
+    window, B_own = plan.alloc_window(dev)  # B sharded by rows like C: the rank's rows live inside its window buffer
+    B_own.copy_(torch.randint(1, 101, (e0 - s0, k), device=dev).double())
     C_own = torch.empty((e0 - s0, k), dtype=torch.float64, device=dev)
-    window, w0 = plan.exchange_halo(B_own)
-    t_halo = timed(lambda: plan.exchange_halo(B_own), 5)
+    w0 = plan.exchange_halo_inplace(window)
+    t_halo = timed(lambda: plan.exchange_halo_inplace(window), 5)
     t_kernel = timed(lambda: eng.multiply_window(A, window, w0, k, C_own), 10)
-    t_all = timed(lambda: plan.multiply_sharded(B_own, C_own), 5)
+    t_all = timed(lambda: eng.multiply_window(A, window, plan.exchange_halo_inplace(window), k, C_own), 5)
     t_gather = timed(lambda: plan.gather(C_own), 3)
     halo_bytes = (window.shape[0] - (e0 - s0)) * k * 8
     A.close()

@@ -196,31 +196,56 @@ class RowWise:
             self._halo = (spans, owners)
         return self._halo
 
-    def exchange_halo(self, B_own: torch.Tensor) -> tuple[torch.Tensor, int]:
-        """B_own = this rank's rows of B. Returns (window, first_row): the rows [first_row, first_row + len(window)) of B
-        that this rank's block reads, its own part copied locally, the rest received peer to peer from their owners."""
+    def window_range(self) -> tuple[int, int]:
+        """Rows [w0, w1) of B this rank keeps resident: the rows its block reads and the rows it owns."""
         spans, owners = self.halo_plan()
         lo, hi = spans[self.rank]
         bs, be = owners[self.rank]
-        assert B_own.shape[0] == be - bs
-        window = torch.empty((max(0, hi - lo + 1), self.k), dtype=B_own.dtype, device=B_own.device)
+        if hi < lo:
+            return bs, be
+        return min(lo, bs), max(hi + 1, be)
+
+    def alloc_window(self, device=None, dtype=torch.float64) -> tuple[torch.Tensor, torch.Tensor]:
+        """(window, own): one buffer for the rows window_range() of B and the view of the rows this rank owns. A caller
+        that produces its share of B straight into `own` (e.g. the C of the previous multiply) exchanges halos in place:
+        nothing but the halo rows is ever copied."""
+        w0, w1 = self.window_range()
+        bs, be = self.halo_plan()[1][self.rank]
+        window = torch.empty((w1 - w0, self.k), dtype=dtype, device=device if device is not None else self.compute.device)
+        return window, window[bs - w0:be - w0]
+
+    def exchange_halo_inplace(self, window: torch.Tensor) -> int:
+        """Fill the halo rows of `window` (allocated by alloc_window, own rows already in place) from their owners, peer to
+        peer; returns the first row of the window."""
+        spans, owners = self.halo_plan()
+        w0, w1 = self.window_range()
+        lo, hi = spans[self.rank]
+        bs, be = owners[self.rank]
         ops = []
         for q in range(self.P):
+            if q == self.rank:
+                continue
             qs, qe = owners[q]
-            a, b = max(lo, qs), min(hi + 1, qe)  # rows of mine that q owns
+            a, b = max(lo, qs), min(hi + 1, qe)  # rows I read that q owns
             if b > a:
-                if q == self.rank:
-                    window[a - lo:b - lo].copy_(B_own[a - bs:b - bs])
-                else:
-                    ops.append(dist.P2POp(dist.irecv, window[a - lo:b - lo], q, group=self.group))
+                ops.append(dist.P2POp(dist.irecv, window[a - w0:b - w0], q, group=self.group))
             qlo, qhi = spans[q]
-            a, b = max(qlo, bs), min(qhi + 1, be)  # rows of q's window that I own
-            if b > a and q != self.rank:
-                ops.append(dist.P2POp(dist.isend, B_own[a - bs:b - bs].contiguous(), q, group=self.group))
+            a, b = max(qlo, bs), min(qhi + 1, be)  # rows q reads that I own
+            if b > a:
+                ops.append(dist.P2POp(dist.isend, window[a - w0:b - w0], q, group=self.group))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
-        return window, lo
+        return w0
+
+    def exchange_halo(self, B_own: torch.Tensor) -> tuple[torch.Tensor, int]:
+        """B_own = this rank's rows of B (any buffer). Returns (window, first_row): the rows of B this rank's block reads,
+        its own part copied in, the rest received peer to peer from their owners. (alloc_window + exchange_halo_inplace
+        avoid the local copy.)"""
+        window, own = self.alloc_window(B_own.device, B_own.dtype)
+        assert B_own.shape[0] == own.shape[0]
+        own.copy_(B_own)
+        return window, self.exchange_halo_inplace(window)
 
     def multiply_sharded(self, B_own: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """C[start:end] from B sharded by rows: halo exchange, then the block multiply on the window."""

@@ -100,6 +100,11 @@ def _worker(rank, world, port, case, results):
         # B sharded by rows like C: halo exchange, then the block multiply on the window; gathered for the check
         bs, be = spmm.partition_rows(n, world, rank)
         out["row_sharded"] = row.gather(row.multiply_sharded(Bt[bs:be].clone()))
+        window, own = row.alloc_window(torch.device("cpu"))
+        own.copy_(Bt[bs:be])
+        w0 = row.exchange_halo_inplace(window)  # no local copy: the rank's rows already sit inside the window buffer
+        again = row.gather(eng.multiply_window(row.A, window, w0, k))
+        assert again is None if rank else torch.equal(again, out["row_sharded"])
         results[f"row_overlap_{rank}"] = extra["row_overlap"].numpy().copy()
         if rank == 0:
             results.update({name: t.numpy().copy() for name, t in out.items()})
