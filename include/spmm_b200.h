@@ -224,6 +224,10 @@ int spmm_add_device(int device, double *d_dst, const double *d_src, long long n_
 int spmm_copy_device(int device, void *d_dst, const void *d_src, long long bytes, void *stream);
 int spmm_fill_zero_device(int device, void *d_dst, long long bytes, void *stream);
 int spmm_device_sync(int device); /* wait for all work enqueued on `device` */
+/* Create the CUDA context of every visible device, start the host threads and (enable_peers != 0) enable peer access between
+ * all pairs of devices now instead of inside the first multiply: the one-off cost (seconds on an 8-GPU box) belongs to
+ * program start (the reference's MPI_Init, main.cpp:14), not to a timed call. Called by libspmm_entry.so when it is loaded. */
+int spmm_devices_init(int enable_peers);
 
 /* ---- partition formulas (bit-for-bit the reference's integer arithmetic) ---- */
 void spmm_partition_rows(int n_rows, int n_ranks, int rank, int *begin, int *end);           /* RowWise.cpp:26-29 */

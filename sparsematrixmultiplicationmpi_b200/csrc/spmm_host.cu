@@ -735,6 +735,33 @@ int spmm_peer_enable(int device, int peer)
     return SPMM_OK;
 }
 
+int spmm_devices_init(int enable_peers)
+{
+    int count = 0;
+    SPMM_CUDA(cudaGetDeviceCount(&count));
+    for (int d = 0; d < count; ++d)
+    {
+        SPMM_CUDA(cudaSetDevice(d));
+        SPMM_CUDA(cudaFree(nullptr)); // creates the primary context
+    }
+    for (int d = 0; enable_peers && d < count; ++d)
+        for (int p = 0; p < count; ++p)
+        {
+            int can = 0;
+            if (p == d || cudaDeviceCanAccessPeer(&can, d, p) != cudaSuccess || !can)
+                continue;
+            cudaSetDevice(d);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(p, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+            cudaGetLastError();
+        }
+    if (count)
+        SPMM_CUDA(cudaSetDevice(0));
+    pool(); // host threads
+    return SPMM_OK;
+}
+
 int spmm_host_threads(void) { return pool().threads(); }
 
 void spmm_host_parallel_for(int n, void (*fn)(int, void *), void *ctx)

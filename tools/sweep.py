@@ -82,6 +82,7 @@ def main():
     ap.add_argument("--k", default="4,64")
     ap.add_argument("--repeat", type=int, default=3, help="calls per entry point; the fastest is reported (the first one uploads A)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "results.csv"))
+    ap.add_argument("--append", action="store_true", help="add the rows to an existing CSV (one file over several launches at 1, 2, 4, 8 GPUs)")
     args = ap.parse_args()
     P, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
@@ -139,7 +140,7 @@ def main():
                     best = t if best is None else min(best, t)
                 serial_t = best
                 # device-resident kernel time of the same multiply, for the roofline columns
-                with spmm.DeviceCSR.from_host(M, dev, 0) as A:
+                with spmm.DeviceCSR.from_host(M, dev) as A:
                     dB = torch.from_numpy(v).cuda()
                     dC = torch.empty((M.numRows, k), dtype=torch.float64, device="cuda")
                     st = torch.cuda.current_stream().cuda_stream
@@ -175,9 +176,11 @@ def main():
         spmm.clear_cache()
     if rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
-        with open(args.out, "w", newline="") as f:
+        fresh = not (args.append and os.path.exists(args.out))
+        with open(args.out, "w" if fresh else "a", newline="") as f:
             w = csv.writer(f)
-            w.writerow(HEADER)
+            if fresh:
+                w.writerow(HEADER)
             w.writerows(rows)
         print("wrote", args.out)
     if P > 1:
