@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -343,11 +344,19 @@ FatVector sparseMatrixFatVectorMultiply(const SparseMatrix &sparseMatrix, const 
     const size_t n = (size_t)sparseMatrix.numRows;
     if (n == 0 || vecCols == 0)
         return FatVector(n, std::vector<double>((size_t)vecCols, 0.0));
+    static const bool timing = std::getenv("SPMM_HOST_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
     Shard &A = whole_matrix(sparseMatrix, device_for_rank(0));
+    const double t_shard = ms();
     const std::vector<const double *> B = row_pointers(fatVector, 0, (size_t)sparseMatrix.numCols, vecCols);
     FatVector out(n);
+    const double t_prep = ms();
     RowBuilder rb{&out, (size_t)vecCols};
     ok(spmm_multiply_host_sink(A.h, B.data(), vecCols, build_rows, &rb, SPMM_KERNEL_AUTO));
+    if (timing)
+        std::fprintf(stderr, "[spmm entry] shard lookup %.2f ms, row pointers + result header %.2f ms, multiply %.2f ms\n", t_shard,
+                     t_prep - t_shard, ms() - t_prep);
     return out;
 }
 

@@ -17,6 +17,8 @@
 // rank's device buffer over NVLink (peer access), and to bring the finished C down once.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -380,6 +382,10 @@ int host_multiply(spmm_csr_t A, const HostRows &B, int b0, int b1, int k, const 
         return rc;
     if (!(b_direct && c_direct))
         slabs = 1;
+    static const bool timing = getenv("SPMM_HOST_TIMING") != nullptr; // phase times of every call on stderr (diagnostics)
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+    double t_up = 0, t_kernel = 0;
     while (slabs > 1 && (k % slabs != 0 || (k / slabs) % 2 != 0))
         --slabs;
     slabs = std::max(1, std::min(slabs, 8));
@@ -406,10 +412,20 @@ int host_multiply(spmm_csr_t A, const HostRows &B, int b0, int b1, int k, const 
         }
         SPMM_CUDA(cudaEventRecord(up, A->stream_up));
         SPMM_CUDA(cudaStreamWaitEvent(A->stream, up, 0));
+        if (timing)
+        {
+            cudaStreamSynchronize(A->stream_up);
+            t_up = since();
+        }
         rc = launch(A->d_B, A->d_C, k0, ks, A->stream);
         if (rc)
             return rc;
         SPMM_CUDA(cudaEventRecord(done, A->stream));
+        if (timing)
+        {
+            cudaStreamSynchronize(A->stream);
+            t_kernel = since();
+        }
         SPMM_CUDA(cudaStreamWaitEvent(A->stream_down, done, 0));
         if (c_direct)
         {
@@ -431,6 +447,9 @@ int host_multiply(spmm_csr_t A, const HostRows &B, int b0, int b1, int k, const 
     if (e == cudaSuccess)
         e = cudaStreamSynchronize(A->stream);
     SPMM_CUDA(e);
+    if (timing)
+        fprintf(stderr, "[spmm host] upload done %.2f ms, kernel done %.2f ms, download done %.2f ms (last slab; %d slab%s, %s source, %s sink)\n",
+                t_up, t_kernel, since(), slabs, slabs > 1 ? "s" : "", b_direct ? "pinned" : "staged", c_direct ? "pinned" : "staged");
     return rc;
 }
 
