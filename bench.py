@@ -193,7 +193,7 @@ def entry_lib():
     return lib
 
 
-def entry_run(lib, strategy, P, host, B, k, steps, want_result=False, warmup=2):
+def entry_run(lib, strategy, P, host, B, k, steps, want_result=False, warmup=10):
     """C++ SparseMatrix + FatVector in, FatVector out, `steps` calls after the first: (first_call_s, mean_s, C or None)."""
     import ctypes as C
     out = np.empty((host.numRows, k)) if want_result else None

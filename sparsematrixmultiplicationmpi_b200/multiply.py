@@ -53,11 +53,11 @@ def clear_cache() -> None:
 
 def _fingerprint(m: SparseMatrix) -> int:
     """Cheap content check of a cache hit (the reference functions are pure: a matrix edited in place, or a new one
-    at a recycled address, must not meet the old shard): every array whole up to 64 Ki elements, else 64 Ki evenly
+    at a recycled address, must not meet the old shard): every array whole up to 4 Ki elements, else 4 Ki evenly
     spaced probes."""
     h = 0
     for a in (m.rowPtr, m.colIndices, m.values):
-        step = 1 if a.size <= (1 << 16) else a.size // (1 << 16)
+        step = 1 if a.size <= (1 << 12) else a.size // (1 << 12)
         h = hash((h, a[::step].tobytes(), a[-1:].tobytes()))
     return h
 

@@ -272,6 +272,8 @@ def test_auto_rebuilds_its_layouts_across_k(oracle):
     """One handle, AUTO, a sequence of k that crosses every layout boundary (8-column k-tile for k <= 8, 16-column above,
     chunks shared by 2 / 4 CTAs from k = 32 / 64, row kernels for odd k and k = 2): each result against the oracle."""
     n, nc, r, c, v, sym = gen.cop20k_A_shaped(n=30_000, nnz=600_000, nx=20, ny=25, seed=7)
+    _cabi.tune("reset", 0)
+    _cabi.tune("tiled.auto_after", 1)
     with spmm.DeviceCSR.from_coo_host(n, nc, r, c, v, sym) as A:
         host = A.download()
         for k in (64, 4, 2, 16, 6, 8, 128, 1, 32, 5, 64):
@@ -287,6 +289,7 @@ def test_auto_rebuilds_its_layouts_across_k(oracle):
             info = A.tile_info()
             if k in (4, 6, 8, 16, 32, 64, 128):
                 assert info["rows_per_tile"] > 0, (k, info)  # FEM-like rows: AUTO must have built a tile layout
+    _cabi.tune("reset", 0)
 
 
 def test_large_banded_vs_oracle_and_properties(oracle):
