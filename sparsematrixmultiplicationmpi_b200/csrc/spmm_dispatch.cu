@@ -118,7 +118,10 @@ int launch_rows(const spmm_csr_s *A, int row_begin, int row_end, long long nnz_l
     if (s.nv != 1)
         np = 1;
     np = std::max(1, std::min(np, 32 / s.kl));
-    int u = t.rows_unroll > 0 ? t.rows_unroll : (np >= 8 ? 1 : np >= 2 ? 2 : (s.nv >= 4 ? 2 : 4));
+    // B larger than L2 (gathers go to HBM): more rows in flight per team pay (cfg5: 25.5 -> 23.6 ms at unroll 4); B resident
+    // in L2 / L1 (cfg2): 2 is the measured optimum for wide pieces
+    const bool b_beyond_l2 = (long long)A->n_cols * kc * 8 > device_props(A->device).l2_bytes;
+    int u = t.rows_unroll > 0 ? t.rows_unroll : (np >= 8 ? 1 : np >= 2 ? 2 : (s.nv >= 4 ? (b_beyond_l2 ? 4 : 2) : 4));
     const bool sweep = t.rows_sweep > 0 && s.w == 2;
     if (sweep && t.rows_np > 0)
         np = std::max(1, std::min(t.rows_np, 32 / s.kl)); // sweep shapes allow NP > 1 with NV > 1
@@ -165,7 +168,20 @@ int launch_merge(spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, lo
     if (row_end <= row_begin || kc <= 0)
         return SPMM_OK;
     const Tuning &t = tuning();
-    const Shape s = pick_shape(d_B, ldb, d_C, ldc, kc);
+    Shape s = pick_shape(d_B, ldb, d_C, ldc, kc);
+    // The merge kernel is latency-bound at low occupancy on power-law matrices (ncu: 80 registers, 29 % of the warps resident,
+    // long-scoreboard stalls): one access per lane across a wider team keeps fewer registers per thread and more rows of B
+    // in flight per warp. cfg3 (R-MAT 2^22, k=32): 3.50 ms with 8 lanes x 2 accesses, 3.06 ms with 16 x 1 (gpurun_out/r2l_tune_cfg3.jsonl).
+    if (t.rows_kl <= 0 && t.rows_nv <= 0 && s.nv > 1)
+    {
+        const int kq = (kc + s.w - 1) / s.w;
+        if (kq <= 32)
+        {
+            s.kl = next_pow2(kq);
+            s.nv = 1;
+            s.tiles = 1;
+        }
+    }
     const int u = t.rows_unroll > 0 ? t.rows_unroll : (s.nv >= 4 ? 2 : 4);
     const long long total = (long long)(row_end - row_begin) + (nnz_hi - nnz_lo);
     long long items = t.merge_items > 0 ? t.merge_items : 512;

@@ -74,7 +74,9 @@ int launch_rows_full(const spmm_csr_s *A, const SpmmArgs &args, int tiles, int d
     a2.bounds = nullptr;
     const Tuning &tn = tuning();
     // enough rows for >= 16 tiles per CTA: deal tiles round-robin (L2-resident B window), else one chunk per CTA
-    const int tile = tn.rows_tile > 0 ? tn.rows_tile : SLOTS * 8;
+    // (tile height measured on cfg4, 2^25 banded rows x 32, k=16: 16.3 ms at 8 rows per team slot, 12.5 ms at 3 — short tiles keep
+    // the CTAs of a wave on neighbouring rows, whose B window they then share in L2; gpurun_out/r2l_tune_cfg4.jsonl)
+    const int tile = tn.rows_tile > 0 ? tn.rows_tile : SLOTS * 3;
     a2.tile_rows = (tn.rows_tile > 0 || (tn.rows_tile == 0 && rows >= grid * 16LL * tile)) ? tile : 0;
     if (a2.tile_rows)
         ;

@@ -84,7 +84,7 @@ def run_variants(name, sets, k, variants, iters, emit, nnz, n_rows, extra=None):
             A, B, C = sets[i % len(sets)]
             A.multiply(B.data_ptr(), k, C.data_ptr(), kernel, stream)
         try:
-            ms = time_launches(fn, iters, warmup=max(5, 2 * len(sets)))  # every set once: AUTO builds its layouts lazily
+            ms = time_launches(fn, iters, warmup=max(5, 10 * len(sets)))  # AUTO builds a handle's tile layout on its 9th multiply: outside the timing
         except Exception as e:  # unsupported shape for this k: report and go on
             emit({"config": name, "k": k, "variant": label, "error": str(e)[:200]})
             continue
