@@ -521,7 +521,61 @@ def north_star_extras(spmm, torch, dist, dev, rank, world, timed, barrier):
                 "kernel_plus_p2p_rank_order_reduce_ms": t_p2p, "one_gpu_kernel_ms": one5,
                 "kernel_speedup_vs_1gpu": one5 / t_k5, "all_in_speedup_vs_1gpu": one5 / best5,
                 "reduce_scatter_bus_GBs": (world - 1) / world * n5 * k5 * 8 / (t_rs * 1e-3) / 1e9}
-    out["north_star_scaling"] = {"cfg4_banded_32M_1B_k16": out_cfg4, "cfg5_uniform_8M_256M_k64": out_cfg5}
+    # ---- cfg3: R-MAT 2^22, 2^26 edges, k = 32 — equal non-zero ranges (NonZeroElement.cpp:24-39), only the rows cut by a
+    # range boundary exchanged peer to peer; beside it the same matrix in equal ROW blocks (one rank gets the hub rows) ----
+    k3 = 32
+    whole = spmm.DeviceCSR.rmat(22, 16 << 22, seed=11, device=dev.index)  # same seed: the same matrix on every rank
+    n3, nnz3 = whole.n_rows, whole.nnz
+    b3, e3 = spmm.partition_nnz(nnz3, world, rank)
+    first, last = whole.nnz_range_rows(b3, e3)
+    rp3 = whole.download().rowPtr
+    B3 = torch.randint(1, 101, (n3, k3), device=dev).double()
+    C3 = torch.empty((last - first + 1, k3), dtype=torch.float64, device=dev)
+
+    class RangeOfWhole:  # the rank's shard is a non-zero range of the resident CSR: no second copy of the matrix
+        device = dev
+
+        def multiply(self, A_, B_, k_, out_=None):
+            whole.multiply_nnz_range(b3, e3, first, last, B_.data_ptr(), k_, C3.data_ptr(), "auto", torch.cuda.current_stream().cuda_stream)
+            return C3
+
+    class RowsOf:
+        n_rows = last - first + 1
+
+    plan3 = spmm.NonZeroRanges(RangeOfWhole(), n3, k3, RowsOf(), first, last, bool(b3 > rp3[first]))
+    t_k3 = timed(lambda: plan3.multiply_local(B3), 5)
+    Cl = plan3.multiply_local(B3)
+    t_f3 = timed(lambda: plan3.fix_boundaries(Cl), 3)
+    t_all3 = timed(lambda: plan3.fix_boundaries(plan3.multiply_local(B3)), 5)
+    rs, re_ = spmm.partition_rows(n3, world, rank)
+    Cr = torch.empty((re_ - rs, k3), dtype=torch.float64, device=dev)
+    t_rows3 = timed(lambda: whole.multiply_rows(rs, re_, B3.data_ptr(), k3, Cr.data_ptr(), "rows", torch.cuda.current_stream().cuda_stream), 2, warm=1)
+    Cfull = torch.empty((n3, k3), dtype=torch.float64, device=dev)
+    one3 = timed_local(torch, lambda: whole.multiply(B3.data_ptr(), k3, Cfull.data_ptr(), "auto", torch.cuda.current_stream().cuda_stream), 5) if rank == 0 else 0.0
+    barrier()
+    one3 = float(_bcast(torch, dist, dev, one3))
+    whole.close()
+    del B3, C3, Cr, Cfull, Cl
+    torch.cuda.empty_cache()
+    out_cfg3 = {"strategy": "equal non-zero ranges, rows cut by a range boundary fixed up peer to peer in rank order", "n_rows": n3,
+                "nnz": nnz3, "k": k3, "kernel_ms": t_k3, "boundary_fixup_ms": t_f3, "kernel_plus_fixup_ms": t_all3,
+                "one_gpu_kernel_ms": one3, "kernel_speedup_vs_1gpu": one3 / t_k3, "all_in_speedup_vs_1gpu": one3 / t_all3,
+                "equal_row_blocks_row_kernel_ms": t_rows3}
+
+    # ---- the reference's own reading of column-wise (ColumnWise.cpp:25-48): B's k columns split across the ranks, on cfg2 ----
+    n2, nc2, r2, c2, v2, sym2 = build_workload(64)
+    with spmm.DeviceCSR.from_coo_host(n2, nc2, r2, c2, v2, sym2, device=dev.index) as A2:
+        slabs = spmm.ColumnSlabs(eng, 64, A2)
+        B2 = torch.randint(1, 101, (n2, 64), device=dev).double()
+        C2 = torch.zeros((n2, 64), dtype=torch.float64, device=dev)
+        t_slab_k = timed(lambda: eng.multiply_slab(A2, B2, 64, slabs.k_start, slabs.k_end - slabs.k_start, C2), 20, warm=12)
+        t_slab_all = timed(lambda: slabs.run(B2), 5)
+        one_slab = timed_local(torch, lambda: A2.multiply(B2.data_ptr(), 64, C2.data_ptr(), "auto", torch.cuda.current_stream().cuda_stream), 20, warm=12)
+    out_slabs = {"strategy": "k-slabs of B (the reference's reading): every rank multiplies all of A by k/P columns, slabs gathered on the root",
+                 "matrix": "cfg2", "k": 64, "kernel_ms": t_slab_k, "kernel_plus_gather_ms": t_slab_all, "one_gpu_kernel_ms_this_rank": one_slab}
+
+    out["north_star_scaling"] = {"cfg4_banded_32M_1B_k16": out_cfg4, "cfg5_uniform_8M_256M_k64": out_cfg5,
+                                 "cfg3_rmat_4M_64M_k32": out_cfg3, "cfg2_column_slabs_k64": out_slabs}
     out["parity_ok"] = multi_gpu_parity(spmm, torch, dist, dev, rank, world)
     return out
 

@@ -30,3 +30,15 @@ def test_reference_arm_prints_one_contract_line():
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
     assert d.get("gpu_launches", 0) == 0
+
+
+def test_plot_tool_writes_the_four_families(tmp_path):
+    """tools/plot_results.py: execution time, speed-up, performance, efficiency (the reference notebook's families) as SVG."""
+    out = tmp_path / "plots"
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "plot_results.py"), os.path.join(ROOT, "profiles", "r1_results.csv"),
+                          "--matrix", "cfg1", "--out", str(out)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr[-1000:]
+    names = sorted(os.listdir(out))
+    for family in ("execution_time", "speedup", "performance", "efficiency"):
+        assert any(family in n for n in names), names
+    assert open(out / names[0]).read().startswith("<svg")

@@ -38,6 +38,9 @@ def timed(fn, iters=40, warm=6):
     return a.elapsed_time(b) / iters * 1e3
 
 
+BOX = int(sys.argv[1]) if len(sys.argv) > 1 else 0  # box height of the tile layout (0 = the default, 16 rows)
+
+
 def main():
     k = 64
     n, nc, r, c, v, sym = gen.cop20k_A_shaped()
@@ -62,7 +65,7 @@ def main():
         sets = []
         for _ in range(3):
             Ad = spmm.DeviceCSR.from_coo_host(n, nc, hi, lo, v, sym, device=0)
-            info = Ad.build_tiles(-1, 0, k)
+            info = Ad.build_tiles(-1, BOX, k)
             sets.append((Ad, torch.randint(1, 101, (n, k), device="cuda").double(),
                          torch.empty((n, k), dtype=torch.float64, device="cuda")))
         host = sets[0][0].download()
@@ -72,7 +75,7 @@ def main():
             return timed(lambda i: sets[i % 3][0].multiply(sets[i % 3][1].data_ptr(), k, sets[i % 3][2].data_ptr(), kernel, stream))
         t_auto, t_rows = run("auto"), run("rows")
         from sparsematrixmultiplicationmpi_b200 import _cabi
-        print(json.dumps({"ordering": name, "bandwidth": bw, "tiles": info, "auto_us": t_auto, "rows_us": t_rows,
+        print(json.dumps({"ordering": name, "box_rows": BOX or 16, "bandwidth": bw, "tiles": info, "auto_us": t_auto, "rows_us": t_rows,
                           "auto_kernel": (_cabi.lib().spmm_last_kernel_name() or b"").decode()}), flush=True)
         for Ad, _, _ in sets:
             Ad.close()
