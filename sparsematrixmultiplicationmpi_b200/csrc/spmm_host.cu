@@ -217,41 +217,105 @@ int ensure_streams(spmm_csr_t A)
     return SPMM_OK;
 }
 
-// Pinned staging rings: RING_SLOTS chunks per direction, with one event per slot. A small ring instead of full mirrors of B
-// and C keeps the first call on a new matrix cheap (page-locking 124 MB costs tens of milliseconds; the reference calls each
-// function once per run), and the rings outlive the handles: a ring is borrowed for the duration of one host-buffer call and
-// goes back to its device's free list, so main()'s four functions (four shards per rank) page-lock once.
-struct Ring
+// Pinned staging rings: two slots per packing thread and direction, one event per slot. Small rings instead of full mirrors
+// of B and C keep the first call on a new matrix cheap (page-locking 124 MB costs tens of milliseconds; the reference calls
+// each function once per run). The slots are carved from one portable page-locked arena that spmm_devices_init allocates at
+// program start (outside every timed call; 8 rank-threads that each page-locked their own ring inside their first row-wise
+// call made that call 279 ms at -np 8); a lease that does not fit the arena page-locks its own memory and keeps it for later.
+constexpr int ARENA_SLOTS = 128; // 1 MB each
+struct Arena
 {
-    int device = 0;
     double *buf = nullptr;
-    cudaEvent_t ev[2 * RING_SLOTS] = {};
-    double *slot(int dir, int i) const { return buf + ((size_t)(dir * 2 * ring_workers() + i) * CHUNK_BYTES) / sizeof(double); }
-    cudaEvent_t event(int dir, int i) const { return ev[dir * RING_SLOTS + i]; }
+    bool used[ARENA_SLOTS] = {};
 };
 std::mutex g_ring_mu;
-std::vector<Ring *> g_rings_free;
+Arena g_arena;
 
-int borrow_ring(int device, Ring **out)
+struct Ring
 {
+    int device = -1, n_slots = 0; // slots per direction
+    double *buf = nullptr;
+    int arena_first = -1;         // >= 0: carved from the arena
+    cudaEvent_t ev[2 * RING_SLOTS] = {};
+    double *slot(int dir, int i) const { return buf + ((size_t)(dir * n_slots + i) * CHUNK_BYTES) / sizeof(double); }
+    cudaEvent_t event(int dir, int i) const { return ev[dir * RING_SLOTS + i]; }
+};
+std::vector<Ring *> g_rings_free; // private (non-arena) rings waiting for their next lease
+
+int arena_init()
+{
+    std::lock_guard<std::mutex> lk(g_ring_mu);
+    if (g_arena.buf)
+        return SPMM_OK;
+    SPMM_CUDA(cudaHostAlloc((void **)&g_arena.buf, (size_t)ARENA_SLOTS * CHUNK_BYTES, cudaHostAllocPortable));
+    return SPMM_OK;
+}
+
+// a ring with `want` slots per direction for work on `device`
+int borrow_ring(int device, int want, Ring **out)
+{
+    want = std::max(1, std::min(want, RING_SLOTS));
+    Ring *r = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_ring_mu);
-        for (size_t i = 0; i < g_rings_free.size(); ++i)
-            if (g_rings_free[i]->device == device)
+        if (g_arena.buf)
+        {
+            int run = 0;
+            for (int i = 0; i < ARENA_SLOTS && !r; ++i)
             {
-                *out = g_rings_free[i];
+                run = g_arena.used[i] ? 0 : run + 1;
+                if (run == 2 * want)
+                {
+                    r = new Ring();
+                    r->arena_first = i + 1 - run;
+                    r->buf = g_arena.buf + ((size_t)r->arena_first * CHUNK_BYTES) / sizeof(double);
+                    for (int j = r->arena_first; j <= i; ++j)
+                        g_arena.used[j] = true;
+                }
+            }
+        }
+        for (size_t i = 0; !r && i < g_rings_free.size(); ++i)
+            if (g_rings_free[i]->n_slots >= want)
+            {
+                r = g_rings_free[i];
                 g_rings_free.erase(g_rings_free.begin() + (long)i);
-                return SPMM_OK;
             }
     }
-    Ring *r = new Ring();
-    r->device = device;
-    cudaError_t e = cudaHostAlloc((void **)&r->buf, (size_t)4 * ring_workers() * CHUNK_BYTES, cudaHostAllocDefault); // 2 directions x 2 slots per worker
-    for (int i = 0; e == cudaSuccess && i < 2 * RING_SLOTS; ++i)
-        e = cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming);
+    cudaError_t e = cudaSuccess;
+    if (!r)
+    {
+        r = new Ring();
+        e = cudaHostAlloc((void **)&r->buf, (size_t)2 * want * CHUNK_BYTES, cudaHostAllocPortable);
+        r->n_slots = want;
+    }
+    if (r->arena_first >= 0)
+        r->n_slots = want;
+    if (e == cudaSuccess && r->device != device)
+    {
+        // events belong to a device: (re)create them for this lease's device
+        for (int i = 0; i < 2 * RING_SLOTS; ++i)
+            if (r->ev[i])
+            {
+                cudaEventDestroy(r->ev[i]);
+                r->ev[i] = nullptr;
+            }
+        for (int d = 0; d < 2 && e == cudaSuccess; ++d)
+            for (int i = 0; i < r->n_slots && e == cudaSuccess; ++i)
+                e = cudaEventCreateWithFlags(&r->ev[d * RING_SLOTS + i], cudaEventDisableTiming);
+        r->device = device;
+    }
     if (e != cudaSuccess)
     {
-        if (r->buf)
+        for (int i = 0; i < 2 * RING_SLOTS; ++i)
+            if (r->ev[i])
+                cudaEventDestroy(r->ev[i]);
+        if (r->arena_first >= 0)
+        {
+            std::lock_guard<std::mutex> lk(g_ring_mu);
+            for (int j = 0; j < 2 * r->n_slots; ++j)
+                g_arena.used[r->arena_first + j] = false;
+        }
+        else if (r->buf)
             cudaFreeHost(r->buf);
         delete r;
         return cuda_fail(e, "pinned staging ring", __FILE__, __LINE__);
@@ -263,6 +327,17 @@ void return_ring(Ring *r)
 {
     if (!r)
         return;
+    if (r->arena_first >= 0)
+    {
+        for (int i = 0; i < 2 * RING_SLOTS; ++i)
+            if (r->ev[i])
+                cudaEventDestroy(r->ev[i]);
+        std::lock_guard<std::mutex> lk(g_ring_mu);
+        for (int j = 0; j < 2 * r->n_slots; ++j)
+            g_arena.used[r->arena_first + j] = false;
+        delete r;
+        return;
+    }
     std::lock_guard<std::mutex> lk(g_ring_mu);
     g_rings_free.push_back(r);
 }
@@ -271,6 +346,9 @@ struct RingLease
     Ring *r = nullptr;
     ~RingLease() { return_ring(r); }
 };
+int rows_per_chunk(int k);
+// slots per direction a transfer of `rows` rows of k doubles can use: two per packing thread
+int ring_want(long long rows, int k);
 
 // One row into the pinned ring with streaming stores: the copy engine reads the chunk next, and lines left dirty in the packing
 // core's cache would have to be snooped out one by one (measured: the H2D of chunks packed with plain memcpy ran at 14 GB/s).
@@ -288,6 +366,11 @@ inline void pack_row(double *dst, const double *src, size_t bytes)
 }
 
 int rows_per_chunk(int k) { return (int)std::max<size_t>(1, CHUNK_BYTES / (sizeof(double) * (size_t)std::max(k, 1))); }
+int ring_want(long long rows, int k)
+{
+    const long long chunks = (rows + rows_per_chunk(k) - 1) / rows_per_chunk(k);
+    return 2 * (int)std::max<long long>(1, std::min<long long>({(long long)ring_workers(), (long long)pool().threads(), chunks}));
+}
 
 // Rows [r0, r1) of `src` (all k columns) -> the device image d (row r at d + r*k), enqueued on `s`. RING_WORKERS host threads
 // each take every RING_WORKERS-th chunk: pack it into one of their two ring slots (serialize(), utils.cpp:216-228), hand it
@@ -298,7 +381,7 @@ int staged_upload(const Ring &ring, int device, const HostRows &src, double *d, 
         return SPMM_OK;
     const int rpc = rows_per_chunk(k), n_chunks = (r1 - r0 + rpc - 1) / rpc;
     const size_t width = sizeof(double) * (size_t)k;
-    const int W = std::max(1, std::min({ring_workers(), pool().threads(), n_chunks}));
+    const int W = std::max(1, std::min({ring_workers(), pool().threads(), n_chunks, ring.n_slots / 2}));
     std::atomic<int> err{(int)cudaSuccess};
     static const bool timing = getenv("SPMM_HOST_TIMING") != nullptr;
     std::atomic<long long> ns_wait{0}, ns_pack{0}, ns_api{0}, ns_start{0};
@@ -352,7 +435,7 @@ int staged_download(const Ring &ring, int device, const double *d_c, int n, int 
         return SPMM_OK;
     const int rpc = rows_per_chunk(k), n_chunks = (n + rpc - 1) / rpc;
     const size_t width = sizeof(double) * (size_t)k;
-    const int W = std::max(1, std::min({ring_workers(), pool().threads(), n_chunks}));
+    const int W = std::max(1, std::min({ring_workers(), pool().threads(), n_chunks, ring.n_slots / 2}));
     auto issue = [&](int c, int slot) -> cudaError_t {
         const int c0 = c * rpc, c1 = std::min(n, c0 + rpc);
         cudaError_t e = cudaMemcpyAsync(ring.slot(1, slot), d_c + (size_t)c0 * k, width * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, s);
@@ -413,7 +496,7 @@ int host_multiply(spmm_csr_t A, const HostRows &B, int b0, int b1, int k, const 
     const bool b_direct = !B.rows && is_pinned(B.flat), c_direct = !sink && !C.rows && is_pinned(C.flat);
     RingLease lease;
     if (!rc && !(b_direct && c_direct))
-        rc = borrow_ring(A->device, &lease.r);
+        rc = borrow_ring(A->device, ring_want(std::max<long long>(b1 - b0, c_rows), k), &lease.r);
     if (rc)
         return rc;
     if (!(b_direct && c_direct))
@@ -622,7 +705,7 @@ int spmm_stage_b_rows(spmm_csr_t A, const double *const *B_rows, int row_begin, 
         rc = ensure_device(&A->d_B, &A->d_B_elems, nb);
     RingLease lease;
     if (!rc && row_end > row_begin)
-        rc = borrow_ring(A->device, &lease.r);
+        rc = borrow_ring(A->device, ring_want(row_end - row_begin, k), &lease.r);
     if (rc)
         return rc;
     SPMM_REQUIRE(B_rows != nullptr || row_end == row_begin, "B_rows is NULL");
@@ -653,7 +736,7 @@ int spmm_fetch_c_sink(spmm_csr_t A, const double *d_C, int n_rows, int k, spmm_r
     RingLease lease;
     int rc = ensure_streams(A);
     if (!rc)
-        rc = borrow_ring(A->device, &lease.r);
+        rc = borrow_ring(A->device, ring_want(n_rows, k), &lease.r);
     if (rc)
         return rc;
     rc = staged_download(*lease.r, A->device, d_C, n_rows, k, A->stream_down, sink, ctx);
@@ -684,7 +767,7 @@ int spmm_upload_dense(spmm_csr_t A, const double *src, long long n_rows, int k, 
     else
     {
         RingLease lease;
-        int rc = borrow_ring(A->device, &lease.r);
+        int rc = borrow_ring(A->device, ring_want(n_rows, k), &lease.r);
         HostRows b;
         b.flat = src;
         b.ld = k;
@@ -714,7 +797,7 @@ int spmm_download_dense(spmm_csr_t A, const double *d_src, long long n_rows, int
     else
     {
         RingLease lease;
-        rc = borrow_ring(A->device, &lease.r);
+        rc = borrow_ring(A->device, ring_want(n_rows, k), &lease.r);
         HostRowsOut c;
         c.flat = dst;
         c.ld = k;
@@ -812,7 +895,12 @@ int spmm_devices_init(int enable_peers)
             cudaGetLastError();
         }
     if (count)
+    {
         SPMM_CUDA(cudaSetDevice(0));
+        const int rc = arena_init(); // page-locked staging arena, shared by the rank-threads of the process
+        if (rc)
+            return rc;
+    }
     pool(); // host threads
     return SPMM_OK;
 }
