@@ -68,6 +68,7 @@ const int g_malloc_tuned = [] {
 // threads. The reference's main() times every function exactly once (main.cpp:77-79,161-163); its own one-off cost, MPI_Init,
 // is outside those timers too. Without a GPU nothing happens here and the first call reports the error.
 const int g_devices_ready = [] {
+    setenv("CUDA_MODULE_LOADING", "LAZY", 0); // (the CUDA 12 default, made explicit: eager loading of every kernel variant costs seconds per GPU)
     const char *off = std::getenv("SPMM_NO_EAGER_INIT");
     // (a process that was given one device of a multi-process launch, SPMM_DEVICE_BASE, leaves the other GPUs alone)
     if (!(off && *off == '1') && !std::getenv("SPMM_DEVICE_BASE"))
