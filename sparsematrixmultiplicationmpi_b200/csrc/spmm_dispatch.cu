@@ -169,19 +169,10 @@ int launch_merge(spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, lo
         return SPMM_OK;
     const Tuning &t = tuning();
     Shape s = pick_shape(d_B, ldb, d_C, ldc, kc);
-    // The merge kernel is latency-bound at low occupancy on power-law matrices (ncu: 80 registers, 29 % of the warps resident,
-    // long-scoreboard stalls): one access per lane across a wider team keeps fewer registers per thread and more rows of B
-    // in flight per warp. cfg3 (R-MAT 2^22, k=32): 3.50 ms with 8 lanes x 2 accesses, 3.06 ms with 16 x 1 (gpurun_out/r2l_tune_cfg3.jsonl).
-    if (t.rows_kl <= 0 && t.rows_nv <= 0 && s.nv > 1)
-    {
-        const int kq = (kc + s.w - 1) / s.w;
-        if (kq <= 32)
-        {
-            s.kl = next_pow2(kq);
-            s.nv = 1;
-            s.tiles = 1;
-        }
-    }
+    // Team shape: pick_shape's (8 lanes x 2 accesses at k = 32). Measured on cfg3 (R-MAT 2^22, k = 32) after the kernel was
+    // rebuilt around batches of KL non-zeros (coalesced id/value loads one batch ahead, B rows gathered 4 at a time whatever
+    // rows they belong to): 8 x 2 unroll 4 at 80 registers 2.17 ms, 16 x 1 2.34 ms, unroll 8 (127 registers) 4.5 ms
+    // (gpurun_out/s5_tune_mb1.jsonl); the row-by-row kernel before it took 3.06-3.50 ms.
     const int u = t.rows_unroll > 0 ? t.rows_unroll : (s.nv >= 4 ? 2 : 4);
     const long long total = (long long)(row_end - row_begin) + (nnz_hi - nnz_lo);
     long long items = t.merge_items > 0 ? t.merge_items : 512;

@@ -537,8 +537,19 @@ __device__ __forceinline__ void merge_path_search(const RowClip &rp, int row_beg
     y_out = (int)(diag - x_min);
 }
 
+// The merge kernel hides its gather latency with resident warps (measured on R-MAT: fewer registers and more warps beat deeper
+// unrolling, gpurun_out/s4_tune_cfg3.jsonl), so it asks for more CTAs per SM than the row kernel's estimate.
+#ifndef SPMM_MERGE_EXTRA_BLOCKS
+#define SPMM_MERGE_EXTRA_BLOCKS 1
+#endif
+constexpr int merge_min_blocks(int nv, int w, int u, int threads)
+{
+    const int mb = min_blocks(nv, w, u, 1, threads) + SPMM_MERGE_EXTRA_BLOCKS;
+    return mb > 8 ? 8 : mb;
+}
+
 template <int KL, int NV, int W, int U, bool FULL, int THREADS>
-__global__ void __launch_bounds__(THREADS, min_blocks(NV, W, U, 1, THREADS)) spmm_merge_kernel(const SpmmArgs a)
+__global__ void __launch_bounds__(THREADS, merge_min_blocks(NV, W, U, THREADS)) spmm_merge_kernel(const SpmmArgs a)
 {
     constexpr int RW = 32 / KL;
     using S = Slice<KL, NV, W>;
@@ -575,71 +586,92 @@ __global__ void __launch_bounds__(THREADS, min_blocks(NV, W, U, 1, THREADS)) spm
     acc.zero();
     // fresh = no earlier team consumed a non-zero of `row`
     bool fresh = row < a.row_end ? (j == rp(row)) : true;
+    // The team's items are walked in batches of up to U NON-ZEROS, whatever rows they belong to: their column ids,
+    // values and B rows are loaded before the row structure is looked at, so U gathers are in flight per team even
+    // where rows hold one or two entries (R-MAT: half the rows are empty, a fifth hold one or two). Row ends are
+    // consumed in path order between the FMAs; `re` / `re2` = end offsets of the open row and of the row after it
+    // (fetched one row ahead, so closing a row does not wait for memory).
+    int re = row < a.row_end ? rp(row + 1) : 0x7FFFFFFF;
+    int re2 = row + 1 < a.row_end ? rp(row + 2) : 0x7FFFFFFF;
+    auto close_row = [&]() {
+        if (fresh)
+        {
+            double *const cp = a.C + (long long)(row - a.c_row0) * a.ldc + tile0 + kl * W;
+            acc.store(cp, mask);
+            for (int d = 0; d < a.extra.n; ++d)
+                acc.store(cp + a.extra.off[d], mask);
+        }
+        else
+        {
+            acc.store_plain(carry_head);
+            head_row = row;
+        }
+        acc.zero();
+        fresh = true;
+        ++row;
+        --items;
+        re = re2;
+        re2 = row + 1 < a.row_end ? rp(row + 2) : 0x7FFFFFFF;
+    };
+    // A batch = KL consecutive non-zeros: lane kl of the team loads column id and value of non-zero j + kl (one coalesced
+    // request per team instead of one per non-zero), the next batch is requested before this one is worked on, and the
+    // B rows are gathered UU at a time with the ids passed around by shuffles inside the team.
+    constexpr int UU = U < KL ? U : KL;
+    const unsigned team_mask = KL == 32 ? 0xFFFFFFFFu : (((1u << KL) - 1u) << (lane - kl));
+    const int team_lane0 = lane - kl;
+    auto fetch = [&](int base, int &c_out, double &v_out) {
+        const int jj = max(min(base + kl, nnz_hi - 1), 0);
+        c_out = nnz_hi > 0 ? ld_stream_i32(a.colidx + jj) : 0;
+        v_out = nnz_hi > 0 ? ld_stream_f64(a.vals + jj) : 0.0;
+    };
+    int cc, cn;
+    double vv, vn;
+    fetch(j, cc, vv);
     while (items > 0 && row < a.row_end)
     {
-        const int row_end_j = rp(row + 1);
-        const int n = min(row_end_j - j, items);
-        const int je = j + n;
-        for (; j + U <= je; j += U)
+        const int nb = min(min(KL, items), nnz_hi - j); // non-zeros of this batch (0: only row ends are left)
+        if (nb <= 0)
         {
-            int c[U];
-            double xv[U];
-            S b[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-            {
-                c[u] = ld_stream_i32(a.colidx + j + u);
-                xv[u] = ld_stream_f64(a.vals + j + u);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                b[u].template load<FULL>(Bk + (long long)c[u] * a.ldb, mask);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                acc.fma(xv[u], b[u]);
+            close_row(); // j == nnz_hi: every remaining row ends here
+            continue;
         }
-        if (j < je)
+        fetch(j + nb, cn, vn);
+#pragma unroll
+        for (int g = 0; g < KL; g += UU)
         {
-            int c[U - 1];
-            double xv[U - 1];
-            S b[U - 1];
-#pragma unroll
-            for (int u = 0; u < U - 1; ++u)
+            if (g < nb)
             {
-                const int jj = min(j + u, je - 1);
-                c[u] = ld_stream_i32(a.colidx + jj);
-                xv[u] = ld_stream_f64(a.vals + jj);
+                int c[UU];
+                double xv[UU];
+                S b[UU];
+#pragma unroll
+                for (int u = 0; u < UU; ++u)
+                {
+                    c[u] = __shfl_sync(team_mask, cc, team_lane0 + g + u);
+                    xv[u] = __shfl_sync(team_mask, vv, team_lane0 + g + u);
+                }
+#pragma unroll
+                for (int u = 0; u < UU; ++u)
+                    b[u].template load<FULL>(Bk + (long long)c[u] * a.ldb, mask);
+#pragma unroll
+                for (int u = 0; u < UU; ++u)
+                {
+                    if (g + u < nb)
+                    {
+                        while (j >= re && items > 0) // the rows that end before this non-zero (row < row_end: the non-zero lies in one)
+                            close_row();
+                        if (items > 0)
+                        {
+                            acc.fma(xv[u], b[u]);
+                            ++j;
+                            --items;
+                        }
+                    }
+                }
             }
-#pragma unroll
-            for (int u = 0; u < U - 1; ++u)
-                b[u].template load<FULL>(Bk + (long long)c[u] * a.ldb, mask);
-#pragma unroll
-            for (int u = 0; u < U - 1; ++u)
-                if (j + u < je)
-                    acc.fma(xv[u], b[u]);
         }
-        j = je;
-        items -= n;
-        if (items > 0)
-        {
-            // the row-end item: this team closes `row`
-            if (fresh)
-            {
-                double *const cp = a.C + (long long)(row - a.c_row0) * a.ldc + tile0 + kl * W;
-                acc.store(cp, mask);
-                for (int d = 0; d < a.extra.n; ++d)
-                    acc.store(cp + a.extra.off[d], mask);
-            }
-            else
-            {
-                acc.store_plain(carry_head);
-                head_row = row;
-            }
-            acc.zero();
-            fresh = true;
-            ++row;
-            --items;
-        }
+        cc = cn;
+        vv = vn;
     }
     // ran out of items inside a row some of whose non-zeros are already consumed
     if (row < a.row_end && j > rp(row))

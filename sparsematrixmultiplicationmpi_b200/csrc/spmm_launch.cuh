@@ -299,6 +299,7 @@ int launch_merge_one(const SpmmArgs &args, int tiles, cudaStream_t stream)
 template <int KL, int NV, int W>
 int launch_merge_u(int u, const SpmmArgs &a, int tiles, cudaStream_t s)
 {
+    // (unroll 1 and 8 were measured on cfg3 and lost to 2 and 4: gpurun_out/s5_tune_mb1.jsonl)
     if (u >= 4)
         return launch_merge_one<KL, NV, W, 4>(a, tiles, s);
     return launch_merge_one<KL, NV, W, 2>(a, tiles, s);
