@@ -397,25 +397,44 @@ FatVector sparseMatrixFatVectorMultiplyRowWise(const SparseMatrix &sparseMatrix,
 
     if (kRanksShareProcess)
     {
+        static const bool timing = std::getenv("SPMM_HOST_TIMING") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
+        auto ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+        double t[8] = {};
         const int root_device = device_for_rank(0);
         double *root_C = root_buffer(root_device, n, k, worldRank);
+        t[0] = ms();
         Shard *mine = nullptr;
         if (end > start)
         {
             mine = &row_shard(sparseMatrix, device, start, end);
+            t[1] = ms();
             ok(spmm_peer_enable(device, root_device));
             const std::vector<const double *> B = row_pointers(fatVector, 0, (size_t)sparseMatrix.numCols, k);
+            t[2] = ms();
             const double *dB = nullptr;
             void *stream = nullptr;
             ok(spmm_stage_b_rows(mine->h, B.data(), mine->cmin, mine->cmax + 1, k, &dB, &stream)); // only the rows this block reads
+            t[3] = ms();
             double *dst = root_C + (size_t)start * (size_t)k;
             ok(spmm_multiply_scatter_device(mine->h, dB, k, 1, &dst, SPMM_KERNEL_AUTO, stream));
+            t[4] = ms();
             ok(spmm_csr_stream_sync(mine->h));
+            t[5] = ms();
         }
         MPI_Barrier(MPI_COMM_WORLD); // every block of C has landed in the root's buffer
+        t[6] = ms();
+        if (timing)
+            std::fprintf(stderr,
+                         "[spmm entry] row-wise rank %d: root buffer %.2f, shard %.2f, peer + row pointers %.2f, stage B %.2f, launch %.2f, "
+                         "sync %.2f, barrier %.2f ms (cumulative)\n",
+                         worldRank, t[0], t[1], t[2], t[3], t[4], t[5], t[6]);
         if (worldRank != 0)
             return FatVector{}; // RowWise.cpp:125
-        return fetch_result(mine->h, root_C, n, k);
+        FatVector out = fetch_result(mine->h, root_C, n, k);
+        if (timing)
+            std::fprintf(stderr, "[spmm entry] row-wise root: result fetched at %.2f ms\n", ms());
+        return out;
     }
 
     // ranks in different processes: multiply on the rank's GPU, Gatherv of the row blocks on host buffers (RowWise.cpp:63-87)
