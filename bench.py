@@ -508,6 +508,12 @@ def north_star_extras(spmm, torch, dist, dev, rank, world, timed, barrier):
     except Exception as e:
         t_p2p = None
         out["cfg5_p2p_error"] = str(e)[:200]
+    try:
+        t_push = timed(lambda: planb.multiply_reduce_scatter_push(Bl, mine), 3)
+    except Exception as e:
+        t_push = None
+        out["cfg5_push_error"] = str(e)[:200]
+    planb._symm = planb._symm_push = None
     Ab.close()
     del partial, mine, Bl, planb
     torch.cuda.empty_cache()
@@ -515,10 +521,11 @@ def north_star_extras(spmm, torch, dist, dev, rank, world, timed, barrier):
     one5 = cfg5_single() if rank == 0 else 0.0
     barrier()
     one5 = float(_bcast(torch, dist, dev, one5))
-    best5 = min(x for x in (t_all5, t_p2p) if x)
+    best5 = min(x for x in (t_all5, t_p2p, t_push) if x)
     out_cfg5 = {"strategy": "column blocks of A, partial C summed by reduce-scatter over NVLink", "n_rows": n5, "nnz": nnz5,
                 "k": k5, "kernel_ms": t_k5, "reduce_scatter_nccl_ms": t_rs, "kernel_plus_reduce_scatter_nccl_ms": t_all5,
-                "kernel_plus_p2p_rank_order_reduce_ms": t_p2p, "one_gpu_kernel_ms": one5,
+                "kernel_plus_p2p_rank_order_reduce_ms": t_p2p, "fused_peer_store_multiply_plus_local_reduce_ms": t_push,
+                "one_gpu_kernel_ms": one5,
                 "kernel_speedup_vs_1gpu": one5 / t_k5, "all_in_speedup_vs_1gpu": one5 / best5,
                 "reduce_scatter_bus_GBs": (world - 1) / world * n5 * k5 * 8 / (t_rs * 1e-3) / 1e9}
     # ---- cfg3: R-MAT 2^22, 2^26 edges, k = 32 — equal non-zero ranges (NonZeroElement.cpp:24-39), only the rows cut by a
@@ -618,6 +625,11 @@ def multi_gpu_parity(spmm, torch, dist, dev, rank, world) -> bool:
     results["row_wise_p2p"] = row.run_p2p(Bd)
     blk = spmm.ColumnBlocks.from_host(eng, host, k)
     results["column_blocks"] = blk.run(blk.local_B(Bd))
+    # the fused variant (the kernel stores every row block into its owner's slots over NVLink, local rank-order sum)
+    counts = [max(0, min(blk.block, n - r_ * blk.block)) for r_ in range(world)]
+    from sparsematrixmultiplicationmpi_b200.strategies import _gather_rows_to_root
+    results["column_blocks_fused_peer_stores"] = _gather_rows_to_root(
+        blk.multiply_reduce_scatter_push(blk.local_B(Bd))[:counts[rank]], counts, k, None)
     results["non_zero_ranges"] = spmm.NonZeroRanges.from_host(eng, host, k).run(Bd)
     torch.cuda.synchronize()
     ok = True

@@ -394,6 +394,39 @@ class ColumnBlocks:
                             self.block * self.k, out.data_ptr(), torch.cuda.current_stream(B_local.device).cuda_stream)
         return out
 
+    def multiply_reduce_scatter_push(self, B_local: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """This rank's block of C with the exchange fused into the multiply: the partial of row block o is not written to
+        local memory and reduce-scattered afterwards, it is STORED BY THE SPMM KERNEL straight into slot `rank` of a
+        staging buffer on rank o (symmetric memory, peer stores over NVLink / NVSwitch), one launch per destination in
+        ring order (rank p starts with block p+1, so every GPU receives from one sender at a time). After one barrier each
+        rank adds its P local slots in ascending rank order (spmm_reduce_blocks_device on local pointers): the same
+        deterministic sum as the pull variant, with the NVLink traffic overlapped by the arithmetic of the next block and
+        no partial C written to and read back from HBM (replaces the collective of ColumnWise.cpp:82-84)."""
+        if self.P == 1 or self.P > 8 or (self.block * self.k) % 2:
+            return self.reduce_scatter(self.multiply_local(B_local), out)
+        if getattr(self, "_symm_push", None) is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            group = self.group if self.group is not None else dist.group.WORLD
+            buf = symm_mem.empty((self.P, self.block, self.k), dtype=torch.float64, device=B_local.device)
+            buf.zero_()  # (rows past n_rows in the last block are never written: they stay zero)
+            self._symm_push = (buf, symm_mem.rendezvous(buf, group))
+        slots, hdl = self._symm_push
+        if out is None:
+            out = torch.empty((self.block, self.k), dtype=torch.float64, device=B_local.device)
+        stream = torch.cuda.current_stream(B_local.device).cuda_stream
+        slot_bytes = self.block * self.k * 8
+        hdl.barrier(channel=0)  # nobody still adds up the slots of the previous call
+        for step in range(self.P):
+            o = (self.rank + 1 + step) % self.P  # the own block last: its stores are local
+            r0, r1 = min(self.n_rows, o * self.block), min(self.n_rows, (o + 1) * self.block)
+            if r1 > r0:
+                self.A.multiply_rows(r0, r1, B_local.data_ptr(), self.k, int(hdl.buffer_ptrs[o]) + self.rank * slot_bytes, "auto", stream)
+        hdl.barrier(channel=0)  # every sender's rows have landed in this rank's slots
+        base = slots.data_ptr()
+        _cabi.reduce_blocks(B_local.device.index, [base + q * slot_bytes for q in range(self.P)], self.block * self.k,
+                            out.data_ptr(), stream)
+        return out
+
     def multiply_reduce_scatter_overlapped(self, B_local: torch.Tensor, chunks: int = 4) -> torch.Tensor:
         """Same result as reduce_scatter(multiply_local(B)) — this rank's block of C — but the partial
         C is produced in reduce-scatter chunk order: for chunk c the rows c*cb..(c+1)*cb of EVERY rank's

@@ -55,6 +55,10 @@ def main():
         want = ref[r0:r0 + cb.block]
         assert np.all(np.abs(mine_p2p[:want.shape[0]] - want) <= 1e-12 * np.abs(want)), f"rank {rank}: p2p reduce mismatch k={k}"
         assert np.all(np.abs(mine_p2p - mine_nccl) <= 1e-12 * np.abs(mine_nccl) + 1e-300)
+        # the exchange fused into the multiply (peer stores into the owner's slots, local rank-order sum): the same bits
+        for _ in range(2):
+            mine_push = cb.multiply_reduce_scatter_push(Bl).cpu().numpy()
+        assert np.array_equal(mine_push, mine_p2p), f"rank {rank}: fused peer-store reduce differs from the pull variant at k={k}"
         dist.barrier()
     if rank == 0:
         print("p2p ok: world", P)
