@@ -334,6 +334,14 @@ def main():
     wall = time.perf_counter() - t_wall
     clocks = sampler.stop()
     ms_per_step = tmax(ev0.elapsed_time(ev1)) / args.steps
+    # beside it ("both L2-warm and L2-flushed"): the same launches on ONE operand set, whatever fits stays in L2
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
+    for i in range(args.steps):
+        step(0)
+    w1.record()
+    barrier()
+    warm_ms_per_step = tmax(w0.elapsed_time(w1)) / args.steps
     flops_per_step = 2.0 * NNZ * k * world
     value = flops_per_step / (ms_per_step * 1e-3) / 1e9
 
@@ -398,6 +406,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "e2e_first_call": e2e_first, "e2e_pinned": e2e_pinned,
                 "gpu_launches": launches_per_step * args.steps,
                 "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": wall,
+                "l2_warm_ms_per_step": warm_ms_per_step,
                 "hbm_gbs_per_gpu": achieved, "kernel_arg": args.kernel}
         line.update(extras)
         emit(line)
