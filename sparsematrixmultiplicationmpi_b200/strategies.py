@@ -402,6 +402,8 @@ class ColumnBlocks:
         rank adds its P local slots in ascending rank order (spmm_reduce_blocks_device on local pointers): the same
         deterministic sum as the pull variant, with the NVLink traffic overlapped by the arithmetic of the next block and
         no partial C written to and read back from HBM (replaces the collective of ColumnWise.cpp:82-84)."""
+        if self.P > 1 and not B_local.is_cuda:
+            return self._push_host(B_local, out)
         if self.P == 1 or self.P > 8 or (self.block * self.k) % 2:
             return self.reduce_scatter(self.multiply_local(B_local), out)
         if getattr(self, "_symm_push", None) is None:
@@ -425,6 +427,32 @@ class ColumnBlocks:
         base = slots.data_ptr()
         _cabi.reduce_blocks(B_local.device.index, [base + q * slot_bytes for q in range(self.P)], self.block * self.k,
                             out.data_ptr(), stream)
+        return out
+
+    def _push_host(self, B_local: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """The data flow of multiply_reduce_scatter_push on host tensors (gloo): row block o of this rank's partial goes to
+        slot `rank` on rank o (send / receive instead of peer stores), the slots are added in ascending rank order."""
+        slots = torch.zeros((self.P, self.block, self.k), dtype=torch.float64)
+        ops, keep = [], []
+        for step in range(self.P):
+            o = (self.rank + 1 + step) % self.P
+            r0, r1 = min(self.n_rows, o * self.block), min(self.n_rows, (o + 1) * self.block)
+            part = slots[self.rank] if o == self.rank else torch.zeros((self.block, self.k), dtype=torch.float64)
+            if r1 > r0:
+                self.compute.multiply_rows(self.A, r0, r1, B_local, self.k, part[:r1 - r0])
+            if o != self.rank:
+                keep.append(part)
+                ops.append(dist.P2POp(dist.isend, part, o, group=self.group))
+        for q in range(self.P):
+            if q != self.rank:
+                ops.append(dist.P2POp(dist.irecv, slots[q], q, group=self.group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        if out is None:
+            out = torch.empty((self.block, self.k), dtype=torch.float64)
+        out.copy_(slots[0])
+        for q in range(1, self.P):
+            out += slots[q]
         return out
 
     def multiply_reduce_scatter_overlapped(self, B_local: torch.Tensor, chunks: int = 4) -> torch.Tensor:

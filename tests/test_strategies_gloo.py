@@ -96,6 +96,15 @@ def _worker(rank, world, port, case, results):
                  "colblk_plain": blk.reduce_scatter(blk.multiply_local(blk.local_B(Bt))),
                  "row_overlap": row.multiply_all_gather_overlapped(Bt, chunks=3)}
         assert torch.equal(extra["colblk_overlap"], extra["colblk_plain"])  # same sums in the same order
+        # the exchange fused into the multiply (on the GPU: peer stores; here: its host mirror): every row block lands in its
+        # owner's slot `sender`, the slots are added in ascending rank order
+        pushed = blk.multiply_reduce_scatter_push(blk.local_B(Bt))
+        partials = [torch.empty((blk.block * world, k), dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(partials, blk.multiply_local(blk.local_B(Bt)))
+        want = partials[0][rank * blk.block:(rank + 1) * blk.block].clone()
+        for q in range(1, world):
+            want += partials[q][rank * blk.block:(rank + 1) * blk.block]
+        assert torch.equal(pushed, want)
         out["nnz"] = spmm.NonZeroRanges.from_host(eng, m, k).run(Bt)
         # B sharded by rows like C: halo exchange, then the block multiply on the window; gathered for the check
         bs, be = spmm.partition_rows(n, world, rank)
