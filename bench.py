@@ -472,6 +472,19 @@ def north_star_extras(spmm, torch, dist, dev, rank, world, timed, barrier):
                                        "frac_measured_peak": gbs(n, nnz, k, ms4) / peak},
             "cfg5_uniform_8M_256M_k64": {"kernel_ms": ms5, "gflops": 2.0 * nnz5 * k5 / (ms5 * 1e-3) / 1e9,
                                          "frac_measured_peak": gbs(n5, nnz5, k5, ms5) / peak}}
+        # beside the algorithmic-bytes fraction: what the hardware actually moves per launch (RECORDED ncu traffic of the same
+        # kernels, profiles/traffic.json) over this run's time — cfg5 runs at the HBM peak, cfg4 and cfg3 at the L2 -> SM cap
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                rec = json.load(f).get("configs_1gpu", {})
+            for name, entry in out["configs_1gpu"].items():
+                r = rec.get(name)
+                if r:
+                    t = entry["kernel_ms"] * 1e-3
+                    entry["recorded_traffic"] = {"dram_GBs": r["dram_bytes"] / t / 1e9, "dram_frac_measured_peak": r["dram_bytes"] / t / 1e9 / peak,
+                                                 "l2_to_sm_GBs": r["l2_to_sm_bytes"] / t / 1e9, "source": "recorded: " + r["source"]}
+        except Exception:
+            pass
         return out
 
     # ---- world > 1 ----
