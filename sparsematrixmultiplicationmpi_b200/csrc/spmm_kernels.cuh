@@ -169,6 +169,29 @@ struct Slice
             for (int w = 0; w < W; ++w)
                 v[i * W + w] += p[i * KL * W + w];
     }
+    __device__ __forceinline__ void load_plain(const double *p) // volatile: a group of these is issued back to back
+    {
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+        {
+            if constexpr (W == 2)
+                asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v[2 * i]), "=d"(v[2 * i + 1]) : "l"(p + i * KL * W));
+            else
+                asm volatile("ld.global.f64 %0, [%1];" : "=d"(v[i]) : "l"(p + i * KL * W));
+        }
+    }
+    __device__ __forceinline__ void add(const Slice &b)
+    {
+#pragma unroll
+        for (int i = 0; i < NV * W; ++i)
+            v[i] += b.v[i];
+    }
+    __device__ __forceinline__ void add_if(const Slice &b, bool c) // (adds +0.0 otherwise: no branch around the loads)
+    {
+#pragma unroll
+        for (int i = 0; i < NV * W; ++i)
+            v[i] += c ? b.v[i] : 0.0;
+    }
     __device__ __forceinline__ void fma(double a, const Slice &b)
     {
 #if defined(SPMM_ABLATE) && (SPMM_ABLATE & 64) // diagnostic: one integer op per loaded double instead of a DFMA
@@ -689,7 +712,7 @@ __global__ void __launch_bounds__(THREADS, merge_min_blocks(NV, W, U, THREADS)) 
 // One team per carry slot. The first slot of a row's run sums the run in slot order
 // and stores the row. Used slots of one row are at most one unused slot apart.
 template <int KL, int NV, int W, int THREADS>
-__global__ void __launch_bounds__(THREADS) spmm_merge_fixup_kernel(const SpmmArgs a)
+__global__ void __launch_bounds__(THREADS, 2) spmm_merge_fixup_kernel(const SpmmArgs a)
 {
     constexpr int RW = 32 / KL;
     using S = Slice<KL, NV, W>;
@@ -713,23 +736,54 @@ __global__ void __launch_bounds__(THREADS) spmm_merge_fixup_kernel(const SpmmArg
     const int tile0 = blockIdx.y * S::TILE;
     const unsigned mask = slice_mask<KL, NV, W>(tile0, kl, a.kc);
     const double *cp = a.carry + tile0 + kl * W;
-    S acc;
+    // The run is walked eight slots at a time: eight row ids are loaded together, then the eight slots (unconditional loads
+    // from clamped, always valid slots) and those that belong to the run are added into four partial sums, folded in a fixed
+    // order at the end — deterministic, and a hub row cut by a thousand teams no longer costs a thousand dependent memory
+    // round trips (the fix-up of cfg3's first non-zero range took 752 us against 212 us for the multiply itself).
+    S acc, part[4];
     acc.zero();
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        part[t].zero();
     acc.add_plain(cp + s * (long long)a.ldcarry);
     int gap = 0;
-    for (long long q = s + 1; q < n_slots && gap < 2; ++q)
+    bool open = true;
+    for (long long q = s + 1; open && q < n_slots; q += 8)
     {
-        const int r = a.carry_row[q];
-        if (r == row)
+        long long qi[8];
+        int r[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            qi[t] = min(q + t, n_slots - 1);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) // (volatile: issued back to back, in this order, before anything waits for one of them)
+            asm volatile("ld.global.s32 %0, [%1];" : "=r"(r[t]) : "l"(a.carry_row + qi[t]));
+        bool take[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
         {
-            acc.add_plain(cp + q * (long long)a.ldcarry);
-            gap = 0;
+            const bool inside = q + t < n_slots;
+            const bool mine = open && inside && r[t] == row;
+            const bool unused = open && inside && r[t] == -1;
+            take[t] = mine;
+            gap = mine ? 0 : (unused ? gap + 1 : gap);
+            open = open && inside && (mine || (unused && gap < 2));
         }
-        else if (r < 0)
-            ++gap;
-        else
-            break;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+        {
+            S x[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                x[t].load_plain(cp + qi[4 * h + t] * (long long)a.ldcarry);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                part[t].add_if(x[t], take[4 * h + t]);
+        }
     }
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        acc.add(part[t]);
     double *const dst = a.C + (long long)(row - a.c_row0) * a.ldc + tile0 + kl * W;
     acc.store(dst, mask);
     for (int d = 0; d < a.extra.n; ++d)
