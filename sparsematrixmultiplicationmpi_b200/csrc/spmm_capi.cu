@@ -270,6 +270,7 @@ int spmm_tune_set(const char *key, int value)
     else if (k == "rows.vec") t.rows_vec = value;
     else if (k == "rows.ctas_per_sm") t.rows_ctas_per_sm = value;
     else if (k == "merge.items") t.merge_items = value;
+    else if (k == "merge.wave") t.merge_wave = value;
     else if (k == "reset") t = Tuning();
     else
     {

@@ -177,7 +177,11 @@ int launch_merge(spmm_csr_s *A, int row_begin, int row_end, long long nnz_lo, lo
     const long long total = (long long)(row_end - row_begin) + (nnz_hi - nnz_lo);
     long long items = t.merge_items > 0 ? t.merge_items : 512;
     // enough teams to fill the machine, few enough that the carry rows stay a small fraction of C
-    const long long teams_per_wave = (long long)device_props(A->device).sm_count * 64 * (32 / s.kl);
+    // (a shard of long rows — the first non-zero range of an R-MAT matrix averages 477 per row — is cut less finely: every
+    // team inside a row leaves a carry slot and the fix-up walks them in order; measured per range in gpurun_out/s28_*)
+    const double avg_row = (double)(nnz_hi - nnz_lo) / std::max(1, row_end - row_begin);
+    const int wave = t.merge_wave > 0 ? t.merge_wave : (avg_row > 256.0 ? 32 : 64);
+    const long long teams_per_wave = (long long)device_props(A->device).sm_count * wave * (32 / s.kl);
     while (items > 64 && (total + items - 1) / items < teams_per_wave)
         items >>= 1;
     const long long n_teams = std::max(1LL, (total + items - 1) / items);

@@ -54,6 +54,7 @@ struct Tuning
     int rows_vec = 0;       // 1 forces 8-byte accesses
     int rows_ctas_per_sm = 0;
     int merge_items = 0;    // merge-path items per team
+    int merge_wave = 0;     // merge-path: warps per SM the item count is shrunk for on small shards (0 = 64)
     int rows_sweep = 0;     // 1: one CTA per SM walks the column tiles itself (L1-resident window)
     int rows_threads = 0;   // sweep kernels: 512 or 1024 threads
     int rows_tile = 0;      // 0 auto, > 0 rows per round-robin tile, -1 never tile (one chunk per CTA)

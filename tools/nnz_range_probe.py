@@ -7,6 +7,11 @@ import torch
 import sparsematrixmultiplicationmpi_b200 as spmm
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+if len(sys.argv) > 2:  # e.g. merge.items=512
+    from sparsematrixmultiplicationmpi_b200 import _cabi
+    for kv in sys.argv[2:]:
+        key, val = kv.split("=")
+        _cabi.tune(key, int(val))
 A = spmm.DeviceCSR.rmat(22, 16 << 22, seed=11)
 n, k = A.n_rows, 32
 B = torch.randint(1, 101, (n, k), device="cuda").double()
