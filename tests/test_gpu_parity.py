@@ -93,6 +93,25 @@ def test_team_shape_overrides(oracle, tune, kernel):
     assert_close_rel(got, oracle.spmm(rp, ci, va, B, 64), tol=REL_TOL)
 
 
+@pytest.mark.parametrize("k", [1, 5, 32, 64])
+@pytest.mark.parametrize("tune", [{}, {"merge.wave": 4}, {"merge.wave": 64, "merge.items": 64}])
+def test_merge_long_rows_only(oracle, k, tune):
+    """A shard whose rows average far more than 256 non-zeros (the first non-zero range of an R-MAT matrix): the merge-path
+    kernel cuts it into fewer teams, and every row is a run of many carry slots that the fix-up walks eight at a time
+    (runs of 1 to ~400 slots here, with and without unused slots between them), next to a few empty rows."""
+    rng = np.random.default_rng(41)
+    n, nc = 40, 6000
+    lens = rng.integers(300, 3000, n)
+    lens[[3, 17, 18]] = 0
+    lens[7] = 25000
+    rp = np.concatenate(([0], np.cumsum(lens))).astype(np.int32)
+    ci = np.concatenate([np.sort(rng.integers(0, nc, int(l))) for l in lens]).astype(np.int32) if rp[-1] else np.zeros(0, np.int32)
+    va = 0.5 + rng.random(int(rp[-1]))
+    B = rng.integers(1, 101, (nc, k)).astype(np.float64)
+    got = gpu_multiply(spmm.SparseMatrix(va, ci, rp, n, nc), B, k, "merge", tune)
+    assert_close_rel(got, oracle.spmm(rp, ci, va, B, k), tol=REL_TOL)
+
+
 @pytest.mark.parametrize("np_", [1, 2, 4, 8, 16, 32])
 @pytest.mark.parametrize("k", [1, 2, 4, 8])
 def test_side_by_side_nonzeros(oracle, np_, k):
