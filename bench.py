@@ -370,8 +370,9 @@ def main():
                   "vector<vector<double>> in and out, A cached in HBM after the first call",
            "host_threads": int(os.environ["SPMM_HOST_THREADS"])}
     e2e_first = {"value": flops_per_step / first_s / 1e9, "unit": "GFLOP/s", "ms": first_s * 1e3,
-                 "what": "first call on a new matrix: upload of A (32 MB), pinned staging ring, CSR row kernel (AUTO builds the tile "
-                         "layout only when a handle is multiplied again), transfers as above — the reference's one-call-per-run pattern (main.cpp:78)"}
+                 "what": "first call on a new matrix: upload of A (32 MB), CSR row kernel (AUTO builds the tile layout only when a handle "
+                         "is multiplied again), transfers as above — the reference's one-call-per-run pattern (main.cpp:78); the page-locked "
+                         "staging arena and the kernel modules were set up when libspmm_entry.so was loaded (the place of MPI_Init)"}
     # the flat C-ABI call with pinned host buffers (no pack / unpack): what a caller that owns row-major storage gets
     Bp = torch.randint(1, 101, (n, k)).double().pin_memory()
     Cp = torch.empty((n, k), dtype=torch.float64).pin_memory()

@@ -228,6 +228,9 @@ int spmm_device_sync(int device); /* wait for all work enqueued on `device` */
  * all pairs of devices now instead of inside the first multiply: the one-off cost (seconds on an 8-GPU box) belongs to
  * program start (the reference's MPI_Init, main.cpp:14), not to a timed call. Called by libspmm_entry.so when it is loaded. */
 int spmm_devices_init(int enable_peers);
+/* The same for ONE device (a process that was given one GPU of a multi-process launch leaves the others alone): context, host
+ * threads, the page-locked staging arena, and one tiny multiply per kernel module (CUDA loads a module at its first launch). */
+int spmm_device_init(int device);
 
 /* ---- partition formulas (bit-for-bit the reference's integer arithmetic) ---- */
 void spmm_partition_rows(int n_rows, int n_ranks, int rank, int *begin, int *end);           /* RowWise.cpp:26-29 */

@@ -75,6 +75,7 @@ PROTOTYPES = {
     "spmm_copy_device": (_i, [_i, _p, _p, _ll, _p]),
     "spmm_device_sync": (_i, [_i]),
     "spmm_devices_init": (_i, [_i]),
+    "spmm_device_init": (_i, [_i]),
     "spmm_fill_zero_device": (_i, [_i, _p, _ll, _p]),
     "spmm_csr_tile_info": (_i, [_p, _pi, _pi, _pi, _pi, _pd, _pd]),
     "spmm_multiply_device": (_i, [_p, _p, _i, _p, _i, _p]),

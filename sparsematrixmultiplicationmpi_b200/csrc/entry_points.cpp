@@ -71,7 +71,15 @@ const int g_devices_ready = [] {
     setenv("CUDA_MODULE_LOADING", "LAZY", 0); // (the CUDA 12 default, made explicit: eager loading of every kernel variant costs seconds per GPU)
     const char *off = std::getenv("SPMM_NO_EAGER_INIT");
     // (a process that was given one device of a multi-process launch, SPMM_DEVICE_BASE, leaves the other GPUs alone)
-    if (!(off && *off == '1') && !std::getenv("SPMM_DEVICE_BASE"))
+    if (off && *off == '1')
+        return 1;
+    if (const char *base = std::getenv("SPMM_DEVICE_BASE"))
+    {
+        int count = 0;
+        if (spmm_device_count(&count) == SPMM_OK && count > 0)
+            spmm_device_init(((std::atoi(base) % count) + count) % count); // this process's GPU only
+    }
+    else
         spmm_devices_init(kRanksShareProcess ? 1 : 0);
     return 1;
 }();

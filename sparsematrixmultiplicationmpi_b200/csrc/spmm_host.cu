@@ -873,6 +873,37 @@ int spmm_peer_enable(int device, int peer)
     return SPMM_OK;
 }
 
+namespace
+{
+bool warmup_wanted()
+{
+    const char *e = getenv("SPMM_NO_WARMUP");
+    return !(e && *e == '1');
+}
+// one tiny multiply per kernel module on device d (see spmm_devices_init)
+void warm_up_modules(int d)
+{
+    const int rp[3] = {0, 1, 2}, ci[2] = {0, 1};
+    const double v[2] = {1.0, 1.0};
+    spmm_csr_t A = nullptr;
+    double *buf = nullptr;
+    if (cudaSetDevice(d) != cudaSuccess || spmm_csr_create_host(d, 2, 2, 2, rp, ci, v, &A) != SPMM_OK)
+        return;
+    if (cudaMalloc((void **)&buf, sizeof(double) * 16) == cudaSuccess && cudaMemset(buf, 0, sizeof(double) * 16) == cudaSuccess)
+    {
+        int lo = 0, hi = 0;
+        spmm_multiply_device(A, buf, 2, buf + 8, SPMM_KERNEL_ROWS, nullptr);  // even k: 16-byte accesses
+        spmm_multiply_device(A, buf, 1, buf + 8, SPMM_KERNEL_ROWS, nullptr);  // odd k: 8-byte accesses
+        spmm_multiply_device(A, buf, 2, buf + 8, SPMM_KERNEL_MERGE, nullptr);
+        spmm_csr_column_span(A, &lo, &hi);                                     // the CSR build / shard unit
+        cudaDeviceSynchronize();
+    }
+    cudaFree(buf);
+    spmm_csr_destroy(A);
+    cudaGetLastError();
+}
+} // namespace
+
 int spmm_devices_init(int enable_peers)
 {
     int count = 0;
@@ -906,34 +937,31 @@ int spmm_devices_init(int enable_peers)
     // merge kernels (measured: tools/first_launch_probe.py, first multiply of a process 38.1 ms, with any earlier launch from
     // the same unit 0.2 ms). A caller that times each function once (the reference's main.cpp:77-79) would pay that inside
     // its first call on every GPU; one tiny multiply per device and module here pays it at program start instead.
-    if (!(getenv("SPMM_NO_WARMUP") && *getenv("SPMM_NO_WARMUP") == '1'))
+    if (warmup_wanted())
     {
         std::vector<std::thread> th;
         for (int d = 0; d < count; ++d)
-            th.emplace_back([d] {
-                const int rp[3] = {0, 1, 2}, ci[2] = {0, 1};
-                const double v[2] = {1.0, 1.0};
-                spmm_csr_t A = nullptr;
-                double *buf = nullptr;
-                if (cudaSetDevice(d) != cudaSuccess || spmm_csr_create_host(d, 2, 2, 2, rp, ci, v, &A) != SPMM_OK)
-                    return;
-                if (cudaMalloc((void **)&buf, sizeof(double) * 16) == cudaSuccess && cudaMemset(buf, 0, sizeof(double) * 16) == cudaSuccess)
-                {
-                    int lo = 0, hi = 0;
-                    spmm_multiply_device(A, buf, 2, buf + 8, SPMM_KERNEL_ROWS, nullptr);  // even k: 16-byte accesses
-                    spmm_multiply_device(A, buf, 1, buf + 8, SPMM_KERNEL_ROWS, nullptr);  // odd k: 8-byte accesses
-                    spmm_multiply_device(A, buf, 2, buf + 8, SPMM_KERNEL_MERGE, nullptr);
-                    spmm_csr_column_span(A, &lo, &hi);                                     // the CSR build / shard unit
-                    cudaDeviceSynchronize();
-                }
-                cudaFree(buf);
-                spmm_csr_destroy(A);
-                cudaGetLastError();
-            });
+            th.emplace_back([d] { warm_up_modules(d); });
         for (auto &t : th)
             t.join();
         SPMM_CUDA(cudaSetDevice(0));
     }
+    return SPMM_OK;
+}
+
+int spmm_device_init(int device)
+{
+    int count = 0;
+    SPMM_CUDA(cudaGetDeviceCount(&count));
+    SPMM_REQUIRE(device >= 0 && device < count, "no such device");
+    SPMM_CUDA(cudaSetDevice(device));
+    SPMM_CUDA(cudaFree(nullptr)); // creates the primary context
+    const int rc = arena_init();
+    if (rc)
+        return rc;
+    pool();
+    if (warmup_wanted())
+        warm_up_modules(device);
     return SPMM_OK;
 }
 
