@@ -775,3 +775,16 @@ def test_reduce_blocks_rank_order():
     assert torch.equal(out, want)
     with pytest.raises(_cabi.SpmmError):
         _cabi.reduce_blocks(0, [t.data_ptr() for t in srcs], 7, out.data_ptr())  # odd element count
+
+
+def test_device_init_one_gpu(oracle):
+    """spmm_device_init: the start-up work of a process that was given ONE GPU (context, staging arena, one tiny multiply per
+    kernel module) — idempotent, refuses a device that does not exist, and leaves the library usable."""
+    lib = _cabi.lib()
+    assert lib.spmm_device_init(0) == 0
+    assert lib.spmm_device_init(0) == 0
+    assert lib.spmm_device_init(4096) != 0 and b"no such device" in lib.spmm_last_error()
+    rp, ci, va = random_csr(51, 300, 300, 7, long_row=150, empty_every=11, positive=True)
+    B = np.random.default_rng(2).integers(1, 101, (300, 6)).astype(np.float64)
+    got = spmm.sparseMatrixFatVectorMultiply(spmm.SparseMatrix(va, ci, rp, 300, 300), B, 6)
+    assert_close_rel(got, oracle.spmm(rp, ci, va, B, 6), tol=REL_TOL)
