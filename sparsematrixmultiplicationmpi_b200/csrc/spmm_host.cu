@@ -896,6 +896,8 @@ void warm_up_modules(int d)
         spmm_multiply_device(A, buf, 1, buf + 8, SPMM_KERNEL_ROWS, nullptr);  // odd k: 8-byte accesses
         spmm_multiply_device(A, buf, 2, buf + 8, SPMM_KERNEL_MERGE, nullptr);
         spmm_csr_column_span(A, &lo, &hi);                                     // the CSR build / shard unit
+        spmm_csr_build_tiles(A, 8, 0);                                         // the tile-layout / tiled-kernel unit
+        spmm_multiply_device(A, buf, 2, buf + 8, SPMM_KERNEL_AUTO, nullptr);
         cudaDeviceSynchronize();
     }
     cudaFree(buf);

@@ -72,7 +72,8 @@ struct Tuning
     int tiled_npw = 0;      // launch: producer warps (4, 8)
     int host_slabs = 0;     // host-buffer multiply: k-slabs in the PCIe pipeline (0 auto, 1 none)
     int tiled_auto_after = 8; // AUTO builds the tile layout on the multiply after this many whole-matrix multiplies of a handle
-                              // (the build costs ~70 ms of wall clock on cfg2 — device passes plus the host-side search — and saves ~50 us per multiply)
+                              // (the build costs 4-7 ms of wall clock on cfg2 at k = 16 and 14-25 ms at k = 64 — five device passes of 1.9 ms
+                              // plus allocations, tools/build_tiles_probe.py — and saves ~50 us per multiply)
     int tiled_pdl = 1;      // launch: programmatic dependent launch of the tiled kernel (0 off)
     int tiled_group = 0;    // build: tiles one far-band apart walked in turn, this many bands per group (0 auto = 2, 1 off)
     int tiled_stride = 0;   // build: far-band distance in rows (0 = detect from the matrix)

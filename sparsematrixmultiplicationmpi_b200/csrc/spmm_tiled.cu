@@ -1297,39 +1297,64 @@ int build_tiles_once(spmm_csr_s *A, const BuildParams &p, bool dry, BuildResult 
 
 namespace
 {
+// Histogram of the distances col - row >= NEAR over every `step`-th row, in bins of `bin` rows (counts and sums).
+__global__ void far_band_hist_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx, int n_rows, int step,
+                                     int near, int bin, unsigned long long *__restrict__ cnt, unsigned long long *__restrict__ sum)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long r = i * step;
+    if (r >= n_rows)
+        return;
+    for (int j = rowptr[r]; j < rowptr[r + 1]; ++j)
+    {
+        const int d = colidx[j] - (int)r;
+        if (d >= near)
+        {
+            atomicAdd(cnt + d / bin, 1ull);
+            atomicAdd(sum + d / bin, (unsigned long long)d);
+        }
+    }
+}
+
 // Distance (in rows) of the matrix's dominant far band: FEM-like matrices on a 3-D grid couple row r with rows r +- P
-// (the next grid plane). 0 when no band far from the diagonal holds a sizeable share of the non-zeros.
+// (the next grid plane). 0 when no band far from the diagonal holds a sizeable share of the non-zeros. Found on the device
+// from a sample of the rows (every 8th: a band that matters shows in any sample); only the histogram comes back.
 int detect_far_band(const spmm_csr_s *A, int *stride_rows)
 {
     *stride_rows = 0;
-    if (A->n_rows < 4096 || A->nnz == 0 || A->nnz > (32ll << 20)) // (the scan below runs on the host: keep it to mid-sized matrices)
+    if (A->n_rows < 4096 || A->nnz == 0)
         return SPMM_OK;
-    std::vector<int> rp((size_t)A->n_rows + 1), ci((size_t)A->nnz);
-    SPMM_CUDA(cudaMemcpy(rp.data(), A->d_rowptr, sizeof(int) * rp.size(), cudaMemcpyDeviceToHost));
-    SPMM_CUDA(cudaMemcpy(ci.data(), A->d_colidx, sizeof(int) * ci.size(), cudaMemcpyDeviceToHost));
-    constexpr int BIN = 64, NEAR = 256;
-    std::vector<long long> cnt((size_t)A->n_cols / BIN + 2, 0), sum((size_t)A->n_cols / BIN + 2, 0);
-    for (int r = 0; r < A->n_rows; ++r)
-        for (int j = rp[r]; j < rp[r + 1]; ++j)
-        {
-            const int d = ci[j] - r;
-            if (d >= NEAR)
-            {
-                ++cnt[d / BIN];
-                sum[d / BIN] += d;
-            }
-        }
+    constexpr int NEAR = 256, STEP = 8;
+    const int bin = std::max(64, A->n_cols / 32768);
+    const size_t n_bins = (size_t)A->n_cols / bin + 2;
+    unsigned long long *d_hist = nullptr;
+    SPMM_CUDA(cudaMalloc(&d_hist, sizeof(unsigned long long) * 2 * n_bins));
+    std::vector<unsigned long long> h(2 * n_bins);
+    cudaError_t e = cudaMemset(d_hist, 0, sizeof(unsigned long long) * 2 * n_bins);
+    if (e == cudaSuccess)
+    {
+        const long long sampled = ((long long)A->n_rows + STEP - 1) / STEP;
+        far_band_hist_kernel<<<(unsigned)((sampled + 255) / 256), 256>>>(A->d_rowptr, A->d_colidx, A->n_rows, STEP, NEAR, bin,
+                                                                          d_hist, d_hist + n_bins);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpy(h.data(), d_hist, sizeof(unsigned long long) * 2 * n_bins, cudaMemcpyDeviceToHost);
+    cudaFree(d_hist);
+    SPMM_CUDA(e);
+    const unsigned long long *cnt = h.data(), *sum = h.data() + n_bins;
     size_t m = 0;
-    for (size_t i = 1; i < cnt.size(); ++i)
+    for (size_t i = 1; i < n_bins; ++i)
         if (cnt[i] > cnt[m])
             m = i;
-    long long c = 0, sm = 0;
-    for (size_t i = m >= 2 ? m - 2 : 0; i <= m + 2 && i < cnt.size(); ++i)
+    unsigned long long c = 0, sm = 0;
+    for (size_t i = m >= 2 ? m - 2 : 0; i <= m + 2 && i < n_bins; ++i)
     {
         c += cnt[i];
         sm += sum[i];
     }
-    if (c * 12 >= A->nnz && c > 0) // the band holds at least 1/12 of all non-zeros (a third of the upper triangle of a 27-point stencil)
+    // the band holds at least 1/12 of all non-zeros (a third of the upper triangle of a 27-point stencil); c counts a sample
+    if (c > 0 && (long long)c * STEP * 12 >= A->nnz)
         *stride_rows = (int)(sm / c);
     return SPMM_OK;
 }
