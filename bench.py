@@ -171,6 +171,12 @@ def cpu_reference_run(host, B, k, steps, warmup, max_seconds=60.0):
                 break
         best[(strategy, P)] = statistics.mean(times)
     (strategy, P), t = min(best.items(), key=lambda kv: kv[1])
+    # one call of the row-wise function on ONE rank: its flatten / Gatherv / re-nest (RowWise.cpp:63-121) is serial work on the
+    # root whatever carries the ranks — the reason its all-cores time does not beat the sequential function at -O3
+    one_rank = None
+    if kind == "reference" and cores > 1 and time.perf_counter() - t_begin < max_seconds:
+        run("row", 1)
+        one_rank = run("row", 1)
     flops = 2.0 * host.nnz * k
     blocks = max(1, host.numRows // N_ROWS)
     return {"value": flops / t / 1e9, "unit": "GFLOP/s", "cores": P, "kind": kind,
@@ -179,6 +185,7 @@ def cpu_reference_run(host, B, k, steps, warmup, max_seconds=60.0):
             "seconds_per_step": t,
             "sequential_gflops": flops / best[("seq", 1)] / 1e9 if ("seq", 1) in best else None,
             "rowwise_all_cores_gflops": flops / best[("row", cores)] / 1e9 if ("row", cores) in best else None,
+            "rowwise_one_rank_seconds": one_rank,
             "host_cores": os.cpu_count()}
 
 
